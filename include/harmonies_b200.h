@@ -1,0 +1,264 @@
+/*
+ * harmonies_b200.h — C ABI of the B200-native batched Harmonies engine + MCTS core.
+ *
+ * This is the drop-in boundary for the hot path of IllyaArtemchuk/Harmonies-Alphazero
+ * (reference files cited as file:line, relative to the reference root).  The reference
+ * has no FFI: its boundary is the Python object API of `harmonies_engine.py`,
+ * `process_game_state.py` and `MCTS.py`.  Each entry point below names the reference
+ * function it replaces; `INTEGRATION.md` shows the ctypes stub a maintainer adds.
+ *
+ * Conventions
+ *  - every function is `extern "C"`, returns an `int` status (HZ_OK == 0, negative = error),
+ *    never throws, never synchronises the device unless stated;
+ *  - all data pointers are DEVICE pointers owned by the caller unless the name ends in
+ *    `_host`; `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *  - work is stream-ordered; one host thread per handle.
+ *
+ * ---------------------------------------------------------------------------------------
+ * Packed game state: 128 bytes = 32 little-endian uint32 words, array-of-records.
+ * (reference state fields: harmonies_engine.py:70-78)
+ *
+ *  hex index i (0..22)  = position of (q,r) in sorted(VALID_HEXES)   (constants.py:47-49)
+ *  tile type t (0..5)   = index in TILE_TYPES: water,plant,wood,stone,building,field
+ *                                                                     (constants.py:1)
+ *  tile code            = t+1 (1..6), 0 = no tile at that level
+ *
+ *  w[ 0.. 8]  board of player 0 as 9 bit-planes: w[level*3 + b] has bit i set iff bit b of
+ *             the tile code at stack level `level` (0 = bottom) of hex i is set
+ *  w[ 9..17]  board of player 1, same layout
+ *  w[18]      pile 0 (bits 0-15) | pile 1 (bits 16-31)
+ *  w[19]      pile 2 | pile 3
+ *  w[20]      pile 4 | hand (bits 16-31)
+ *             a pile / the hand is a multiset of <=3 tiles: 6 x 2-bit counts, type t at
+ *             bits 2t..2t+1 (the reference compares piles and hands as sorted tuples,
+ *             harmonies_engine.py:98-100, so the multiset is the canonical form)
+ *  w[21]      bag counts: water | plant<<8 | wood<<16 | stone<<24
+ *  w[22]      bag building | bag field<<8 | n_piles<<16 | meta<<24
+ *             meta: bit0 current_player; bits1-3 phase (0 choose_pile, 1..3 place_tile_k,
+ *             4 game_over); bit4 the `game_over` attribute ("ending" flag,
+ *             harmonies_engine.py:312-315); bits5-6 winner (0 None, 1 player 0,
+ *             2 player 1, 3 tie == reference winner -1)
+ *  w[23]      final_scores[0] (int16, bits 0-15) | final_scores[1] (bits 16-31)
+ *  w[24..25]  rng key (uint64, lo/hi) of this game's draw stream
+ *  w[26]      draw-event counter of the stream (one event per call that replenishes piles)
+ *  w[27]      number of actions applied so far (game_move_count, trainer.py:466,509)
+ *  w[28..31]  reserved, zero
+ *
+ *  Canonical identity (get_canonical_tuple, harmonies_engine.py:81-110) = words 0..22 with
+ *  the ending flag and winner bits masked out (meta & 0x0F).
+ *
+ * Actions are the reference's flat action indices (process_game_state.py:156-177):
+ *  a < 5: take pile a;  a >= 5: t=(a-5)/23, hex=(a-5)%23.   143 actions.
+ *
+ * Deterministic draw source (replaces the global `random` of harmonies_engine.py:126):
+ *  mix(z): z=(z^(z>>30))*0xBF58476D1CE4E5B9; z=(z^(z>>27))*0x94D049BB133111EB; z^=z>>31
+ *  rand(key,ctr) = mix(key ^ mix(ctr + 0x9E3779B97F4A7C15))
+ *  pile k (k-th pile drawn inside one replenish) of draw event e of stream `key` uses
+ *  z = rand(key, e*8 + k); tile j (j<min(3,total)) : x=(z>>(21*j))&0x1FFFFF;
+ *  r=(x*total)>>21; the tile is the type whose cumulative bag count (TILE_TYPES order)
+ *  first exceeds r; counts are decremented between tiles (sampling without replacement
+ *  from the multiset, as random.sample over the flattened bag does).
+ */
+#ifndef HARMONIES_B200_H
+#define HARMONIES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HZ_ABI_VERSION      1
+#define HZ_STATE_WORDS      32
+#define HZ_STATE_BYTES      128
+#define HZ_NUM_HEXES        23
+#define HZ_NUM_TYPES        6
+#define HZ_NUM_PILES        5
+#define HZ_ACTION_SIZE      143
+#define HZ_MASK_WORDS       5
+#define HZ_BOARD_CHANNELS   38
+#define HZ_BOARD_H          5
+#define HZ_BOARD_W          7
+#define HZ_GLOBAL_FEATURES  42
+#define HZ_CANON_WORDS      23
+
+/* word indices of the packed state */
+#define HZ_W_BOARD0   0
+#define HZ_W_BOARD1   9
+#define HZ_W_PILES01  18
+#define HZ_W_PILES23  19
+#define HZ_W_PILE4H   20
+#define HZ_W_BAG0     21
+#define HZ_W_BAG1META 22
+#define HZ_W_SCORES   23
+#define HZ_W_KEYLO    24
+#define HZ_W_KEYHI    25
+#define HZ_W_EVENT    26
+#define HZ_W_MOVES    27
+
+/* phases */
+#define HZ_PHASE_CHOOSE 0
+#define HZ_PHASE_PLACE1 1
+#define HZ_PHASE_PLACE2 2
+#define HZ_PHASE_PLACE3 3
+#define HZ_PHASE_OVER   4
+
+/* call status */
+#define HZ_OK               0
+#define HZ_ERR_ARG         -1   /* null pointer / bad size */
+#define HZ_ERR_CUDA        -2   /* a CUDA runtime call failed; see hz_last_cuda_error() */
+#define HZ_ERR_NO_DEVICE   -3
+#define HZ_ERR_WORKSPACE   -4   /* workspace too small / misaligned */
+
+/* per-game status bytes written by hz_apply; each mirrors one ValueError site of
+ * HarmoniesGameState.apply_move.  A game with status != 0 is left untouched. */
+#define HZ_MOVE_OK            0
+#define HZ_MOVE_BAD_PILE      1  /* harmonies_engine.py:220 */
+#define HZ_MOVE_BAD_FORMAT    2  /* :234  (pile index given in a placement phase) */
+#define HZ_MOVE_BAD_COORD     3  /* :242  (action index outside 0..142) */
+#define HZ_MOVE_NOT_IN_HAND   4  /* :246 */
+#define HZ_MOVE_ILLEGAL_STACK 5  /* :281 */
+#define HZ_MOVE_BAD_PHASE     6  /* :296 */
+#define HZ_MOVE_BAD_DRAW      7  /* explicit replay draw not available in the bag */
+
+/* encode dtypes / layouts */
+#define HZ_DTYPE_F32  0
+#define HZ_DTYPE_BF16 1
+#define HZ_LAYOUT_NCHW 0
+#define HZ_LAYOUT_NHWC 1
+
+/* node-key modes (hz_canon_hash, hz_tree_create):
+ *  HZ_KEY_EXACT     identity = equality of get_canonical_tuple (harmonies_engine.py:81-118)
+ *  HZ_KEY_REFERENCE identity = equality of Python's hash() of that tuple, which is what
+ *                   MCTS.py keys nodes by (MCTS.py:14,177,185).  CPython has
+ *                   hash(-1) == hash(-2), so board items at aliased coordinates
+ *                   (q or r equal to -1 vs -2) are indistinguishable to the reference's tree;
+ *                   this mode reproduces that relation exactly (needed for identical visit
+ *                   counts).  Alias pairs of hex indices: {1,6},{2,7},{3,8},{4,5},{9,10},
+ *                   {14,15},{19,20}; the key is the state with every board replaced by the
+ *                   leftmost embedding of its sorted (alias class, stack) sequence. */
+#define HZ_KEY_EXACT     0
+#define HZ_KEY_REFERENCE 1
+
+/* "no draw given" marker for hz_apply draws */
+#define HZ_NO_DRAW 0xFFFFu
+
+int         hz_abi_version(void);
+const char *hz_status_string(int status);
+const char *hz_last_cuda_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t    hz_launch_count(void);
+
+/* ---- engine (harmonies_engine.py) ------------------------------------------------ */
+
+/* New games: HarmoniesGameState.__init__ (harmonies_engine.py:66-79) incl. the initial
+ * _replenish_piles (:132-137) as draw event 0.  keys==NULL -> key_i = rand(seed, first_id+i). */
+int hz_init_states(void *states, int64_t n, const uint64_t *keys, uint64_t seed,
+                   uint64_t first_id, void *stream);
+
+/* get_legal_moves (harmonies_engine.py:145-208) as a 143-bit mask per game, bit a of
+ * mask[g*5 + a/32] set iff action a is legal.  Ascending bit order is the canonical
+ * move order of this library. */
+int hz_legal_mask(const void *states, int64_t n, uint32_t *mask, void *stream);
+
+/* apply_move + _end_turn_actions + _replenish_piles + _draw_tiles + final scoring
+ * (harmonies_engine.py:210-329,120-137,344-354), in place.  draws may be NULL; else
+ * draws[g] != HZ_NO_DRAW is the pile (packed counts) to use for the first pile drawn by
+ * this call instead of the state's rng stream (trace replay).  status may be NULL. */
+int hz_apply(void *states, int64_t n, const int16_t *actions, const uint16_t *draws,
+             uint8_t *status, void *stream);
+
+/* calculate_score_for_player for both players (harmonies_engine.py:357-523):
+ * scores[g*2+p].  terms (nullable): [g][p][5] = grass, mountains, fields, buildings, water. */
+int hz_score(const void *states, int64_t n, int16_t *scores, int16_t *terms, void *stream);
+
+/* create_state_tensors (process_game_state.py:15-137): board [n,38,5,7] (NCHW) or
+ * [n,5,7,38] (NHWC) and glob [n,42], fp32 (bit-exact) or bf16 (RNE of the fp32 value). */
+int hz_encode(const void *states, int64_t n, void *board, void *glob, int dtype, int layout,
+              void *stream);
+
+/* 64-bit key of get_canonical_tuple / __hash__ (harmonies_engine.py:81-113). */
+int hz_canon_hash(const void *states, int64_t n, int key_mode, uint64_t *hashes, void *stream);
+
+/* is_game_over / get_game_outcome (harmonies_engine.py:332-342): over[g] in {0,1},
+ * outcome[g] in {+1,-1,0} from player 0's view (0 also when not over). Either may be NULL. */
+int hz_outcome(const void *states, int64_t n, uint8_t *over, int8_t *outcome, void *stream);
+
+/* The uniform-random playout policy of BASELINE.json configs[0..1]
+ * (`random.choice(get_legal_moves())`): action = k-th legal action in ascending order,
+ * k = ((rand(key ^ HZ_PLAYOUT_SALT, moves) >> 32) * n_legal) >> 32.  -1 if none. */
+int hz_random_actions(const void *states, int64_t n, int16_t *actions, void *stream);
+
+/* Fused playout: repeat {legal -> random action -> apply} on-chip until the game is over
+ * or max_steps actions were applied.  steps (nullable): actions applied per game.
+ * total_steps (nullable): device uint64 to which the launch adds its step total. */
+int hz_playout(void *states, int64_t n, int max_steps, uint32_t *steps,
+               unsigned long long *total_steps, void *stream);
+
+/* ---- search tree (MCTS.py) ---------------------------------------------------------- */
+
+typedef struct hz_tree hz_tree;   /* opaque: n_trees independent DAGs in flat arrays */
+
+/* Bytes of device workspace for n_trees searches of at most max_sims simulations.
+ * max_nodes == 0 selects the worst case (1 + 69*max_sims nodes per tree). */
+size_t hz_tree_workspace_bytes(int n_trees, int max_sims, int max_nodes);
+
+/* Node/MCTS construction (MCTS.py:8-61) over caller-owned, 256-byte-aligned workspace. */
+int hz_tree_create(hz_tree **out, void *workspace, size_t workspace_bytes, int n_trees,
+                   int max_sims, int max_nodes, int key_mode);
+int hz_tree_destroy(hz_tree *t);
+
+/* Start a new search per tree (get_best_action_and_pi, MCTS.py:288-289: no tree reuse).
+ * root_states: [n_trees] packed states; search_keys: [n_trees] uint64, the key of the
+ * in-tree draw stream: child of action a expanded in simulation s (0-based) draws event
+ * (s<<8)|a. */
+int hz_tree_reset(hz_tree *t, const void *root_states, const uint64_t *search_keys,
+                  void *stream);
+
+/* move_to_leaf (MCTS.py:63-149) for every tree, then create_state_tensors of the leaf
+ * (MCTS.py:299) into board/glob (see hz_encode).  cpuct is applied as fp32(cpuct)*P in fp32
+ * then promoted to fp64, the reference's numpy>=2 arithmetic (MCTS.py:107-112).
+ * leaf_states (nullable): [n_trees] packed leaf states. */
+int hz_tree_select(hz_tree *t, float cpuct, void *leaf_states, void *board, void *glob,
+                   int dtype, int layout, void *stream);
+
+/* expand_leaf + terminal value + back_fill (MCTS.py:151-264,297-352).  policy: [n,143]
+ * softmax probabilities (or logits when is_logits != 0; softmax is then fused), value: [n].
+ * noise (nullable): [n,143] unnormalised gamma samples indexed by action; at the root
+ * expansion they are normalised over the legal moves and mixed with weight eps
+ * (MCTS.py:308-326).  Advances each tree's simulation counter. */
+int hz_tree_expand_backup(hz_tree *t, const float *policy, const float *value,
+                          int is_logits, const float *noise, double eps, void *stream);
+
+/* Synthetic evaluator for tests/benches: exact dyadic priors/values from the leaf's
+ * canonical hash: P[a] = (mix(h ^ (a+1)) >> 40) * 2^-24, v = (mix(h ^ 0x5EED) >> 40) *
+ * 2^-23 - 1.  Stands in for ModelManager.predict (model.py:81-110). */
+int hz_tree_fake_eval(hz_tree *t, float *policy, float *value, void *stream);
+
+/* Root visit counts and pi = N / sum N (MCTS.py:355-381): visits [n,143] int32,
+ * pi [n,143] fp32 (either nullable). */
+int hz_tree_root_policy(hz_tree *t, int32_t *visits, float *pi, void *stream);
+
+/* Move choice (MCTS.py:394-441): u01 == NULL or exploratory[g]==0 -> first max-N edge in
+ * ascending action order; else the edge where the running sum of N first exceeds
+ * u01[g]*sum N.  action -1 = no edge (search failure, MCTS.py:439). */
+int hz_tree_choose(hz_tree *t, const float *u01, const uint8_t *exploratory,
+                   int16_t *actions, void *stream);
+
+/* Per-tree counters: n_nodes, n_edges (int32 each, nullable) and status bytes (nullable):
+ * 0 ok, 1 node arena overflow, 2 edge arena overflow, 4 path overflow. */
+int hz_tree_stats(hz_tree *t, int32_t *n_nodes, int32_t *n_edges, uint8_t *status,
+                  void *stream);
+
+/* Root edge statistics for parity checks: N int32, W fp64, P fp32, child node id int32,
+ * all [n,143] indexed by action (absent edges: N=0,W=0,P=0,child=-1). Any may be NULL. */
+int hz_tree_root_edges(hz_tree *t, int32_t *N, double *W, float *P, int32_t *child,
+                       void *stream);
+
+#define HZ_PLAYOUT_SALT 0xA5A5F00DC0FFEE11ull
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HARMONIES_B200_H */

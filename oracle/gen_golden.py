@@ -1,0 +1,380 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_harness.py).  Run here (the dev container);
+the fixtures are committed because the reference cannot travel to the GPU box.
+
+    python oracle/gen_golden.py            # writes tests/golden/{engine,scoring,encode,equiv,mcts}.npz
+
+Every array is produced by reference code (harmonies_engine.py, process_game_state.py,
+MCTS.py); this script only chooses inputs, injects the deterministic draw source and
+serialises states with harmonies_alphazero_b200.packed (format conversion, no game logic).
+"""
+
+import os
+import random
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+import ref_harness as rh  # noqa: E402
+from harmonies_alphazero_b200 import packed as pk  # noqa: E402
+from harmonies_alphazero_b200.constants import TILE_TYPES, sorted_coords  # noqa: E402
+
+OUT = os.environ.get("HZ_GOLDEN_OUT", os.path.join(os.path.dirname(HERE), "tests", "golden"))
+
+
+def legal_mask(state, gai):
+    return pk.actions_to_mask([gai(m) for m in state.get_legal_moves()])
+
+
+def playout_pick(key, moves, n_legal):
+    return ((pk.rand(key ^ pk.PLAYOUT_SALT, moves) >> 32) * n_legal) >> 32
+
+
+# --------------------------------------------------------------------------------------
+def gen_engine(n_python=24, n_stream=40):
+    ref = rh.load_reference()
+    gai = ref["pgs"].get_action_index
+    before, after, legal, action, draw, game_of = [], [], [], [], [], []
+    starts, finals, winners, keys, lengths = [0], [], [], [], []
+    g = 0
+    for mode in ["python"] * n_python + ["stream"] * n_stream:
+        if mode == "python":
+            key = 0
+            state = rh.new_game_python(seed=g)
+            picker = random.Random(10_000 + g)
+        else:
+            key = pk.rand(0xB200, g)
+            state = rh.new_game_stream(key)
+        moves = 0
+        while not state.is_game_over():
+            lm = state.get_legal_moves()
+            assert lm, "reference produced a stuck state"
+            if mode == "python":
+                mv = lm[picker.randrange(len(lm))]
+                ev = 0
+            else:
+                mv = lm[playout_pick(key, moves, len(lm))]
+                ev = rh.ctx.event
+            before.append(pk.pack_state(state, rng_key=key, rng_event=ev, moves=moves))
+            legal.append(legal_mask(state, gai))
+            action.append(gai(mv))
+            rh.ctx.recorded = []
+            state = state.apply_move(mv)
+            rec, rh.ctx.recorded = rh.ctx.recorded, None
+            assert len(rec) <= 1
+            draw.append(rec[0] if rec else pk.NO_DRAW)
+            moves += 1
+            ev = rh.ctx.event if mode == "stream" else 0
+            after.append(pk.pack_state(state, rng_key=key, rng_event=ev, moves=moves))
+            game_of.append(g)
+        starts.append(len(action))
+        finals.append(list(state.final_scores))
+        winners.append(state.winner)
+        keys.append(key)
+        lengths.append(moves)
+        g += 1
+    np.savez_compressed(
+        os.path.join(OUT, "engine.npz"),
+        before=np.array(before, dtype=np.uint32),
+        after=np.array(after, dtype=np.uint32),
+        legal=np.array(legal, dtype=np.uint32),
+        action=np.array(action, dtype=np.int16),
+        draw=np.array(draw, dtype=np.uint16),
+        game_of=np.array(game_of, dtype=np.int32),
+        starts=np.array(starts, dtype=np.int64),
+        final_scores=np.array(finals, dtype=np.int16),
+        winner=np.array(winners, dtype=np.int8),
+        keys=np.array(keys, dtype=np.uint64),
+        lengths=np.array(lengths, dtype=np.int32),
+        n_python=np.int32(n_python),
+    )
+    print(f"engine: {g} games, {len(action)} steps, lengths {min(lengths)}..{max(lengths)}")
+    return np.array(before, dtype=np.uint32), np.array(after, dtype=np.uint32)
+
+
+# --------------------------------------------------------------------------------------
+def synth_state(G, rng, kind):
+    """Synthetic positions (BASELINE.json configs[2]): full boards with stacks of height
+    ~{1,1,2,3} and uniform types (incl. unreachable stacks); 'sparse' leaves holes and
+    'watery'/'fieldy'/'stony' skew the type distribution to grow large components."""
+    weights = {
+        "full": [1, 1, 1, 1, 1, 1],
+        "sparse": [1, 1, 1, 1, 1, 1],
+        "watery": [6, 1, 1, 1, 1, 1],
+        "fieldy": [1, 1, 1, 1, 1, 6],
+        "stony": [1, 1, 1, 6, 3, 1],
+    }[kind]
+    boards = []
+    for p in (0, 1):
+        b = {}
+        occ = 1.0 if kind == "full" else rng.choice([0.35, 0.6, 0.85, 1.0])
+        for c in sorted_coords:
+            if rng.random() > occ:
+                continue
+            h = rng.choice([1, 1, 2, 3])
+            b[c] = [rng.choices(TILE_TYPES, weights)[0] for _ in range(h)]
+        boards.append(b)
+    hand = [rng.choice(TILE_TYPES) for _ in range(3)]
+    piles = [[rng.choice(TILE_TYPES) for _ in range(3)] for _ in range(rng.choice([4, 4, 3, 0]))]
+    bag = {t: rng.randrange(0, 20) for t in ["water", "plant", "wood", "stone", "field", "building"]}
+    return G(
+        initial_state={
+            "player_boards": boards,
+            "tile_bag": bag,
+            "available_piles": piles,
+            "current_player": rng.randrange(2),
+            "tiles_in_hand": hand,
+            "turn_phase": rng.choice(["place_tile_1", "place_tile_2", "place_tile_3"]),
+            "game_over": False,
+            "winner": None,
+            "final_scores": [0, 0],
+        }
+    )
+
+
+def gen_scoring(n=6000):
+    ref = rh.load_reference()
+    G, gai = ref["G"], ref["pgs"].get_action_index
+    rng = random.Random(20240)
+    kinds = ["full"] * 3 + ["sparse", "watery", "fieldy", "stony"]
+    states, terms, totals, legal = [], [], [], []
+    for i in range(n):
+        s = synth_state(G, rng, kinds[i % len(kinds)])
+        if i % 3 == 0:  # hands with repeated / single types exercise the distinct-type rule
+            s.tiles_in_hand = s.tiles_in_hand[: rng.choice([1, 2, 3])]
+        states.append(pk.pack_state(s))
+        tt = []
+        for p in (0, 1):
+            b = s.player_boards[p]
+            tt.append(
+                [
+                    s._score_grass(b, p),
+                    s._score_mountains(b, p),
+                    s._score_fields(b, p),
+                    s._score_buildings(b, p),
+                    s._score_water(b, p),
+                ]
+            )
+        terms.append(tt)
+        totals.append([s.calculate_score_for_player(0), s.calculate_score_for_player(1)])
+        legal.append(legal_mask(s, gai))
+    np.savez_compressed(
+        os.path.join(OUT, "scoring.npz"),
+        states=np.array(states, dtype=np.uint32),
+        terms=np.array(terms, dtype=np.int16),
+        totals=np.array(totals, dtype=np.int16),
+        legal=np.array(legal, dtype=np.uint32),
+    )
+    t = np.array(terms)
+    print(f"scoring: {n} positions, max terms {t.max(axis=(0, 1))}, max total {np.max(totals)}")
+    return np.array(states, dtype=np.uint32)
+
+
+# --------------------------------------------------------------------------------------
+def gen_encode(trace_states, synth_states, n_trace=400, n_synth=100):
+    ref = rh.load_reference()
+    G, cst = ref["G"], ref["pgs"].create_state_tensors
+    rng = np.random.default_rng(7)
+    pick = list(rng.choice(len(trace_states), n_trace, replace=False))
+    # make sure terminal states (phase game_over) are in
+    term = [i for i in range(len(trace_states)) if ((trace_states[i][22] >> 25) & 7) == 4][:24]
+    sel = [trace_states[i] for i in pick + term] + list(
+        synth_states[rng.choice(len(synth_states), n_synth, replace=False)]
+    )
+    boards, globs = [], []
+    for w in sel:
+        f = pk.unpack_fields(w)
+        for k in ("rng_key", "rng_event", "moves"):
+            f.pop(k)
+        b, gl = cst(G(initial_state=f))
+        boards.append(b.numpy())
+        globs.append(gl.numpy())
+    np.savez_compressed(
+        os.path.join(OUT, "encode.npz"),
+        states=np.array(sel, dtype=np.uint32),
+        board=np.array(boards, dtype=np.float32),
+        glob=np.array(globs, dtype=np.float32),
+    )
+    print(f"encode: {len(sel)} states")
+
+
+# --------------------------------------------------------------------------------------
+def gen_equiv(n_roots=12, depth=3, cap=6000, n_sparse=3000):
+    """States with the reference's own equivalence classes, two ways:
+    cls  = classes of __eq__ (harmonies_engine.py:115-118), i.e. tuple equality;
+    hcls = classes of hash(state) (harmonies_engine.py:112-113) — what MCTS.py keys its node
+           dict by (MCTS.py:14,177,185).  They differ because hash(-1) == hash(-2)."""
+    ref = rh.load_reference()
+    G = ref["G"]
+    states, cls, hcls = [], [], []
+    seen, hseen = {}, {}
+    rng = random.Random(99)
+
+    def add(c):
+        states.append(pk.pack_state(c))
+        cls.append(seen.setdefault(c, len(seen)))
+        hcls.append(hseen.setdefault(hash(c), len(hseen)))
+
+    for r in range(n_roots):
+        key = pk.rand(0xE9, r)
+        s = rh.new_game_stream(key)
+        for _ in range(rng.choice([1, 5, 9, 21])):
+            lm = s.get_legal_moves()
+            s = s.apply_move(lm[rng.randrange(len(lm))])
+        rh.ctx.mode, rh.ctx.key, rh.ctx.sim = "tree", key ^ 0x77, 0
+        frontier = [s]
+        for d in range(depth):
+            nxt = []
+            for st in frontier:
+                lm = st.get_legal_moves()
+                rng.shuffle(lm)
+                for mv in lm[:12]:
+                    rh.ctx.sim = 0  # same (sim, action) -> same draw: transpositions survive
+                    c = st.apply_move(mv)
+                    add(c)
+                    nxt.append(c)
+            rng.shuffle(nxt)
+            frontier = nxt[:40]
+        if len(states) > cap:
+            break
+    # sparse boards drawn from a small pool of stacks, so that alias collisions
+    # (coordinates differing by -1 vs -2) and true duplicates are both frequent
+    stacks = [["water"], ["wood"], ["wood", "plant"], ["stone", "stone"], ["field"]]
+    for i in range(n_sparse):
+        boards = []
+        for p in (0, 1):
+            k = rng.choice([0, 1, 1, 2, 2, 3, 4, 6])
+            b = {c: list(rng.choice(stacks[: rng.choice([1, 2, 5])])) for c in rng.sample(sorted_coords, k)}
+            boards.append(b)
+        add(
+            G(
+                initial_state={
+                    "player_boards": boards,
+                    "tile_bag": {"water": 3, "plant": 3, "wood": 3, "stone": 3, "field": 3, "building": 3},
+                    "available_piles": [["water", "wood", "field"]],
+                    "current_player": i % 2,
+                    "tiles_in_hand": ["plant"],
+                    "turn_phase": "place_tile_3",
+                    "game_over": False,
+                    "winner": None,
+                    "final_scores": [0, 0],
+                }
+            )
+        )
+    np.savez_compressed(
+        os.path.join(OUT, "equiv.npz"),
+        states=np.array(states, dtype=np.uint32),
+        cls=np.array(cls, dtype=np.int32),
+        hcls=np.array(hcls, dtype=np.int32),
+    )
+    print(f"equiv: {len(states)} states, {len(seen)} __eq__ classes, {len(hseen)} hash() classes")
+
+
+# --------------------------------------------------------------------------------------
+def gen_mcts():
+    ref = rh.load_reference()
+    gai = ref["pgs"].get_action_index
+    rng = random.Random(4242)
+    nrng = np.random.default_rng(4242)
+    cases = []
+    # roots: positions along stream-mode playout games
+    for g in range(10):
+        key = pk.rand(0x3C75, g)
+        s = rh.new_game_stream(key)
+        traj = [(s, 0, rh.ctx.event)]
+        moves = 0
+        while not s.is_game_over():
+            lm = s.get_legal_moves()
+            s = s.apply_move(lm[playout_pick(key, moves, len(lm))])
+            moves += 1
+            traj.append((s, moves, rh.ctx.event))
+        L = moves
+        wanted = sorted({0, 1, 2, 3, 4, 9, 22, 38, L - 9, L - 6, L - 4, L - 3, L - 2, L - 1} & set(range(L)))
+        for m in rng.sample(wanted, 6 if g else len(wanted)):
+            cases.append((traj[m][0], key, m, traj[m][2]))
+        if g == 0:
+            cases.append((traj[L][0], key, L, traj[L][2]))  # terminal root
+    out = {k: [] for k in "root skey sims cpuct testing eps noise choice_u move_no tau0 N W P pi action n_nodes n_edges".split()}
+    t0 = time.time()
+    for i, (state, key, m, ev) in enumerate(cases):
+        sims = [16, 40, 100, 64, 200][i % 5] if i % 11 else 320
+        variant = i % 4
+        cfg = {
+            "num_simulations": sims,
+            "cpuct": [2, 1.0, 2, 1.25][variant],
+            "dirichlet_alpha": 0.4,
+            "dirichlet_epsilon": [0.25, 0.0, 0.25, 0.4][variant],
+            "fpu_value": 0.25,
+            "turns_until_tau0": [15, 0, 15, 200][variant],
+            "action_size": 143,
+            "testing": variant == 1,
+        }
+        noise = nrng.gamma(0.4, size=143).astype(np.float32) + np.float32(1e-6)
+        u = float(np.float32(nrng.random()))
+        skey = pk.rand(key ^ 0x5EA7C4, m)
+        use_noise = not cfg["testing"]
+        mv, pi, info = rh.run_search(
+            state, skey, cfg, m, noise=noise if use_noise else None, choice_u=u
+        )
+        out["root"].append(pk.pack_state(state, rng_key=key, rng_event=ev, moves=m))
+        out["skey"].append(skey)
+        out["sims"].append(sims)
+        out["cpuct"].append(float(cfg["cpuct"]))
+        out["testing"].append(int(cfg["testing"]))
+        out["eps"].append(cfg["dirichlet_epsilon"])
+        out["noise"].append(noise)
+        out["choice_u"].append(u)
+        out["move_no"].append(m)
+        out["tau0"].append(cfg["turns_until_tau0"])
+        out["N"].append(info["N"])
+        out["W"].append(info["W"])
+        out["P"].append(info["P"])
+        out["pi"].append(pi)
+        out["action"].append(-1 if mv is None else gai(mv))
+        out["n_nodes"].append(info["n_nodes"])
+        out["n_edges"].append(info["n_edges"])
+    dt = time.time() - t0
+    np.savez_compressed(
+        os.path.join(OUT, "mcts.npz"),
+        root=np.array(out["root"], dtype=np.uint32),
+        skey=np.array(out["skey"], dtype=np.uint64),
+        sims=np.array(out["sims"], dtype=np.int32),
+        cpuct=np.array(out["cpuct"], dtype=np.float64),
+        testing=np.array(out["testing"], dtype=np.uint8),
+        eps=np.array(out["eps"], dtype=np.float64),
+        noise=np.array(out["noise"], dtype=np.float32),
+        choice_u=np.array(out["choice_u"], dtype=np.float32),
+        move_no=np.array(out["move_no"], dtype=np.int32),
+        tau0=np.array(out["tau0"], dtype=np.int32),
+        N=np.array(out["N"], dtype=np.int32),
+        W=np.array(out["W"], dtype=np.float64),
+        P=np.array(out["P"], dtype=np.float32),
+        pi=np.array(out["pi"], dtype=np.float64),
+        action=np.array(out["action"], dtype=np.int16),
+        n_nodes=np.array(out["n_nodes"], dtype=np.int32),
+        n_edges=np.array(out["n_edges"], dtype=np.int32),
+    )
+    tot = int(np.sum(out["sims"]))
+    print(f"mcts: {len(cases)} searches, {tot} sims in {dt:.1f}s ({tot / dt:.0f} sims/s reference+fake eval)")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["engine", "scoring", "encode", "equiv", "mcts"]
+    tb = ta = ss = None
+    if "engine" in which or "encode" in which:
+        tb, ta = gen_engine()
+    if "scoring" in which or "encode" in which:
+        ss = gen_scoring()
+    if "encode" in which:
+        term = ta[((ta[:, 22] >> 25) & 7) == 4]
+        gen_encode(np.concatenate([tb, term]), ss)
+    if "equiv" in which:
+        gen_equiv()
+    if "mcts" in which:
+        gen_mcts()
