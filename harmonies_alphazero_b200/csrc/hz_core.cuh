@@ -1,0 +1,560 @@
+// hz_core.cuh — device-side Harmonies engine on the 128-byte packed state
+// (layout: include/harmonies_b200.h).  One thread owns one state in registers; every
+// function is branch-light bit-board arithmetic over 23-bit hex masks.
+//
+// Reference behaviour reproduced (file:line into the reference):
+//   legal moves      harmonies_engine.py:145-208
+//   apply_move       harmonies_engine.py:210-298
+//   end of turn      harmonies_engine.py:301-329, draws :120-137
+//   scoring          harmonies_engine.py:357-523
+//   canonical key    harmonies_engine.py:81-113 (+ MCTS.py:14,177,185 for HZ_KEY_REFERENCE)
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/harmonies_b200.h"
+
+namespace hz {
+
+constexpr uint32_t VALID = 0x7FFFFFu;  // 23 hexes
+constexpr int SW = 28;                 // live words of a state (28..31 are reserved zeros)
+
+struct State {
+    uint32_t w[SW];
+};
+
+// ---- neighbour tables ------------------------------------------------------------------
+// NBR[i] = mask of hexes adjacent to hex i (constants.py:35 + harmonies_engine.py:31-43),
+// derived offline from the axial coordinates; checked against the reference in the tests.
+__constant__ uint32_t NBR[23] = {
+    0x00000Cu, 0x000064u, 0x0000CBu, 0x000185u, 0x000220u, 0x000652u, 0x000CA6u, 0x00194Cu,
+    0x003088u, 0x004430u, 0x00CA60u, 0x0194C0u, 0x032980u, 0x061100u, 0x088600u, 0x194C00u,
+    0x329800u, 0x253000u, 0x022000u, 0x50C000u, 0x698000u, 0x130000u, 0x180000u};
+// (y*7+x) cell of hex i in the 5x7 plane (process_game_state.py:9-12,36-37)
+__constant__ uint8_t HEX_CELL[23] = {28, 15, 22, 29, 2, 9, 16, 23, 30, 3, 10, 17,
+                                     24, 31, 4,  11, 18, 25, 32, 5, 12, 19, 6};
+// fp32 bit patterns of float(c / INITIAL_BAG[t]) are produced with a double division, as
+// the reference does (process_game_state.py:122-130)
+__constant__ int INIT_BAG[6] = {23, 19, 21, 23, 15, 19};
+
+// Shared-memory neighbour-expansion LUT: nbr(m) = L[0][m&255] | L[1][(m>>8)&255] | L[2][m>>16]
+struct NbrLut {
+    uint32_t t[3][256];
+};
+__device__ __forceinline__ void build_nbr_lut(NbrLut* lut) {
+    for (int e = threadIdx.x; e < 768; e += blockDim.x) {
+        int c = e >> 8, v = e & 255;
+        uint32_t m = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            int i = c * 8 + b;
+            if (((v >> b) & 1) && i < 23) m |= NBR[i];
+        }
+        lut->t[c][v] = m;
+    }
+}
+__device__ __forceinline__ uint32_t nbr(const NbrLut* lut, uint32_t m) {
+    return lut->t[0][m & 255] | lut->t[1][(m >> 8) & 255] | lut->t[2][(m >> 16) & 127];
+}
+
+// ---- rng ---------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t rand64(uint64_t key, uint64_t ctr) {
+    return mix64(key ^ mix64(ctr + 0x9E3779B97F4A7C15ull));
+}
+
+// ---- state access -------------------------------------------------------------------------
+__device__ __forceinline__ void load_state(State& s, const void* base, int64_t idx) {
+    const uint4* p = reinterpret_cast<const uint4*>(base) + idx * 8;
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        uint4 v = p[k];
+        s.w[4 * k] = v.x; s.w[4 * k + 1] = v.y; s.w[4 * k + 2] = v.z; s.w[4 * k + 3] = v.w;
+    }
+}
+__device__ __forceinline__ void store_state(const State& s, void* base, int64_t idx) {
+    uint4* p = reinterpret_cast<uint4*>(base) + idx * 8;
+#pragma unroll
+    for (int k = 0; k < 7; k++) p[k] = make_uint4(s.w[4 * k], s.w[4 * k + 1], s.w[4 * k + 2], s.w[4 * k + 3]);
+    p[7] = make_uint4(0, 0, 0, 0);
+}
+
+__device__ __forceinline__ uint32_t meta(const State& s) { return s.w[HZ_W_BAG1META] >> 24; }
+__device__ __forceinline__ int player_of(const State& s) { return (s.w[HZ_W_BAG1META] >> 24) & 1; }
+__device__ __forceinline__ int phase_of(const State& s) { return (s.w[HZ_W_BAG1META] >> 25) & 7; }
+__device__ __forceinline__ int ending_of(const State& s) { return (s.w[HZ_W_BAG1META] >> 28) & 1; }
+__device__ __forceinline__ int winner_code(const State& s) { return (s.w[HZ_W_BAG1META] >> 29) & 3; }
+__device__ __forceinline__ int n_piles_of(const State& s) { return (s.w[HZ_W_BAG1META] >> 16) & 0xFF; }
+__device__ __forceinline__ uint32_t hand_of(const State& s) { return s.w[HZ_W_PILE4H] >> 16; }
+__device__ __forceinline__ bool is_over(const State& s) { return ending_of(s) && winner_code(s) != 0; }
+__device__ __forceinline__ int outcome_of(const State& s) {   // harmonies_engine.py:335-342
+    int wc = winner_code(s);
+    return (!ending_of(s)) ? 0 : wc == 1 ? 1 : wc == 2 ? -1 : 0;
+}
+__device__ __forceinline__ uint64_t key_of(const State& s) {
+    return (uint64_t)s.w[HZ_W_KEYLO] | ((uint64_t)s.w[HZ_W_KEYHI] << 32);
+}
+
+// one player's board: 9 planes, bp[level*3+bit]
+struct Board {
+    uint32_t p[9];
+};
+__device__ __forceinline__ Board board_of(const State& s, int player) {
+    Board b;
+#pragma unroll
+    for (int k = 0; k < 9; k++) b.p[k] = player ? s.w[9 + k] : s.w[k];
+    return b;
+}
+__device__ __forceinline__ void set_board(State& s, int player, const Board& b) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+        if (player) s.w[9 + k] = b.p[k]; else s.w[k] = b.p[k];
+    }
+}
+
+// derived masks of one board
+struct Tops {
+    uint32_t occ0, occ1, occ2;  // height >= 1, 2, 3
+    uint32_t t0, t1, t2;        // bits of the top tile's code
+};
+__device__ __forceinline__ Tops tops_of(const Board& b) {
+    Tops t;
+    t.occ0 = b.p[0] | b.p[1] | b.p[2];
+    t.occ1 = b.p[3] | b.p[4] | b.p[5];
+    t.occ2 = b.p[6] | b.p[7] | b.p[8];
+    t.t0 = b.p[6] | (b.p[3] & ~t.occ2) | (b.p[0] & ~t.occ1);
+    t.t1 = b.p[7] | (b.p[4] & ~t.occ2) | (b.p[1] & ~t.occ1);
+    t.t2 = b.p[8] | (b.p[5] & ~t.occ2) | (b.p[2] & ~t.occ1);
+    return t;
+}
+// tile codes: water 1, plant 2, wood 3, stone 4, building 5, field 6
+__device__ __forceinline__ uint32_t top_water(const Tops& t) { return t.t0 & ~t.t1 & ~t.t2; }
+__device__ __forceinline__ uint32_t top_plant(const Tops& t) { return ~t.t0 & t.t1 & ~t.t2; }
+__device__ __forceinline__ uint32_t top_wood(const Tops& t) { return t.t0 & t.t1 & ~t.t2; }
+__device__ __forceinline__ uint32_t top_stone(const Tops& t) { return ~t.t0 & ~t.t1 & t.t2; }
+__device__ __forceinline__ uint32_t top_building(const Tops& t) { return t.t0 & ~t.t1 & t.t2; }
+__device__ __forceinline__ uint32_t top_field(const Tops& t) { return ~t.t0 & t.t1 & t.t2; }
+
+// ---- legal moves (harmonies_engine.py:145-208) ---------------------------------------------
+// per-type 23-bit masks of legal hexes for the mover; types not in hand give 0.
+struct Legal {
+    uint32_t m[6];
+    int n_piles;  // choose phase: number of selectable piles (else 0)
+};
+__device__ __forceinline__ Legal legal_of(const State& s) {
+    Legal L;
+#pragma unroll
+    for (int t = 0; t < 6; t++) L.m[t] = 0;
+    L.n_piles = 0;
+    int ph = phase_of(s);
+    if (ph == HZ_PHASE_CHOOSE) {
+        L.n_piles = n_piles_of(s);                                   // :158
+    } else if (ph <= HZ_PHASE_PLACE3) {
+        uint32_t hand = hand_of(s);
+        Tops t = tops_of(board_of(s, player_of(s)));
+        uint32_t empty = ~t.occ0 & VALID;                            // :173
+        uint32_t on_plant = top_wood(t) & ~t.occ2;                   // :183  (h <= 2)
+        uint32_t on_stone = top_stone(t) & ~t.occ2;                  // :186  (h < 3)
+        uint32_t on_build = (top_wood(t) | top_stone(t) | top_building(t)) & ~t.occ1;  // :190-192
+        L.m[0] = (hand & 0x003) ? empty : 0;
+        L.m[1] = (hand & 0x00C) ? (empty | on_plant) : 0;
+        L.m[2] = (hand & 0x030) ? empty : 0;
+        L.m[3] = (hand & 0x0C0) ? (empty | on_stone) : 0;
+        L.m[4] = (hand & 0x300) ? (empty | on_build) : 0;
+        L.m[5] = (hand & 0xC00) ? empty : 0;
+    }
+    return L;
+}
+__device__ __forceinline__ int legal_count(const Legal& L) {
+    return L.n_piles + __popc(L.m[0]) + __popc(L.m[1]) + __popc(L.m[2]) + __popc(L.m[3]) +
+           __popc(L.m[4]) + __popc(L.m[5]);
+}
+// 143-bit action mask, bit a = 5 + 23*t + hex (process_game_state.py:156-177)
+__device__ __forceinline__ void legal_words(const Legal& L, uint32_t out[5]) {
+    uint64_t lo = ((1u << L.n_piles) - 1u);           // bits 0..4
+    lo |= (uint64_t)L.m[0] << 5;                      // 5..27
+    lo |= (uint64_t)L.m[1] << 28;                     // 28..50
+    uint64_t mid = (uint64_t)L.m[2] >> 13;            // bit 51.. -> word pair 1 (bits 64..127)
+    lo |= (uint64_t)L.m[2] << 51;
+    mid |= (uint64_t)L.m[3] << 10;                    // 74 - 64
+    mid |= (uint64_t)L.m[4] << 33;                    // 97 - 64
+    mid |= (uint64_t)L.m[5] << 56;                    // 120 - 64
+    uint32_t hi = L.m[5] >> 8;                        // bits 128..142
+    out[0] = (uint32_t)lo; out[1] = (uint32_t)(lo >> 32);
+    out[2] = (uint32_t)mid; out[3] = (uint32_t)(mid >> 32);
+    out[4] = hi;
+}
+// position of the k-th (0-based) set bit of m; k < popc(m)
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int k) {
+    int pos = 0, c;
+    c = __popc(m & 0xFFFFu); if (k >= c) { k -= c; pos += 16; m >>= 16; }
+    c = __popc(m & 0xFFu);   if (k >= c) { k -= c; pos += 8;  m >>= 8; }
+    c = __popc(m & 0xFu);    if (k >= c) { k -= c; pos += 4;  m >>= 4; }
+    c = __popc(m & 0x3u);    if (k >= c) { k -= c; pos += 2;  m >>= 2; }
+    c = m & 1u;              if (k >= c) { pos += 1; }
+    return pos;
+}
+// k-th legal action in ascending action-index order; k < legal_count(L)
+__device__ __forceinline__ int kth_action(const Legal& L, int k) {
+    if (k < L.n_piles) return k;
+    k -= L.n_piles;
+    int a = -1;
+#pragma unroll
+    for (int t = 0; t < 6; t++) {
+        int c = __popc(L.m[t]);
+        if (a < 0) {
+            if (k < c) a = 5 + 23 * t + nth_set_bit(L.m[t], k);
+            else k -= c;
+        }
+    }
+    return a;
+}
+// the uniform-random playout policy (see hz_random_actions in harmonies_b200.h)
+__device__ __forceinline__ int random_action(const State& s, const Legal& L) {
+    int n = legal_count(L);
+    if (n == 0) return -1;
+    uint64_t r = rand64(key_of(s) ^ HZ_PLAYOUT_SALT, (uint64_t)s.w[HZ_W_MOVES]);
+    int k = (int)(((r >> 32) * (uint64_t)n) >> 32);
+    return kth_action(L, k);
+}
+
+// ---- scoring (harmonies_engine.py:357-523) --------------------------------------------------
+__device__ __forceinline__ uint32_t flood(const NbrLut* lut, uint32_t seed, uint32_t within) {
+    uint32_t f = seed, nf;
+    while ((nf = (f | nbr(lut, f)) & within) != f) f = nf;
+    return f;
+}
+__device__ __forceinline__ int water_points(int len) {              // :18-27
+    return len <= 1 ? 0 : len == 2 ? 2 : len <= 5 ? 3 * len - 4 : 15 + (len - 6) * 4;
+}
+__device__ __forceinline__ void score_board(const NbrLut* lut, const Board& b, int terms[5]) {
+    Tops t = tops_of(b);
+    uint32_t h1 = t.occ0 & ~t.occ1, h2 = t.occ1 & ~t.occ2, h3 = t.occ2;
+    // grass :369-385
+    uint32_t tp = top_plant(t);
+    uint32_t l0_wood = b.p[0] & b.p[1] & ~b.p[2], l1_wood = b.p[3] & b.p[4] & ~b.p[5];
+    terms[0] = __popc(tp & h1) + 3 * __popc(tp & h2 & l0_wood) + 7 * __popc(tp & h3 & l0_wood & l1_wood);
+    // mountains :392-413
+    uint32_t ts = top_stone(t);
+    uint32_t adj = ts & nbr(lut, ts);
+    terms[1] = __popc(adj & h1) + 3 * __popc(adj & h2) + 7 * __popc(adj & h3);
+    // fields :424-443
+    int sc = 0;
+    uint32_t rem = top_field(t);
+    while (rem) {
+        uint32_t comp = flood(lut, rem & (0u - rem), rem);
+        rem &= ~comp;
+        sc += (comp & (comp - 1)) ? 5 : 0;                           // size >= 2
+    }
+    terms[2] = sc;
+    // buildings :454-469
+    sc = 0;
+    uint32_t tb = top_building(t) & h2;
+    if (tb) {
+        uint32_t tw = top_water(t), twd = top_wood(t), tf = top_field(t), tbl = top_building(t);
+        while (tb) {
+            uint32_t bit = tb & (0u - tb);
+            tb ^= bit;
+            uint32_t nb = nbr(lut, bit);
+            int kinds = ((tw & nb) != 0) + ((tp & nb) != 0) + ((twd & nb) != 0) + ((ts & nb) != 0) +
+                        ((tbl & nb) != 0) + ((tf & nb) != 0);
+            sc += kinds >= 3 ? 5 : 0;
+        }
+    }
+    terms[3] = sc;
+    // water :480-518 — per component of size >= 2: (BFS diameter + 1) -> table
+    sc = 0;
+    rem = top_water(t);
+    while (rem) {
+        uint32_t comp = flood(lut, rem & (0u - rem), rem);
+        rem &= ~comp;
+        if (!(comp & (comp - 1))) continue;
+        int diameter = 0;
+        uint32_t src = comp;
+        while (src) {
+            uint32_t f = src & (0u - src), nf;
+            src ^= f;
+            int d = 0;
+            while ((nf = (f | nbr(lut, f)) & comp) != f) { f = nf; d++; }
+            diameter = max(diameter, d);
+        }
+        sc += water_points(diameter + 1);
+    }
+    terms[4] = sc;
+}
+__device__ __forceinline__ int score_player(const NbrLut* lut, const State& s, int p) {
+    int t[5];
+    score_board(lut, board_of(s, p), t);
+    return t[0] + t[1] + t[2] + t[3] + t[4];
+}
+
+// ---- draws (harmonies_engine.py:120-137) -----------------------------------------------------
+// bag as 6 bytes of a 64-bit word (TILE_TYPES order)
+__device__ __forceinline__ uint64_t bag_of(const State& s) {
+    return (uint64_t)s.w[HZ_W_BAG0] | ((uint64_t)(s.w[HZ_W_BAG1META] & 0xFFFFu) << 32);
+}
+__device__ __forceinline__ void set_bag(State& s, uint64_t bag) {
+    s.w[HZ_W_BAG0] = (uint32_t)bag;
+    s.w[HZ_W_BAG1META] = (s.w[HZ_W_BAG1META] & 0xFFFF0000u) | (uint32_t)(bag >> 32);
+}
+__device__ __forceinline__ int bag_total(uint64_t bag) {
+    uint32_t lo = (uint32_t)bag, hi = (uint32_t)(bag >> 32);
+    uint32_t s = (lo & 0x00FF00FFu) + ((lo >> 8) & 0x00FF00FFu) + (hi & 0xFFu) + ((hi >> 8) & 0xFFu);
+    return (s & 0xFFFFu) + (s >> 16);
+}
+// draws min(3,total) tiles; returns the pile's multiset code (0 if the bag was empty)
+__device__ __forceinline__ uint32_t draw_pile(uint64_t& bag, uint64_t z) {
+    uint32_t code = 0;
+    int total = bag_total(bag);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        if (total > 0) {
+            uint32_t x = (uint32_t)(z >> (21 * j)) & 0x1FFFFFu;
+            uint32_t r = (x * (uint32_t)total) >> 21;               // 21+7 bits < 32
+            uint64_t cum = bag * 0x0101010101010101ull;              // byte k = sum of bytes 0..k
+            uint32_t clo = (uint32_t)cum, c4 = (uint32_t)(cum >> 32) & 0xFFu;
+            uint32_t rr = r * 0x01010101u;
+            int t = __popc(__vcmpleu4(clo, rr) & 0x01010101u) + (c4 <= r ? 1 : 0);
+            bag -= 1ull << (8 * t);
+            code += 1u << (2 * t);
+            total--;
+        }
+    }
+    return code;
+}
+__device__ __forceinline__ bool pile_available(uint64_t bag, uint32_t code) {
+    bool ok = true;
+#pragma unroll
+    for (int t = 0; t < 6; t++) ok &= ((code >> (2 * t)) & 3u) <= ((uint32_t)(bag >> (8 * t)) & 0xFFu);
+    return ok;
+}
+__device__ __forceinline__ uint64_t bag_minus(uint64_t bag, uint32_t code) {
+#pragma unroll
+    for (int t = 0; t < 6; t++) bag -= (uint64_t)((code >> (2 * t)) & 3u) << (8 * t);
+    return bag;
+}
+
+// piles as 5 registers
+struct Piles {
+    uint32_t p[5];
+};
+__device__ __forceinline__ Piles piles_of(const State& s) {
+    Piles P;
+    P.p[0] = s.w[HZ_W_PILES01] & 0xFFFFu; P.p[1] = s.w[HZ_W_PILES01] >> 16;
+    P.p[2] = s.w[HZ_W_PILES23] & 0xFFFFu; P.p[3] = s.w[HZ_W_PILES23] >> 16;
+    P.p[4] = s.w[HZ_W_PILE4H] & 0xFFFFu;
+    return P;
+}
+__device__ __forceinline__ void set_piles(State& s, const Piles& P, uint32_t hand, int n_piles) {
+    s.w[HZ_W_PILES01] = P.p[0] | (P.p[1] << 16);
+    s.w[HZ_W_PILES23] = P.p[2] | (P.p[3] << 16);
+    s.w[HZ_W_PILE4H] = P.p[4] | (hand << 16);
+    s.w[HZ_W_BAG1META] = (s.w[HZ_W_BAG1META] & 0xFF00FFFFu) | ((uint32_t)n_piles << 16);
+}
+__device__ __forceinline__ void set_meta(State& s, uint32_t m) {
+    s.w[HZ_W_BAG1META] = (s.w[HZ_W_BAG1META] & 0x00FFFFFFu) | (m << 24);
+}
+
+// ---- apply_move (harmonies_engine.py:210-329) -------------------------------------------------
+// dkey/devent: draw stream used if this move ends a turn; explicit_code != HZ_NO_DRAW
+// replaces the first pile drawn (trace replay); bump_event: advance the state's own event
+// counter (engine streams) or leave it (in-tree draws keyed by (simulation, action)).
+// Returns an HZ_MOVE_* status; the state is modified only on HZ_MOVE_OK.
+__device__ __forceinline__ int apply_move(State& s, int a, uint32_t explicit_code, uint64_t dkey,
+                                          uint32_t devent, bool bump_event, const NbrLut* lut) {
+    int ph = phase_of(s);
+    if (ph == HZ_PHASE_CHOOSE) {
+        int np = n_piles_of(s);
+        if (a < 0 || a >= np) return HZ_MOVE_BAD_PILE;               // :217-220
+        Piles P = piles_of(s);
+        uint32_t hand = P.p[0];
+#pragma unroll
+        for (int j = 1; j < 5; j++) hand = (a == j) ? P.p[j] : hand;
+#pragma unroll
+        for (int j = 0; j < 4; j++) P.p[j] = (j >= a) ? P.p[j + 1] : P.p[j];   // pop(i), :221
+        P.p[4] = 0;
+        set_piles(s, P, hand, np - 1);
+        set_meta(s, (meta(s) & ~0xEu) | (HZ_PHASE_PLACE1 << 1));      // :223
+        s.w[HZ_W_MOVES]++;
+        return HZ_MOVE_OK;
+    }
+    if (ph > HZ_PHASE_PLACE3) return HZ_MOVE_BAD_PHASE;              // :296
+    if (a < 5) return HZ_MOVE_BAD_FORMAT;                            // :227-236
+    if (a >= HZ_ACTION_SIZE) return HZ_MOVE_BAD_COORD;               // :241-242
+    int tile = (a - 5) / 23, hex = (a - 5) - 23 * tile;
+    uint32_t hand = hand_of(s);
+    if (((hand >> (2 * tile)) & 3u) == 0) return HZ_MOVE_NOT_IN_HAND;   // :244-248
+    int pl = player_of(s);
+    Board b = board_of(s, pl);
+    Tops t = tops_of(b);
+    uint32_t bit = 1u << hex;
+    uint32_t ok = ~t.occ0;                                            // :255-257
+    ok |= (tile == 1) ? (top_wood(t) & ~t.occ2) : 0u;                 // :263
+    ok |= (tile == 3) ? (top_stone(t) & ~t.occ2) : 0u;                // :265
+    ok |= (tile == 4) ? ((top_wood(t) | top_stone(t) | top_building(t)) & ~t.occ1) : 0u;  // :267-271
+    if (!(ok & bit)) return HZ_MOVE_ILLEGAL_STACK;                    // :281
+    bool ends_turn = ph == HZ_PHASE_PLACE3;
+    int np = n_piles_of(s);
+    uint64_t bag = bag_of(s);
+    bool use_explicit = ends_turn && explicit_code != HZ_NO_DRAW && np < 5;
+    if (use_explicit && !pile_available(bag, explicit_code)) return HZ_MOVE_BAD_DRAW;
+
+    // place the tile on level h of the hex (:257,275)
+    uint32_t code = (uint32_t)tile + 1u;
+    uint32_t at0 = bit & ~t.occ0, at1 = bit & t.occ0 & ~t.occ1, at2 = bit & t.occ1;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        uint32_t on = (code >> k) & 1u ? 0xFFFFFFFFu : 0u;
+        b.p[k] |= at0 & on; b.p[3 + k] |= at1 & on; b.p[6 + k] |= at2 & on;
+    }
+    set_board(s, pl, b);
+    hand -= 1u << (2 * tile);                                         // hand.remove, :250
+    s.w[HZ_W_PILE4H] = (s.w[HZ_W_PILE4H] & 0xFFFFu) | (hand << 16);
+    s.w[HZ_W_MOVES]++;
+    if (!ends_turn) {
+        set_meta(s, meta(s) + 2u);                                    // phase+1, :287-290
+        return HZ_MOVE_OK;
+    }
+
+    // ---- _end_turn_actions (:301-329)
+    bool player_trigger = (23 - __popc(t.occ0 | bit)) <= 2;           // :304-305
+    bool bag_empty_before = bag_total(bag) == 0;                      // :307
+    Piles P = piles_of(s);
+    for (int k = 0; np < 5; k++) {                                    // _replenish_piles :132-137
+        uint32_t pc;
+        if (k == 0 && use_explicit) { pc = explicit_code; bag = bag_minus(bag, pc); }
+        else pc = draw_pile(bag, rand64(dkey, (uint64_t)devent * 8 + (uint64_t)k));
+        if (pc == 0) break;                                           // :135-136
+#pragma unroll
+        for (int j = 0; j < 5; j++) P.p[j] = (j == np) ? pc : P.p[j];
+        np++;
+    }
+    set_bag(s, bag);
+    set_piles(s, P, 0, np);
+    if (bump_event) s.w[HZ_W_EVENT]++;
+    bool triggered = player_trigger || (bag_empty_before && np == 0);  // :309-311
+    bool ending = ending_of(s);
+    uint32_t m = meta(s) & 1u;                                        // keep player
+    if (triggered && !ending && pl == 0) {                            // :314-318
+        m = 1u | (HZ_PHASE_CHOOSE << 1) | (1u << 4);
+    } else if ((triggered && !ending) || ending) {                    // :319-326
+        set_meta(s, m);  // scores read boards only
+        int s0 = score_player(lut, s, 0), s1 = score_player(lut, s, 1);   // :344-346
+        s.w[HZ_W_SCORES] = ((uint32_t)s0 & 0xFFFFu) | (((uint32_t)s1 & 0xFFFFu) << 16);
+        uint32_t wc = s0 > s1 ? 1u : s1 > s0 ? 2u : 3u;               // :348-354
+        m = m | (HZ_PHASE_OVER << 1) | (1u << 4) | (wc << 5);
+    } else {                                                          // :327-329
+        m = (m ^ 1u) | (HZ_PHASE_CHOOSE << 1);
+    }
+    set_meta(s, m);
+    return HZ_MOVE_OK;
+}
+
+// ---- canonical keys ----------------------------------------------------------------------------
+// Leftmost-embedding normal form of one board under the reference's hash aliasing
+// (HZ_KEY_REFERENCE in harmonies_b200.h).  Alias pairs {1,6},{2,7},{3,8} (shift 5) and
+// {4,5},{9,10},{14,15},{19,20} (shift 1); a stack moves to its lower partner iff every
+// earlier stack embeds strictly below that partner.
+__device__ __forceinline__ void alias_normalise(Board& b) {
+    uint32_t occ = b.p[0] | b.p[1] | b.p[2];
+    // adjacent pairs: hi occupied, lo empty
+    uint32_t m1 = occ & ~(occ << 1) & ((1u << 5) | (1u << 10) | (1u << 15) | (1u << 20));
+    bool o1 = occ & 2u, o2 = occ & 4u, o3 = occ & 8u, o4 = occ & 16u, o5 = occ & 32u;
+    bool o6 = occ & 64u, o7 = occ & 128u, o8 = occ & 256u;
+    bool clear25 = !(o2 | o3 | o4 | o5);
+    bool mv6 = o6 && !o1 && clear25;
+    bool mv7 = o7 && clear25 && (o6 ? mv6 : true);
+    bool mv8 = o8 && !(o3 | o4 | o5) && (o7 ? mv7 : (o6 ? mv6 : true));
+    uint32_t m5 = (mv6 ? 64u : 0u) | (mv7 ? 128u : 0u) | (mv8 ? 256u : 0u);
+    uint32_t keep = ~(m1 | m5);
+#pragma unroll
+    for (int k = 0; k < 9; k++) b.p[k] = (b.p[k] & keep) | ((b.p[k] & m1) >> 1) | ((b.p[k] & m5) >> 5);
+}
+__device__ __forceinline__ uint64_t hash_step(uint64_t h, uint32_t x) {
+    h = (h ^ x) * 0x9FB21C651E98DF25ull;
+    return h ^ (h >> 32);
+}
+// key words: 23 words of canonical identity (mode-normalised)
+__device__ __forceinline__ void key_words(const State& s, int mode, uint32_t k[HZ_CANON_WORDS]) {
+    if (mode == HZ_KEY_REFERENCE) {
+        Board b0 = board_of(s, 0), b1 = board_of(s, 1);
+        alias_normalise(b0); alias_normalise(b1);
+#pragma unroll
+        for (int i = 0; i < 9; i++) { k[i] = b0.p[i]; k[9 + i] = b1.p[i]; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 18; i++) k[i] = s.w[i];
+    }
+    k[18] = s.w[18]; k[19] = s.w[19]; k[20] = s.w[20]; k[21] = s.w[21];
+    k[22] = s.w[22] & 0x0FFFFFFFu;
+}
+__device__ __forceinline__ uint64_t hash_key_words(const uint32_t k[HZ_CANON_WORDS]) {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int i = 0; i < HZ_CANON_WORDS; i++) h = hash_step(h, k[i]);
+    return mix64(h);
+}
+__device__ __forceinline__ uint64_t canon_hash(const State& s, int mode) {
+    uint32_t k[HZ_CANON_WORDS];
+    key_words(s, mode, k);
+    return hash_key_words(k);
+}
+
+// ---- state tensors (process_game_state.py:15-137): per-channel hex masks + global features ----
+__constant__ uint8_t CELL_HEX[35] = {31, 31, 4, 9, 14, 19, 22, 31, 31, 5, 10, 15, 20, 31, 31, 1, 6, 11,
+                                     16, 21, 31, 31, 2, 7, 12, 17, 31, 31, 0, 3, 8, 13, 18, 31, 31};
+
+template <typename T> __device__ __forceinline__ T cvt(float v);
+template <> __device__ __forceinline__ float cvt<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// channel mask c (<38) of a state given its words; bit i = value at hex i is non-zero
+__device__ __forceinline__ uint32_t channel_mask(const uint32_t* w, int c) {
+    if (c < 36) {
+        int p = c / 18, r = c - 18 * p, t = r / 3, l = r - 3 * t;
+        const uint32_t* pl = w + p * 9 + l * 3;
+        uint32_t code = (uint32_t)t + 1u;
+        uint32_t a = pl[0], b = pl[1], d = pl[2];
+        return ((code & 1u) ? a : ~a) & ((code & 2u) ? b : ~b) & ((code & 4u) ? d : ~d) & VALID;  // :43-67
+    }
+    uint32_t m = w[HZ_W_BAG1META] >> 24;
+    if (c == 36) return (m & 1u) ? VALID : 0u;                       // :70-71
+    uint32_t ph = (m >> 1) & 7u;
+    return (ph >= 1 && ph <= 3) ? VALID : 0u;                        // :74-81 (phase 0 and game_over -> 0)
+}
+__device__ __forceinline__ float global_feature(const uint32_t* w, int g) {
+    const float third[4] = {0.0f, (float)(1.0 / 3.0), (float)(2.0 / 3.0), 1.0f};
+    if (g < 30) {                                                    // :98-107
+        int i = g / 6, t = g - 6 * i;
+        uint32_t np = (w[HZ_W_BAG1META] >> 16) & 0xFFu;
+        uint32_t word = w[HZ_W_PILES01 + (i >> 1)];
+        uint32_t code = (i & 1) ? (word >> 16) : (word & 0xFFFFu);
+        return (uint32_t)i < np ? third[(code >> (2 * t)) & 3u] : 0.0f;
+    }
+    if (g < 36) return third[((w[HZ_W_PILE4H] >> 16) >> (2 * (g - 30))) & 3u];   // :112-118
+    int t = g - 36;                                                  // :122-130
+    uint32_t cnt = t < 4 ? (w[HZ_W_BAG0] >> (8 * t)) & 0xFFu : (w[HZ_W_BAG1META] >> (8 * (t - 4))) & 0xFFu;
+    return (float)((double)cnt / (double)INIT_BAG[t]);
+}
+
+
+// ---- new game (harmonies_engine.py:66-79) ---------------------------------------------------------
+__device__ __forceinline__ void init_state(State& s, uint64_t key) {
+#pragma unroll
+    for (int i = 0; i < SW; i++) s.w[i] = 0;
+    uint64_t bag = 23ull | (19ull << 8) | (21ull << 16) | (23ull << 24) | (15ull << 32) | (19ull << 40);
+    Piles P;
+#pragma unroll
+    for (int k = 0; k < 5; k++) P.p[k] = draw_pile(bag, rand64(key, (uint64_t)k));   // event 0
+    s.w[HZ_W_KEYLO] = (uint32_t)key; s.w[HZ_W_KEYHI] = (uint32_t)(key >> 32);
+    s.w[HZ_W_EVENT] = 1;
+    set_bag(s, bag);
+    set_piles(s, P, 0, 5);
+}
+
+}  // namespace hz

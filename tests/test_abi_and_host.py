@@ -1,0 +1,112 @@
+"""CPU: the C-ABI library loads and exports every symbol include/harmonies_b200.h declares
+(no compute calls), device-side constant tables match the reference geometry, and the host
+packer round-trips."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests.conftest import ROOT, load_golden
+from harmonies_alphazero_b200 import constants as K
+from harmonies_alphazero_b200 import packed as pk
+
+HEADER = os.path.join(ROOT, "include", "harmonies_b200.h")
+CORE = os.path.join(ROOT, "harmonies_alphazero_b200", "csrc", "hz_core.cuh")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hz_[a-z_0-9]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from harmonies_alphazero_b200 import build
+
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from harmonies_alphazero_b200 import _lib
+
+    syms = _declared_symbols()
+    assert len(syms) >= 24
+    lib = ctypes.CDLL(built_lib)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in harmonies_b200.h but not exported"
+    # the Python binding declares a signature for each of them, and nothing else
+    assert sorted(_lib.SIGNATURES) == syms
+    loaded = _lib.load()
+    assert loaded.hz_abi_version() == 1
+    assert loaded.hz_status_string(-4).decode().startswith("workspace")
+    assert loaded.hz_launch_count() == 0
+    assert loaded.hz_tree_workspace_bytes(4096, 100, 0) > 4096 * 6901 * 128
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    from harmonies_alphazero_b200 import _lib
+
+    with pytest.raises(_lib.HarmoniesLibraryError):
+        _lib.load(str(tmp_path / "nope.so"))
+
+
+def test_device_tables_match_reference_geometry():
+    """NBR / HEX_CELL / CELL_HEX / INIT_BAG literals in hz_core.cuh vs constants.py"""
+    src = open(CORE).read()
+
+    def table(name):
+        m = re.search(name + r"\[\d+\]\s*=\s*\{(.*?)\}", src, flags=re.S)
+        return [int(x.rstrip("u"), 0) for x in re.findall(r"0x[0-9A-Fa-f]+u?|\d+", m.group(1))]
+
+    assert table("NBR") == K.NEIGHBOR_MASKS
+    assert table("HEX_CELL") == [y * 7 + x for (y, x) in K.HEX_CELL]
+    cell_hex = [31] * 35
+    for i, (y, x) in enumerate(K.HEX_CELL):
+        cell_hex[y * 7 + x] = i
+    assert table("CELL_HEX") == cell_hex
+    assert table("INIT_BAG") == K.INITIAL_BAG_BY_TYPE
+    # neighbourhood is symmetric, degree histogram of the 5-4-5-4-5 grid
+    deg = [bin(m).count("1") for m in K.NEIGHBOR_MASKS]
+    assert sorted(deg) == sorted([2] * 4 + [3] * 2 + [4] * 6 + [5] * 4 + [6] * 7)
+    for i, m in enumerate(K.NEIGHBOR_MASKS):
+        for j in range(23):
+            assert ((m >> j) & 1) == ((K.NEIGHBOR_MASKS[j] >> i) & 1)
+
+
+def test_pack_unpack_roundtrip():
+    g = load_golden("engine")
+    for w in np.concatenate([g["before"][::97], g["after"][-3:]]):
+        f = pk.unpack_fields(w)
+        keys = {k: f.pop(k) for k in ("rng_key", "rng_event", "moves")}
+        w2 = pk.pack_fields(**f, rng_key=keys["rng_key"], rng_event=keys["rng_event"], moves=keys["moves"])
+        assert np.array_equal(w2, w)
+    with pytest.raises(ValueError):
+        pk.pack_fields([{(9, 9): ["water"]}, {}], {}, [], 0, [], "choose_pile")
+    with pytest.raises(ValueError):
+        pk.pack_fields([{(0, 0): ["lava"]}, {}], {}, [], 0, [], "choose_pile")
+    with pytest.raises(ValueError):
+        pk.pack_fields([{}, {}], {}, [], 0, [], "thinking")
+    assert pk.action_to_move(3) == 3
+    assert pk.action_to_move(5 + 23 * 2 + 11) == ("wood", (0, 0))
+    assert pk.mask_to_actions(pk.actions_to_mask([0, 4, 31, 32, 142])) == [0, 4, 31, 32, 142]
+
+
+def test_draw_source_is_uniform_without_replacement():
+    """the counter-based draw is a permutation-uniform sample from the multiset bag"""
+    counts = np.zeros(6)
+    n = 4000
+    for i in range(n):
+        bag = list(pk.INITIAL_BAG_COUNTS)
+        tiles = pk.draw_pile(bag, pk.rand(12345, i))
+        assert len(tiles) == 3 and sum(bag) == 117
+        for t in tiles:
+            counts[t] += 1
+    expect = np.array(pk.INITIAL_BAG_COUNTS) / 120 * 3 * n
+    assert np.abs(counts - expect).max() < 5 * np.sqrt(expect.max())
+    bag = [0, 0, 1, 0, 1, 0]
+    assert sorted(pk.draw_pile(bag, pk.rand(1, 1))) == [2, 4] and bag == [0] * 6
+    assert pk.draw_pile([0] * 6, 99) == []
