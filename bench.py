@@ -57,8 +57,34 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.samples, self.stop_flag = None, [], False
+        try:  # in-process NVML polls every ~1 ms: the timed region of this bench is milliseconds long
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        R = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), sm, [k for k, bit in R.items() if rs & bit]))
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def start(self):
+        if self.nvml:
+            self.t0 = time.perf_counter()
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
@@ -73,6 +99,18 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            self.th.join(timeout=1)
+            nv = self.nvml
+            sm = [s[1] for s in self.samples]
+            reasons = sorted({r for s in self.samples for r in s[2]})
+            try:
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            except Exception:
+                mx = None
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml, ~1 ms polling during the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()

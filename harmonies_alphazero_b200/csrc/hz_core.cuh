@@ -201,18 +201,16 @@ __device__ __forceinline__ int nth_set_bit(uint32_t m, int k) {
 }
 // k-th legal action in ascending action-index order; k < legal_count(L)
 __device__ __forceinline__ int kth_action(const Legal& L, int k) {
-    if (k < L.n_piles) return k;
+    if (k < L.n_piles) return k;                      // choose phase (all type masks are zero)
+    // placement: pick the type whose cumulative count covers k with selects, then ONE bit search
+    // shared by all lanes (a per-type branch leaves ~5 of 32 lanes active in each search)
     k -= L.n_piles;
-    int a = -1;
-#pragma unroll
-    for (int t = 0; t < 6; t++) {
-        int c = __popc(L.m[t]);
-        if (a < 0) {
-            if (k < c) a = 5 + 23 * t + nth_set_bit(L.m[t], k);
-            else k -= c;
-        }
-    }
-    return a;
+    int c0 = __popc(L.m[0]), c1 = c0 + __popc(L.m[1]), c2 = c1 + __popc(L.m[2]);
+    int c3 = c2 + __popc(L.m[3]), c4 = c3 + __popc(L.m[4]);
+    int t = (k >= c0) + (k >= c1) + (k >= c2) + (k >= c3) + (k >= c4);
+    uint32_t m = t == 0 ? L.m[0] : t == 1 ? L.m[1] : t == 2 ? L.m[2] : t == 3 ? L.m[3] : t == 4 ? L.m[4] : L.m[5];
+    int below = t == 0 ? 0 : t == 1 ? c0 : t == 2 ? c1 : t == 3 ? c2 : t == 4 ? c3 : c4;
+    return 5 + 23 * t + nth_set_bit(m, k - below);
 }
 // the uniform-random playout policy (see hz_random_actions in harmonies_b200.h)
 __device__ __forceinline__ int random_action(const State& s, const Legal& L) {
@@ -365,6 +363,16 @@ __device__ __forceinline__ void set_meta(State& s, uint32_t m) {
 // replaces the first pile drawn (trace replay); bump_event: advance the state's own event
 // counter (engine streams) or leave it (in-tree draws keyed by (simulation, action)).
 // Returns an HZ_MOVE_* status; the state is modified only on HZ_MOVE_OK.
+// DEFER_SCORE: at the end of the game only mark phase game_over (winner still None) and let
+// the caller run finalize_scores() later — the fused playout does that once per warp after
+// all of its games have ended, so the scoring loops run with all lanes converged.
+__device__ __forceinline__ void finalize_scores(State& s, const NbrLut* lut) {
+    int s0 = score_player(lut, s, 0), s1 = score_player(lut, s, 1);       // :344-346
+    s.w[HZ_W_SCORES] = ((uint32_t)s0 & 0xFFFFu) | (((uint32_t)s1 & 0xFFFFu) << 16);
+    uint32_t wc = s0 > s1 ? 1u : s1 > s0 ? 2u : 3u;                       // :348-354
+    s.w[HZ_W_BAG1META] = (s.w[HZ_W_BAG1META] & ~(3u << 29)) | (wc << 29);
+}
+template <bool DEFER_SCORE = false>
 __device__ __forceinline__ int apply_move(State& s, int a, uint32_t explicit_code, uint64_t dkey,
                                           uint32_t devent, bool bump_event, const NbrLut* lut) {
     int ph = phase_of(s);
@@ -443,11 +451,9 @@ __device__ __forceinline__ int apply_move(State& s, int a, uint32_t explicit_cod
     if (triggered && !ending && pl == 0) {                            // :314-318
         m = 1u | (HZ_PHASE_CHOOSE << 1) | (1u << 4);
     } else if ((triggered && !ending) || ending) {                    // :319-326
-        set_meta(s, m);  // scores read boards only
-        int s0 = score_player(lut, s, 0), s1 = score_player(lut, s, 1);   // :344-346
-        s.w[HZ_W_SCORES] = ((uint32_t)s0 & 0xFFFFu) | (((uint32_t)s1 & 0xFFFFu) << 16);
-        uint32_t wc = s0 > s1 ? 1u : s1 > s0 ? 2u : 3u;               // :348-354
-        m = m | (HZ_PHASE_OVER << 1) | (1u << 4) | (wc << 5);
+        set_meta(s, m | (HZ_PHASE_OVER << 1) | (1u << 4));            // :320,324 (winner still None)
+        if (!DEFER_SCORE) finalize_scores(s, lut);                    // :321-322,325-326
+        return HZ_MOVE_OK;
     } else {                                                          // :327-329
         m = (m ^ 1u) | (HZ_PHASE_CHOOSE << 1);
     }
