@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--games", type=int, default=65536, help="concurrent games per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mcts", action="store_true", help="skip the secondary MCTS sims/s measurement")
+    ap.add_argument("--mcts-games", type=int, default=4096, help="concurrent games (trees) per GPU")
+    ap.add_argument("--mcts-sims", type=int, default=100)
+    ap.add_argument("--mcts-steps", type=int, default=5, help="timed moves (each = games x sims simulations)")
     return ap.parse_args()
 
 
@@ -189,6 +192,91 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------
+def mcts_measure(args, dev, world, rank, dist):
+    """configs[3]: MCTS self-play with the model.py net (random-init, bf16), 100 sims/move,
+    4,096 concurrent games per GPU.  One step = one move of every game = 4,096 x 100
+    simulations (select -> network forward -> expand+backup, CUDA-graph replayed)."""
+    import torch
+
+    from harmonies_alphazero_b200 import batched as hb
+    from harmonies_alphazero_b200 import net as hznet
+    from harmonies_alphazero_b200 import selfplay as sp
+
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(0)
+    model = hznet.AlphaZeroNet.from_config(hznet.DEFAULT_MODEL_CONFIG).eval()
+    inf = hznet.InferenceNet(model, device=dev, dtype=torch.bfloat16)
+    B, S = args.mcts_games, args.mcts_sims
+    cfg = sp.SelfPlayConfig(n_slots=B, num_simulations=S, cpuct=2.0, dirichlet_alpha=0.4, dirichlet_epsilon=0.25,
+                            turns_until_tau0=15, seed=77, first_game_id=rank * B)
+    drv = sp.BatchedSelfPlay(inf, cfg, device=dev)
+    states = hb.init_states(B, device=dev, seed=77, first_id=rank * B)
+    hb.playout(states, max_steps=8)                 # a few moves in: realistic branching
+    u01 = torch.rand(B, device=dev)
+
+    def one_move():
+        drv.search(states)
+        hb.apply(states, drv.tree.choose(u01, None))
+
+    one_move()                                      # warm-up: cuDNN autotune + graph capture
+    one_move()
+    K = args.mcts_steps
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = hb.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        one_move()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    drv.tree.check_status()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    sims = B * S * K * world
+    v = sims / (ms * 1e-3)
+    pk, pk_src = peaks()
+    flops = hznet.flops_per_position()
+    ach = (v / world) * flops / 1e12
+    return {"metric": "mcts_sims_per_sec", "value": v, "unit": "sims/s", "ms_per_move": ms / K,
+            "config": {"workload": "MCTS self-play, model.py net 128f x 8 blocks random-init, bf16, "
+                                   f"{S} sims/move, {B} concurrent games per GPU (configs[3])",
+                       "fused_conv": inf.fused, "cuda_graph": drv.graph is not None},
+            "dtype": "bf16", "gpu_launches_own": hb.launch_count() - l0,
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
+                         "peak_source": pk_src + " (sustained cuBLAS bf16)",
+                         "note": f"{flops / 1e6:.2f} MFLOP per simulation (network forward) x sims/s per GPU"}}
+
+
+def cpu_mcts_baseline(budget_s=10.0):
+    """the oracle's MCTS (C port of MCTS.py) with the synthetic evaluator on all host threads:
+    tree work only, no network — an upper bound for the CPU side."""
+    from oracle import oracle as orc
+    import numpy as np
+
+    threads = os.cpu_count() or 1
+    roots = orc.init_states(8 * threads, seed=5)
+    keys = np.arange(len(roots), dtype=np.uint64)
+    t0 = time.perf_counter()
+    orc.search_batch(roots, keys, 100, 2.0, n_threads=threads)
+    dt = time.perf_counter() - t0
+    n = int(max(len(roots), min(200000, len(roots) * budget_s / max(dt, 1e-3))))
+    roots = orc.init_states(n, seed=6)
+    keys = np.arange(n, dtype=np.uint64)
+    t0 = time.perf_counter()
+    orc.search_batch(roots, keys, 100, 2.0, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": n * 100 / dt, "unit": "sims/s", "cores": threads, "kind": "port",
+            "sample": f"{n} searches x 100 sims, synthetic evaluator (no network), oracle/hz_oracle.c on {threads} pthreads; "
+                      "the Python reference with its net on CPU does ~75 sims/s/core (BASELINE.md §2)"}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -303,8 +391,13 @@ def run_b200(args):
                      "the fused kernel keeps the state on chip, so DRAM traffic is ~256 B per GAME"},
         "wall_s": wall,
     }
+    if not args.no_mcts:
+        # second half of BASELINE.json's metric: MCTS sims/s (configs[3]), reported alongside
+        out["mcts"] = mcts_measure(args, dev, world, rank, dist if world > 1 else None)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
+        if "mcts" in out:
+            out["mcts"]["cpu_baseline"] = cpu_mcts_baseline()
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(TTPB) k_tree_reset(hz_tree T, const uint4* roo
     v.node_info[0] = (uint32_t)player_of(s) << 8;
     v.table[h & (uint64_t)(T.table_size - 1)] = 1;
     T.depth[t] = 0; T.leaf[t] = 0; T.sim[t] = 0; T.n_nodes[t] = 1; T.n_edges[t] = 0; T.status[t] = 0;
-    T.search_key[t] = keys[t];
+    // default key: a stream of its own per (game, move), independent of the game's draw stream
+    T.search_key[t] = keys ? keys[t] : rand64(key_of(s) ^ HZ_SEARCH_SALT, (uint64_t)s.w[HZ_W_MOVES]);
 }
 
 // ---- warp-level state encoding (shared with hz_encode's definition of the tensors) -----------
@@ -500,7 +501,7 @@ int hz_tree_destroy(hz_tree* t) {
 }
 
 int hz_tree_reset(hz_tree* t, const void* root_states, const uint64_t* search_keys, void* stream) {
-    if (!t || !root_states || !search_keys) return HZ_ERR_ARG;
+    if (!t || !root_states) return HZ_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(t->table, 0, t->table_bytes, st);
     if (e != cudaSuccess) return hz_record_launch(0, e);

@@ -1,0 +1,171 @@
+"""Policy/value network for batched leaf evaluation.
+
+north_star keeps the network a PyTorch forward on tensor cores ("the only dense
+contraction").  Two classes:
+
+* ``AlphaZeroNet`` — the reference architecture (model.py:277-357: 3x3 conv stem, N residual
+  blocks, 1x1-conv policy/value heads whose FC layers also take the 42 global features) with
+  the SAME parameter names, so ``load_state_dict`` accepts the reference's checkpoints
+  (``model_state_dict`` of ModelManager.save_checkpoint, model.py:161-182) and vice versa.
+* ``InferenceNet`` — what self-play actually runs: eval-mode BatchNorm folded into the
+  convolutions, bf16 (or fp32) weights in channels-last layout, bias+ReLU(+residual) fused into
+  the cuDNN convolution call, meant to be captured in a CUDA graph together with the tree
+  kernels.  ``predict`` mirrors ModelManager.predict (model.py:81-110) for a batch.
+"""
+
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from .constants import ACTION_SIZE, BOARD_SIZE, GLOBAL_FEATURE_SIZE, INPUT_CHANNELS
+
+DEFAULT_MODEL_CONFIG = {  # config.py:18-29
+    "input_channels": INPUT_CHANNELS,
+    "cnn_filters": 128,
+    "board_size": BOARD_SIZE,
+    "action_size": ACTION_SIZE,
+    "global_feature_size": GLOBAL_FEATURE_SIZE,
+    "value_head_hidden_dim": 256,
+    "num_res_blocks": 8,
+    "policy_head_conv_filters": 2,
+    "value_head_conv_filters": 1,
+}
+TEST_MODEL_CONFIG = dict(DEFAULT_MODEL_CONFIG, cnn_filters=32, value_head_hidden_dim=64, num_res_blocks=1)  # config.py:103-113
+
+
+class _Block(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv1 = nn.Conv2d(c, c, 3, padding=1)
+        self.bn1 = nn.BatchNorm2d(c)
+        self.conv2 = nn.Conv2d(c, c, 3, padding=1)
+        self.bn2 = nn.BatchNorm2d(c)
+
+    def forward(self, x):
+        y = F.relu(self.bn1(self.conv1(x)))
+        return F.relu(self.bn2(self.conv2(y)) + x)
+
+
+class AlphaZeroNet(nn.Module):
+    def __init__(self, input_channels=INPUT_CHANNELS, cnn_filters=128, board_size=BOARD_SIZE, action_size=ACTION_SIZE,
+                 global_feature_size=GLOBAL_FEATURE_SIZE, value_head_hidden_dim=256, num_res_blocks=8,
+                 policy_head_conv_filters=2, value_head_conv_filters=1):
+        super().__init__()
+        h, w = board_size
+        self.conv = nn.Conv2d(input_channels, cnn_filters, 3, padding=1)
+        self.bn = nn.BatchNorm2d(cnn_filters)
+        self.residual_blocks = nn.ModuleList(_Block(cnn_filters) for _ in range(num_res_blocks))
+        self.policy_conv = nn.Conv2d(cnn_filters, policy_head_conv_filters, 1)
+        self.policy_bn = nn.BatchNorm2d(policy_head_conv_filters)
+        self.policy_fc = nn.Linear(policy_head_conv_filters * h * w + global_feature_size, action_size)
+        self.value_conv = nn.Conv2d(cnn_filters, value_head_conv_filters, 1)
+        self.value_bn = nn.BatchNorm2d(value_head_conv_filters)
+        self.value_fc1 = nn.Linear(value_head_conv_filters * h * w + global_feature_size, value_head_hidden_dim)
+        self.value_fc2 = nn.Linear(value_head_hidden_dim, 1)
+
+    @classmethod
+    def from_config(cls, cfg):
+        return cls(**{k: cfg[k] for k in DEFAULT_MODEL_CONFIG if k in cfg})
+
+    def forward(self, x_board, x_global):
+        x = F.relu(self.bn(self.conv(x_board)))
+        for blk in self.residual_blocks:
+            x = blk(x)
+        p = F.relu(self.policy_bn(self.policy_conv(x))).flatten(1)
+        logits = self.policy_fc(torch.cat((p, x_global), dim=1))
+        v = F.relu(self.value_bn(self.value_conv(x))).flatten(1)
+        v = F.relu(self.value_fc1(torch.cat((v, x_global), dim=1)))
+        return logits, torch.tanh(self.value_fc2(v))
+
+
+def _fold(conv, bn):
+    """eval-mode BatchNorm folded into the preceding convolution (fp32 math)."""
+    scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+    w = conv.weight.detach().float() * scale.view(-1, 1, 1, 1)
+    b = (conv.bias.detach().float() - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+    return w, b
+
+
+class InferenceNet:
+    """Folded, channels-last inference copy of an AlphaZeroNet on one device."""
+
+    def __init__(self, model, device="cuda", dtype=torch.bfloat16, fused=True):
+        self.device, self.dtype = torch.device(device), dtype
+        self.fused = fused and self.device.type == "cuda"
+        self.load(model)
+
+    def load(self, model):
+        """(Re)build the folded weights from ``model`` (after a weight broadcast / checkpoint)."""
+        dev, dt = self.device, self.dtype
+
+        def conv_params(conv, bn):
+            w, b = _fold(conv, bn)
+            return (w.to(dev, dt).contiguous(memory_format=torch.channels_last), b.to(dev, dt))
+
+        self.stem = conv_params(model.conv, model.bn)
+        self.blocks = [(conv_params(b.conv1, b.bn1), conv_params(b.conv2, b.bn2)) for b in model.residual_blocks]
+        self.phead = conv_params(model.policy_conv, model.policy_bn)
+        self.vhead = conv_params(model.value_conv, model.value_bn)
+        lin = lambda l: (l.weight.detach().to(dev, dt).contiguous(), l.bias.detach().to(dev, dt))  # noqa: E731
+        self.policy_fc, self.value_fc1, self.value_fc2 = lin(model.policy_fc), lin(model.value_fc1), lin(model.value_fc2)
+        if self.fused:
+            # the fused cuDNN entry points do not cover every dtype/arch combination: probe once
+            # and use conv2d + relu (still cuDNN) if they refuse
+            try:
+                x = torch.zeros((2, self.stem[0].shape[1], 5, 7), device=dev, dtype=dt).contiguous(memory_format=torch.channels_last)
+                y = self._conv_relu(x, self.stem, 1)
+                self._conv_relu(y, self.blocks[0][0] if self.blocks else self.phead, 1 if self.blocks else 0, residual=y if self.blocks else None)
+                torch.cuda.synchronize(dev)
+            except Exception as e:  # noqa: BLE001
+                self.fused, self.fused_error = False, repr(e)
+
+    def _conv_relu(self, x, wb, pad, residual=None):
+        w, b = wb
+        if self.fused:
+            # one cuDNN kernel: relu(conv(x) + bias [+ residual])
+            if residual is None:
+                return torch.cudnn_convolution_relu(x, w, b, (1, 1), (pad, pad), (1, 1), 1)
+            return torch.cudnn_convolution_add_relu(x, w, residual, 1.0, b, (1, 1), (pad, pad), (1, 1), 1)
+        y = F.conv2d(x, w, b, padding=pad)
+        if residual is not None:
+            y = y + residual
+        return F.relu(y)
+
+    @torch.no_grad()
+    def forward(self, board, glob):
+        """board [B,38,5,7] (channels-last preferred), glob [B,42], both ``dtype``.
+        Returns (logits fp32 [B,143], value fp32 [B])."""
+        x = self._conv_relu(board, self.stem, 1)
+        for c1, c2 in self.blocks:
+            y = self._conv_relu(x, c1, 1)
+            x = self._conv_relu(y, c2, 1, residual=x)
+        B = x.shape[0]
+        p = self._conv_relu(x, self.phead, 0).contiguous(memory_format=torch.contiguous_format).view(B, -1)
+        logits = F.linear(torch.cat((p, glob), dim=1), *self.policy_fc)
+        v = self._conv_relu(x, self.vhead, 0).contiguous(memory_format=torch.contiguous_format).view(B, -1)
+        v = F.relu(F.linear(torch.cat((v, glob), dim=1), *self.value_fc1))
+        v = torch.tanh(F.linear(v, *self.value_fc2))
+        return logits.float(), v.float().view(B)
+
+    __call__ = forward
+
+    @torch.no_grad()
+    def predict(self, board, glob):
+        """Batched ModelManager.predict (model.py:81-110): softmax over ALL 143 logits (no
+        legal masking), value as a scalar per position."""
+        logits, v = self.forward(board.to(self.device, self.dtype), glob.to(self.device, self.dtype))
+        return torch.softmax(logits, dim=1), v
+
+
+def flops_per_position(cfg=DEFAULT_MODEL_CONFIG):
+    """Forward FLOPs (2*MAC) of the network for one position: 168.31 MFLOP for the default
+    configuration."""
+    h, w = cfg["board_size"]
+    c, hw = cfg["cnn_filters"], h * w
+    f = 2 * hw * 9 * cfg["input_channels"] * c
+    f += cfg["num_res_blocks"] * 2 * (2 * hw * 9 * c * c)
+    f += 2 * hw * c * (cfg["policy_head_conv_filters"] + cfg["value_head_conv_filters"])
+    f += 2 * (cfg["policy_head_conv_filters"] * hw + cfg["global_feature_size"]) * cfg["action_size"]
+    f += 2 * (cfg["value_head_conv_filters"] * hw + cfg["global_feature_size"]) * cfg["value_head_hidden_dim"]
+    f += 2 * cfg["value_head_hidden_dim"]
+    return f

@@ -1,0 +1,231 @@
+"""Batched self-play: the B200 replacement for the body of Trainer.execute_self_play_phase /
+self_play_worker (trainer.py:62-134, 434-541).
+
+Thousands of games live in one packed state tensor; every game owns one search tree; one
+"simulation step" advances ALL trees by one simulation: hz_tree_select (PUCT descent + leaf
+encoding) -> network forward on the whole batch of leaves -> hz_tree_expand_backup.  That
+triple is captured once in a CUDA graph and replayed ``num_simulations`` times per move.
+Finished games are replaced by fresh ones in place (continuous batching), so the network
+batch stays full.
+
+Output contract = the reference worker's (trainer.py:531-538): one example per action of
+every completed game: (board f32[38,5,7], global f32[42], pi f32[143], z f32[1]) with the
+state encoded BEFORE the search of that move, pi = root visit distribution, z = final
+outcome from the mover's perspective (0 on a draw).  Examples are kept packed on the device
+(128 B state + int16 visit counts) and expanded on demand.
+"""
+
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import batched as hb
+from .tree import BatchedMCTS
+
+
+@dataclass
+class SelfPlayConfig:
+    n_slots: int = 4096            # concurrent games on this GPU
+    num_simulations: int = 100     # mcts_config["num_simulations"]
+    cpuct: float = 2.0             # mcts_config["cpuct"]
+    dirichlet_alpha: float = 0.4
+    dirichlet_epsilon: float = 0.25
+    turns_until_tau0: int = 15
+    testing: bool = False          # True: no root noise, greedy moves (MCTS.py:308,400)
+    key_mode: int = hb.KEY_REFERENCE
+    seed: int = 0
+    first_game_id: int = 0         # global id of this rank's first game (sharding)
+    use_cuda_graph: bool = True
+    max_nodes: int = 0             # per-tree node arena; 0 = worst case 1 + 69*sims
+    max_moves: int = 200           # hard cap per game (structural maximum is 160 actions)
+
+    @classmethod
+    def from_mcts_config(cls, mcts_config, **kw):
+        """Reads the keys MCTS.py reads: num_simulations, cpuct,
+        dirichlet_alpha, dirichlet_epsilon, turns_until_tau0, testing."""
+        m = dict(
+            num_simulations=int(mcts_config["num_simulations"]),
+            cpuct=float(mcts_config["cpuct"]),
+            dirichlet_alpha=float(mcts_config.get("dirichlet_alpha", 0.4)),
+            dirichlet_epsilon=float(mcts_config.get("dirichlet_epsilon", 0.25)),
+            turns_until_tau0=int(mcts_config.get("turns_until_tau0", 15)),
+            testing=bool(mcts_config.get("testing", False)),
+        )
+        m.update(kw)
+        return cls(**m)
+
+
+@dataclass
+class Trajectories:
+    """Packed examples of completed games, on the device they were produced on."""
+    states: torch.Tensor    # int32 [M, 32]  state before the search of that move (trainer.py:473)
+    visits: torch.Tensor    # int16 [M, 143] root visit counts (pi = visits / sum)
+    z: torch.Tensor         # float32 [M]    outcome from the mover's perspective (trainer.py:523-528)
+    game_id: torch.Tensor   # int64 [M]
+    move_no: torch.Tensor   # int32 [M]
+    stats: dict = field(default_factory=dict)
+
+    def __len__(self):
+        return int(self.states.shape[0])
+
+    def pi(self):
+        v = self.visits.to(torch.float64)
+        return (v / v.sum(dim=1, keepdim=True).clamp_min(1)).to(torch.float32)   # trainer.py:535
+
+    def encode(self, dtype=torch.float32):
+        """(board [M,38,5,7], glob [M,42]) via hz_encode — needs the tensors on a CUDA device."""
+        return hb.encode(self.states.contiguous(), dtype=dtype)
+
+    def to_reference_examples(self):
+        """list[(board, global, pi, z)] of CPU tensors, exactly what self_play_worker returns
+        and ReplayBuffer.extend consumes (trainer.py:127,531-538; buffer.py:55-67)."""
+        if len(self) == 0:
+            return []
+        board, glob = self.encode()
+        board, glob, pi, z = board.cpu(), glob.cpu(), self.pi().cpu(), self.z.cpu().view(-1, 1)
+        return [(board[i], glob[i], pi[i], z[i]) for i in range(len(self))]
+
+    def to(self, device):
+        return Trajectories(self.states.to(device), self.visits.to(device), self.z.to(device),
+                            self.game_id.to(device), self.move_no.to(device), dict(self.stats))
+
+
+class BatchedSelfPlay:
+    def __init__(self, net, cfg: SelfPlayConfig, device="cuda"):
+        self.net, self.cfg = net, cfg
+        self.device = torch.device(device)
+        B = cfg.n_slots
+        self.tree = BatchedMCTS(B, cfg.num_simulations, device=self.device, key_mode=cfg.key_mode, max_nodes=cfg.max_nodes)
+        dt = net.dtype
+        cl = net.device.type == "cuda"
+        self.board = torch.zeros((B, 38, 5, 7), dtype=dt, device=self.device,
+                                 memory_format=torch.channels_last if cl else torch.contiguous_format)
+        self.glob = torch.zeros((B, 42), dtype=dt, device=self.device)
+        self.logits = torch.zeros((B, 143), dtype=torch.float32, device=self.device)
+        self.value = torch.zeros(B, dtype=torch.float32, device=self.device)
+        self.noise = None if cfg.testing else torch.ones((B, 143), dtype=torch.float32, device=self.device)
+        self.alpha = None if cfg.testing else torch.full((B, 143), cfg.dirichlet_alpha, dtype=torch.float32, device=self.device)
+        self.graph = None
+        self.sims_run = 0
+
+    # ---- one simulation for every tree --------------------------------------------------
+    def _sim_step(self):
+        t = self.tree
+        t.select(self.cfg.cpuct, self.board, self.glob, dtype=self.net.dtype, channels_last=True)
+        logits, value = self.net(self.board, self.glob)
+        self.logits.copy_(logits)
+        self.value.copy_(value)
+        t.expand_backup(self.logits, self.value, is_logits=True, noise=self.noise, eps=self.cfg.dirichlet_epsilon)
+
+    def _capture(self):
+        """Warm up (cuDNN algorithm selection must happen outside capture) and capture one
+        simulation step in a CUDA graph."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._sim_step()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._sim_step()
+        self.graph = g
+
+    def search(self, states):
+        """One full search per slot from ``states`` (get_best_action_and_pi up to the root
+        statistics, MCTS.py:288-352)."""
+        cfg = self.cfg
+        self.tree.reset(states)
+        if self.noise is not None:
+            # unnormalised Dirichlet: i.i.d. Gamma(alpha); the expand kernel normalises over
+            # the legal root moves (MCTS.py:314-316)
+            self.noise.copy_(torch._standard_gamma(self.alpha)).clamp_min_(1e-30)
+        if cfg.use_cuda_graph and self.graph is None:
+            self._capture()
+            self.tree.reset(states)   # the warm-up/capture advanced the trees
+        for _ in range(cfg.num_simulations):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._sim_step()
+        self.sims_run += cfg.num_simulations
+
+    # ---- whole games ---------------------------------------------------------------------
+    def play(self, num_games, progress=None):
+        """Play ``num_games`` complete games (ids first_game_id .. +num_games-1).  Returns
+        Trajectories with ``stats`` (sims, seconds, sims_per_s, games, examples)."""
+        cfg, dev, B = self.cfg, self.device, self.cfg.n_slots
+        started = min(B, num_games)
+        states = hb.init_states(B, device=dev, seed=cfg.seed, first_id=cfg.first_game_id)
+        game_id = torch.arange(B, device=dev, dtype=torch.int64)        # local ids
+        live = game_id < started
+        outcome = torch.zeros(num_games, dtype=torch.int8, device=dev)
+        finished = torch.zeros(num_games, dtype=torch.bool, device=dev)
+        chunks, bad_status = [], torch.zeros((), dtype=torch.uint8, device=dev)
+        live_sims = 0
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        step = 0
+        while True:
+            over, oc = hb.outcome(states)
+            done = over.bool() & live
+            n_done = int(done.sum().item())                      # one host sync per move
+            if n_done:
+                ids = game_id[done]
+                outcome[ids] = oc[done]
+                finished[ids] = True
+                k = min(n_done, num_games - started)
+                slots = torch.nonzero(done).flatten()
+                if k:
+                    fresh = hb.init_states(k, device=dev, seed=cfg.seed, first_id=cfg.first_game_id + started)
+                    states[slots[:k]] = fresh
+                    game_id[slots[:k]] = torch.arange(started, started + k, device=dev, dtype=torch.int64)
+                    started += k
+                live[slots[k:]] = False
+            n_live = int(live.sum().item())
+            if n_live == 0:
+                break
+            move_no = states[:, 27].clone()
+            if int(move_no[live].max().item()) >= cfg.max_moves:
+                raise RuntimeError("a game exceeded max_moves without ending")
+            snap = states.clone()
+            self.search(states)
+            visits, _ = self.tree.root_policy()
+            expl = None
+            u01 = None
+            if not cfg.testing and cfg.turns_until_tau0 > 0:
+                expl = (move_no < cfg.turns_until_tau0).to(torch.uint8)   # MCTS.py:399-402
+                u01 = torch.rand(B, device=dev, dtype=torch.float32)
+            actions = self.tree.choose(u01, expl)
+            actions = torch.where(live, actions, torch.full_like(actions, -1))
+            status = hb.apply(states, actions)                   # the real move re-draws independently (trainer.py:502)
+            bad_status = torch.maximum(bad_status, torch.where(live, status, torch.zeros_like(status)).max())
+            chunks.append((snap, visits.to(torch.int16), game_id.clone(), move_no, live.clone()))
+            live_sims += n_live * cfg.num_simulations
+            step += 1
+            if step % 8 == 0:
+                self.tree.check_status()
+            if progress:
+                progress(step, int(finished.sum().item()), num_games)
+        self.tree.check_status()
+        if int(bad_status.item()) != 0:
+            raise RuntimeError(f"engine rejected a searched move (status {int(bad_status.item())})")
+        torch.cuda.synchronize(dev)
+        secs = time.perf_counter() - t0
+        if chunks:
+            S = torch.cat([c[0] for c in chunks]); V = torch.cat([c[1] for c in chunks])
+            G = torch.cat([c[2] for c in chunks]); M = torch.cat([c[3] for c in chunks]); L = torch.cat([c[4] for c in chunks])
+            keep = L & finished[G.clamp_max(num_games - 1)]
+            S, V, G, M = S[keep], V[keep], G[keep], M[keep]
+            mover = ((S[:, 22] >> 24) & 1).to(torch.float32)
+            z = outcome[G].to(torch.float32) * (1.0 - 2.0 * mover)   # trainer.py:523-528
+        else:
+            S = torch.empty((0, 32), dtype=torch.int32, device=dev); V = torch.empty((0, 143), dtype=torch.int16, device=dev)
+            G = torch.empty(0, dtype=torch.int64, device=dev); M = torch.empty(0, dtype=torch.int32, device=dev)
+            z = torch.empty(0, dtype=torch.float32, device=dev)
+        stats = {"sims": live_sims, "seconds": secs, "sims_per_s": live_sims / secs if secs > 0 else 0.0,
+                 "games": int(finished.sum().item()), "examples": int(S.shape[0]), "move_steps": step}
+        return Trajectories(S, V, z, G + cfg.first_game_id, M, stats)

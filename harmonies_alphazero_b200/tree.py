@@ -41,10 +41,11 @@ class BatchedMCTS:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def reset(self, root_states, search_keys):
-        """New search per tree (no tree reuse, MCTS.py:288-289).  search_keys int64[n]."""
-        assert root_states.shape == (self.n, 32) and root_states.dtype == torch.int32
-        assert search_keys.shape == (self.n,) and search_keys.dtype == torch.int64
+    def reset(self, root_states, search_keys=None):
+        """New search per tree (no tree reuse, MCTS.py:288-289).  search_keys int64[n] or None
+        (derived per (game, move) from the root's own rng key and move counter)."""
+        assert root_states.shape == (self.n, 32) and root_states.dtype == torch.int32 and root_states.is_contiguous()
+        assert search_keys is None or (search_keys.shape == (self.n,) and search_keys.dtype == torch.int64)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.hz_tree_reset(self.handle, _ptr(root_states), _ptr(search_keys), self._stream()), "hz_tree_reset")
 

@@ -212,7 +212,9 @@ int hz_tree_destroy(hz_tree *t);
 /* Start a new search per tree (get_best_action_and_pi, MCTS.py:288-289: no tree reuse).
  * root_states: [n_trees] packed states; search_keys: [n_trees] uint64, the key of the
  * in-tree draw stream: child of action a expanded in simulation s (0-based) draws event
- * (s<<8)|a. */
+ * (s<<8)|a.  search_keys == NULL -> key = rand(state key ^ HZ_SEARCH_SALT, state moves), a
+ * stream per (game, move) that is independent of the game's own draws (the reference
+ * re-draws the real move independently of the tree's sample, trainer.py:502). */
 int hz_tree_reset(hz_tree *t, const void *root_states, const uint64_t *search_keys,
                   void *stream);
 
@@ -257,6 +259,7 @@ int hz_tree_root_edges(hz_tree *t, int32_t *N, double *W, float *P, int32_t *chi
                        void *stream);
 
 #define HZ_PLAYOUT_SALT 0xA5A5F00DC0FFEE11ull
+#define HZ_SEARCH_SALT  0x5EA2C47EE5A17B00ull
 
 #ifdef __cplusplus
 }

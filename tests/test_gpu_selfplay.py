@@ -1,0 +1,157 @@
+"""GPU: the batched self-play driver (replacement of trainer.py:62-134,434-541) and MCTS
+parity with a real network: fp32 net outputs captured once and fed to both sides
+(SURVEY.md §8d cfg 4 parity sub-run)."""
+
+import numpy as np
+import pytest
+import torch
+
+from harmonies_alphazero_b200 import packed as pk
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from harmonies_alphazero_b200 import batched, net, selfplay, tree
+
+    batched._lib.load()
+    return batched, net, selfplay, tree
+
+
+def _small_net(net, dtype, seed=0):
+    torch.manual_seed(seed)
+    m = net.AlphaZeroNet.from_config(net.TEST_MODEL_CONFIG)
+    for mod in m.modules():   # non-trivial BatchNorm statistics so that folding is exercised
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.3); mod.running_var.uniform_(0.5, 1.5)
+            mod.weight.data.uniform_(0.5, 1.5); mod.bias.data.normal_(0, 0.2)
+    m.eval()
+    return m, net.InferenceNet(m, device="cuda", dtype=dtype)
+
+
+def test_inference_net_matches_module(mods):
+    hb, net, _, _ = mods
+    m, inf = _small_net(net, torch.float32)
+    st = hb.init_states(300, seed=1)
+    hb.playout(st, max_steps=23)
+    board, glob = hb.encode(st, channels_last=True)
+    with torch.no_grad():
+        l_ref, v_ref = m.cuda()(board.contiguous(), glob)
+    l, v = inf(board, glob)
+    assert torch.allclose(l, l_ref, atol=2e-4, rtol=1e-4) and torch.allclose(v, v_ref.view(-1), atol=1e-4)
+    # bf16 path: same function at reduced precision
+    _, inf16 = _small_net(net, torch.bfloat16)
+    b16, g16 = hb.encode(st, dtype=torch.bfloat16, channels_last=True)
+    l16, v16 = inf16(b16, g16)
+    assert (torch.softmax(l16, 1) - torch.softmax(l_ref, 1)).abs().max() < 0.05
+    assert (v16 - v_ref.view(-1)).abs().max() < 0.1
+
+
+def test_search_with_real_net_matches_oracle(mods, oracle):
+    """64 games x first 8 moves x 24 simulations, fp32 network, testing=True: the GPU tree
+    and the reference-semantics oracle see identical (P, v) per leaf and must produce
+    identical visit counts (tolerance: none) and pi within 1e-6."""
+    hb, net, _, tr = mods
+    _, inf = _small_net(net, torch.float32, seed=3)
+    n, sims, cpuct = 64, 24, 2.0
+    states = hb.init_states(n, seed=42)
+    tree = tr.BatchedMCTS(n, sims)
+    board = torch.empty((n, 38, 5, 7), device="cuda").contiguous(memory_format=torch.channels_last)
+    glob = torch.empty((n, 42), device="cuda")
+    leaf = torch.empty((n, 32), dtype=torch.int32, device="cuda")
+    for move in range(8):
+        roots = states.cpu().numpy().view(np.uint32).copy()
+        skeys = np.array([pk.rand(int(k), move) for k in range(1000, 1000 + n)], dtype=np.uint64)
+        tree.reset(states, tr.search_keys_tensor(skeys))
+        seen = [dict() for _ in range(n)]
+        for s in range(sims):
+            tree.select(cpuct, board, glob, leaf, channels_last=True)
+            logits, value = inf(board, glob)
+            probs = torch.softmax(logits, dim=1).contiguous()       # model.py:104
+            lw = leaf.cpu().numpy().view(np.uint32)
+            pn, vn = probs.cpu().numpy(), value.cpu().numpy()
+            for i in range(n):
+                seen[i][pk.canon_hash(lw[i])] = (pn[i], float(vn[i]))
+            tree.expand_backup(probs, value)
+        tree.check_status()
+        N = tree.root_edges()[0].cpu().numpy()
+        visits, pi = (x.cpu().numpy() for x in tree.root_policy())
+        for i in range(n):
+            r = oracle.search(roots[i], skeys[i], sims, cpuct, eval_fn=lambda w, d=seen[i]: d[pk.canon_hash(w)])
+            assert np.array_equal(N[i], r["N"]), (move, i)
+            tot = r["N"].sum()
+            assert np.abs(pi[i] - r["N"] / max(tot, 1)).max() <= 1e-6
+        states_before = states.clone()
+        hb.apply(states, tree.choose())
+        assert not torch.equal(states, states_before)
+
+
+def test_selfplay_games_and_example_contract(mods, oracle):
+    hb, net, sp, _ = mods
+    _, inf = _small_net(net, torch.bfloat16, seed=5)
+    cfg = sp.SelfPlayConfig(n_slots=96, num_simulations=8, turns_until_tau0=6, seed=11)
+    torch.manual_seed(0)
+    driver = sp.BatchedSelfPlay(inf, cfg)
+    traj = driver.play(150)
+    st = traj.stats
+    assert st["games"] == 150 and st["examples"] == len(traj) and st["sims"] > 0
+    gid = traj.game_id.cpu().numpy(); mv = traj.move_no.cpu().numpy()
+    S = traj.states.cpu().numpy().view(np.uint32); V = traj.visits.cpu().numpy(); z = traj.z.cpu().numpy()
+    assert sorted(set(gid.tolist())) == list(range(150))
+    assert (V.sum(axis=1) == cfg.num_simulations - 1).all()          # sum N = S-1 (MCTS.py:355-381)
+    pi = traj.pi().cpu().numpy()
+    assert np.allclose(pi.sum(axis=1), 1.0, atol=1e-6)
+    # visits only on legal actions of the recorded state
+    legal = oracle.legal_mask(S)
+    for i in range(0, len(S), 37):
+        acts = set(pk.mask_to_actions(legal[i]))
+        assert set(np.nonzero(V[i])[0].tolist()) <= acts
+    # per game: consecutive move numbers from 0, z = +-outcome by mover, successive states are
+    # one legal move apart (boards/hand/piles evolve legally)
+    for g in range(0, 150, 7):
+        idx = np.nonzero(gid == g)[0]
+        idx = idx[np.argsort(mv[idx])]
+        assert mv[idx].tolist() == list(range(len(idx)))
+        movers = (S[idx, 22] >> 24) & 1
+        zz = z[idx]
+        assert set(np.unique(np.abs(zz)).tolist()) <= {0.0, 1.0}
+        if np.abs(zz).max() > 0:
+            assert (zz[movers == 0] == zz[movers == 0][0]).all() and (zz[movers == 1] == -zz[movers == 0][0]).all()
+        for a, b in zip(idx[:-1], idx[1:]):
+            cand_actions = pk.mask_to_actions(legal[a])
+            nxt, stt = oracle.apply(np.repeat(S[a][None], len(cand_actions), 0), np.array(cand_actions, dtype=np.int16))
+            same_board = [(nxt[k, :18] == S[b, :18]).all() and (nxt[k, 20] >> 16) == (S[b, 20] >> 16) for k in range(len(cand_actions))]
+            assert any(same_board)
+    # reference example contract (trainer.py:531-538)
+    ex = traj.to_reference_examples()
+    assert len(ex) == len(traj)
+    b, gl, p, zz = ex[0]
+    assert b.shape == (38, 5, 7) and gl.shape == (42,) and p.shape == (143,) and zz.shape == (1,)
+    assert b.dtype == gl.dtype == p.dtype == zz.dtype == torch.float32 and not b.is_cuda
+    ob, og = oracle.encode(S[:1])
+    assert np.array_equal(b.numpy(), ob[0]) and np.array_equal(gl.numpy(), og[0])
+
+
+def test_selfplay_is_independent_of_slot_count_in_testing_mode(mods):
+    """deterministic mode: the same game ids give the same trajectories whatever the batch
+    shape (keys are per game id, search keys per (game, move))."""
+    hb, net, sp, _ = mods
+
+    class ElementwiseNet:   # row-wise elementwise function: bitwise independent of the batch shape
+        dtype, device = torch.float32, torch.device("cuda")
+
+        def __call__(self, board, glob):
+            a = torch.arange(143, device=glob.device, dtype=torch.float32)
+            x = glob[:, 36:42].repeat(1, 24)[:, :143] * 3.0 + glob[:, 30:36].repeat(1, 24)[:, :143]
+            logits = torch.sin(a * 0.37 + x * 5.0) + board[:, 36, 2, 3].unsqueeze(1) * torch.cos(a)
+            return logits, torch.tanh(glob[:, 36] * 3.0 - glob[:, 41] * 2.0 - glob[:, 33])
+
+    inf = ElementwiseNet()
+    out = []
+    for slots in (16, 40):
+        cfg = sp.SelfPlayConfig(n_slots=slots, num_simulations=6, testing=True, seed=3, use_cuda_graph=(slots == 40))
+        t = sp.BatchedSelfPlay(inf, cfg).play(24)
+        order = torch.argsort(t.game_id * 1000 + t.move_no.to(torch.int64))
+        out.append((t.states[order].cpu(), t.visits[order].cpu(), t.z[order].cpu()))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
