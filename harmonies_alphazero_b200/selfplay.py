@@ -100,8 +100,8 @@ class BatchedSelfPlay:
         self.tree = BatchedMCTS(B, cfg.num_simulations, device=self.device, key_mode=cfg.key_mode, max_nodes=cfg.max_nodes)
         dt = net.dtype
         cl = net.device.type == "cuda"
-        self.board = torch.zeros((B, 38, 5, 7), dtype=dt, device=self.device,
-                                 memory_format=torch.channels_last if cl else torch.contiguous_format)
+        self.board = torch.empty((B, 38, 5, 7), dtype=dt, device=self.device,
+                                 memory_format=torch.channels_last if cl else torch.contiguous_format).zero_()
         self.glob = torch.zeros((B, 42), dtype=dt, device=self.device)
         self.logits = torch.zeros((B, 143), dtype=torch.float32, device=self.device)
         self.value = torch.zeros(B, dtype=torch.float32, device=self.device)
