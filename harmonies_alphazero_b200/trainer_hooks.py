@@ -1,0 +1,69 @@
+"""Batch-level drop-in (boundary b2 of SURVEY.md §8): replacements for the bodies of
+``Trainer.execute_self_play_phase`` (trainer.py:62-134) and ``self_play_worker``
+(trainer.py:434-541) that run the games on the GPU core and hand the reference's
+replay buffer exactly the tuples it expects.
+
+    import trainer                                  # the reference module
+    from harmonies_alphazero_b200 import trainer_hooks
+    trainer_hooks.install(trainer)                  # Trainer now self-plays on the B200
+"""
+
+import time
+
+import torch
+
+from .net import AlphaZeroNet, InferenceNet
+from .selfplay import BatchedSelfPlay, SelfPlayConfig
+
+
+def _inference_net(model, device, dtype):
+    return InferenceNet(model, device=device, dtype=dtype)
+
+
+def execute_self_play_phase(self, data_generating_manager, n_slots=4096, dtype=torch.bfloat16, device="cuda"):
+    """Bound as a method of the reference ``Trainer``.  Same contract as trainer.py:62-134:
+    plays ``num_games_per_iter`` games with the data-generating (best) model and extends
+    ``self.replay_buffer`` with (board, global, pi, z) CPU tensors of every completed game."""
+    num_games = int(self.self_play_config["num_games_per_iter"])
+    print(f"\n--- Starting Self-Play Phase ({num_games} games, batched on {device}) ---")
+    t0 = time.time()
+    model = data_generating_manager.model
+    was_training = model.training
+    model.eval()
+    net = _inference_net(model, device, dtype)
+    cfg = SelfPlayConfig.from_mcts_config(self.mcts_config, n_slots=max(1, min(n_slots, num_games)))
+    traj = BatchedSelfPlay(net, cfg, device=device).play(num_games)
+    examples = traj.to_reference_examples()
+    self.replay_buffer.extend(examples)                      # trainer.py:127
+    if was_training:
+        model.train()
+    print("--- Self-Play Finished ---")
+    print(f"  Completed {traj.stats['games']}/{num_games} games.")
+    print(f"  Added {len(examples)} examples.")
+    print(f"  Buffer size: {len(self.replay_buffer)} / {self.replay_buffer.maxlen}")
+    print(f"  Time taken: {time.time() - t0:.2f} seconds ({traj.stats['sims_per_s']:.0f} sims/s)")
+    return traj.stats
+
+
+def self_play_worker(args):
+    """Signature-compatible with trainer.py:434: (state_dict, model_config, training_config,
+    mcts_config, worker_device) -> list of (board, global, pi, z) for ONE game, [] on error."""
+    model_state_dict, model_config, _training_config, mcts_config, worker_device = args
+    try:
+        model = AlphaZeroNet.from_config(model_config)
+        model.load_state_dict(model_state_dict)
+        model.eval()
+        dev = "cuda" if str(worker_device) in ("cpu", "mps") else worker_device   # the engine is GPU-only
+        net = _inference_net(model, dev, torch.float32)
+        cfg = SelfPlayConfig.from_mcts_config(mcts_config, n_slots=1, use_cuda_graph=False)
+        return BatchedSelfPlay(net, cfg, device=dev).play(1).to_reference_examples()
+    except Exception as e:  # noqa: BLE001  (the reference worker also returns [] on any failure, trainer.py:459-514)
+        print(f"WORKER ERROR: {e}")
+        return []
+
+
+def install(trainer_module):
+    """Monkey-patch the reference ``trainer`` module in place."""
+    trainer_module.Trainer.execute_self_play_phase = execute_self_play_phase
+    trainer_module.self_play_worker = self_play_worker
+    return trainer_module
