@@ -233,11 +233,39 @@ def mcts_measure(args, dev, world, rank, dist):
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
+    direct_launches = hb.launch_count() - l0
     drv.tree.check_status()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
+    collectives = None
+    if dist is not None:
+        # configs[4]: NCCL weight broadcast + packed trajectory gather, once per training step
+        from harmonies_alphazero_b200 import dist as hzdist
+
+        model_dev = model.to(dev)
+        n_ex = B * 62 // 8                        # examples a rank produces between two training steps (B/8 games)
+        traj = sp.Trajectories(
+            states=states[:1].repeat(n_ex, 1), visits=torch.zeros((n_ex, 143), dtype=torch.int16, device=dev),
+            z=torch.zeros(n_ex, device=dev), game_id=torch.arange(n_ex, device=dev, dtype=torch.int64),
+            move_no=torch.zeros(n_ex, dtype=torch.int32, device=dev))
+        for _ in range(2):
+            hzdist.broadcast_weights(model_dev, src=0, dtype=torch.bfloat16)
+            hzdist.gather_trajectories(traj, dst=0)
+        torch.cuda.synchronize(); dist.barrier()
+        c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        c0.record()
+        wbytes = hzdist.broadcast_weights(model_dev, src=0, dtype=torch.bfloat16)
+        c1.record()
+        g = hzdist.gather_trajectories(traj, dst=0)
+        c2.record()
+        torch.cuda.synchronize()
+        tms = torch.tensor([c0.elapsed_time(c1), c1.elapsed_time(c2)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        collectives = {"weight_broadcast_ms": float(tms[0]), "weight_bytes": wbytes,
+                       "trajectory_gather_ms": float(tms[1]), "examples_per_rank": n_ex,
+                       "bytes_per_example": g.stats.get("bytes_per_example"), "backend": "nccl"}
     sims = B * S * K * world
     v = sims / (ms * 1e-3)
     pk, pk_src = peaks()
@@ -247,7 +275,9 @@ def mcts_measure(args, dev, world, rank, dist):
             "config": {"workload": "MCTS self-play, model.py net 128f x 8 blocks random-init, bf16, "
                                    f"{S} sims/move, {B} concurrent games per GPU (configs[3])",
                        "fused_conv": inf.fused, "cuda_graph": drv.graph is not None},
-            "dtype": "bf16", "gpu_launches_own": hb.launch_count() - l0,
+            "dtype": "bf16", "collectives": collectives,
+            # direct C-ABI launches + the two tree kernels replayed inside the CUDA graph per simulation
+            "gpu_launches_own": (direct_launches + (2 * S * K if drv.graph is not None else 0)) * world,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
                          "peak_source": pk_src + " (sustained cuBLAS bf16)",
