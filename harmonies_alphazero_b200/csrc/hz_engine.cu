@@ -141,10 +141,12 @@ __global__ void __launch_bounds__(PTPB) k_playout(void* states, int64_t n, int m
 constexpr int ENC_S = 8;      // states per block iteration
 constexpr int ENC_TPB = 256;
 template <typename T, bool NHWC>
-__global__ void __launch_bounds__(ENC_TPB) k_encode(const void* states, int64_t n, T* board, T* glob) {
+__global__ void __launch_bounds__(ENC_TPB) k_encode(const void* states, int64_t n, T* board, T* glob, int vec_ok) {
     __shared__ uint32_t smask[ENC_S][40];
     __shared__ float sphase[ENC_S];
     __shared__ float sglob[ENC_S][42];
+    __shared__ uint8_t scell[36];   // shared copy: per-lane indices into __constant__ would serialise
+    if (threadIdx.x < 35) scell[threadIdx.x] = CELL_HEX[threadIdx.x];
     const uint32_t* W = reinterpret_cast<const uint32_t*>(states);
     int64_t n_chunks = (n + ENC_S - 1) / ENC_S;
     for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
@@ -161,14 +163,34 @@ __global__ void __launch_bounds__(ENC_TPB) k_encode(const void* states, int64_t 
             }
         }
         __syncthreads();
+        // Write-bound part: every thread emits one 16-byte vector (4 fp32 / 8 bf16) per store.
+        // A chunk of 8 states is 8*1330 elements = a whole number of vectors and starts
+        // 16-byte aligned; a ragged last chunk falls back to scalar stores.
         T* bout = board + base * 1330;
-        for (int e = threadIdx.x; e < cnt * 1330; e += ENC_TPB) {
+        constexpr int VEC = 16 / (int)sizeof(T);
+        int total = cnt * 1330;
+        int nvec = (cnt == ENC_S && vec_ok) ? total / VEC : 0;
+        for (int v = threadIdx.x; v < nvec; v += ENC_TPB) {
+            int e = v * VEC;
             int s = e / 1330, r = e - 1330 * s;
             int c, cell;
             if (NHWC) { cell = r / 38; c = r - 38 * cell; } else { c = r / 35; cell = r - 35 * c; }
-            uint32_t bit = (smask[s][c] >> CELL_HEX[cell]) & 1u;     // bit 31 is never set: masked cells
-            float v = bit ? (c == 37 ? sphase[s] : 1.0f) : 0.0f;
-            bout[e] = cvt<T>(v);
+            alignas(16) T vals[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; j++) {
+                uint32_t bit = (smask[s][c] >> scell[cell]) & 1u;    // bit 31 is never set: masked cells
+                vals[j] = cvt<T>(bit ? (c == 37 ? sphase[s] : 1.0f) : 0.0f);
+                if (NHWC) { if (++c == 38) { c = 0; if (++cell == 35) { cell = 0; s++; } } }
+                else      { if (++cell == 35) { cell = 0; if (++c == 38) { c = 0; s++; } } }
+            }
+            reinterpret_cast<uint4*>(bout)[v] = *reinterpret_cast<const uint4*>(vals);
+        }
+        for (int e = nvec * VEC + threadIdx.x; e < total; e += ENC_TPB) {
+            int s = e / 1330, r = e - 1330 * s;
+            int c, cell;
+            if (NHWC) { cell = r / 38; c = r - 38 * cell; } else { c = r / 35; cell = r - 35 * c; }
+            uint32_t bit = (smask[s][c] >> scell[cell]) & 1u;
+            bout[e] = cvt<T>(bit ? (c == 37 ? sphase[s] : 1.0f) : 0.0f);
         }
         T* gout = glob + base * 42;
         for (int e = threadIdx.x; e < cnt * 42; e += ENC_TPB) gout[e] = cvt<T>(sglob[e / 42][e % 42]);
@@ -225,12 +247,13 @@ int hz_encode(const void* states, int64_t n, void* board, void* glob, int dtype,
     int64_t chunks = (n + ENC_S - 1) / ENC_S;
     int grid = (int)(chunks < 148 * 8 ? chunks : 148 * 8);
     cudaStream_t st = (cudaStream_t)stream;
+    int vec_ok = ((uintptr_t)board & 15) == 0;   // 16-byte vector stores need an aligned base
     if (dtype == HZ_DTYPE_F32) {
-        if (layout == HZ_LAYOUT_NCHW) k_encode<float, false><<<grid, ENC_TPB, 0, st>>>(states, n, (float*)board, (float*)glob);
-        else k_encode<float, true><<<grid, ENC_TPB, 0, st>>>(states, n, (float*)board, (float*)glob);
+        if (layout == HZ_LAYOUT_NCHW) k_encode<float, false><<<grid, ENC_TPB, 0, st>>>(states, n, (float*)board, (float*)glob, vec_ok);
+        else k_encode<float, true><<<grid, ENC_TPB, 0, st>>>(states, n, (float*)board, (float*)glob, vec_ok);
     } else {
-        if (layout == HZ_LAYOUT_NCHW) k_encode<__nv_bfloat16, false><<<grid, ENC_TPB, 0, st>>>(states, n, (__nv_bfloat16*)board, (__nv_bfloat16*)glob);
-        else k_encode<__nv_bfloat16, true><<<grid, ENC_TPB, 0, st>>>(states, n, (__nv_bfloat16*)board, (__nv_bfloat16*)glob);
+        if (layout == HZ_LAYOUT_NCHW) k_encode<__nv_bfloat16, false><<<grid, ENC_TPB, 0, st>>>(states, n, (__nv_bfloat16*)board, (__nv_bfloat16*)glob, vec_ok);
+        else k_encode<__nv_bfloat16, true><<<grid, ENC_TPB, 0, st>>>(states, n, (__nv_bfloat16*)board, (__nv_bfloat16*)glob, vec_ok);
     }
     return hz_launched(1);
 }
