@@ -67,6 +67,17 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
 __host__ __device__ __forceinline__ uint64_t rand64(uint64_t key, uint64_t ctr) {
     return mix64(key ^ mix64(ctr + 0x9E3779B97F4A7C15ull));
 }
+// The inner mix depends on the counter only, and counters are small (move numbers < 200, draw
+// events*8+k < 400): a per-block shared table of the first RTAB_N inner values halves the cost
+// of every random number in the fused playout.  rtab == nullptr computes it.
+constexpr int RTAB_N = 512;
+__device__ __forceinline__ void build_rand_table(uint64_t* rtab) {
+    for (int i = threadIdx.x; i < RTAB_N; i += blockDim.x) rtab[i] = mix64((uint64_t)i + 0x9E3779B97F4A7C15ull);
+}
+__device__ __forceinline__ uint64_t rand64_t(const uint64_t* rtab, uint64_t key, uint64_t ctr) {
+    uint64_t inner = (rtab != nullptr && ctr < (uint64_t)RTAB_N) ? rtab[ctr] : mix64(ctr + 0x9E3779B97F4A7C15ull);
+    return mix64(key ^ inner);
+}
 
 // ---- state access -------------------------------------------------------------------------
 __device__ __forceinline__ void load_state(State& s, const void* base, int64_t idx) {
@@ -146,6 +157,14 @@ struct Legal {
     uint32_t m[6];
     int n_piles;  // choose phase: number of selectable piles (else 0)
 };
+// REL ("mover-relative", fused playout only): words 0..8 always hold the board of the player to
+// move and 9..17 the other one; the halves are swapped whenever the player changes, so board
+// access needs no per-word select on the player bit.  swap_boards() converts both ways.
+__device__ __forceinline__ void swap_boards(State& s) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) { uint32_t x = s.w[k]; s.w[k] = s.w[9 + k]; s.w[9 + k] = x; }
+}
+template <bool REL = false>
 __device__ __forceinline__ Legal legal_of(const State& s) {
     Legal L;
 #pragma unroll
@@ -156,7 +175,7 @@ __device__ __forceinline__ Legal legal_of(const State& s) {
         L.n_piles = n_piles_of(s);                                   // :158
     } else if (ph <= HZ_PHASE_PLACE3) {
         uint32_t hand = hand_of(s);
-        Tops t = tops_of(board_of(s, player_of(s)));
+        Tops t = tops_of(board_of(s, REL ? 0 : player_of(s)));
         uint32_t empty = ~t.occ0 & VALID;                            // :173
         uint32_t on_plant = top_wood(t) & ~t.occ2;                   // :183  (h <= 2)
         uint32_t on_stone = top_stone(t) & ~t.occ2;                  // :186  (h < 3)
@@ -213,10 +232,10 @@ __device__ __forceinline__ int kth_action(const Legal& L, int k) {
     return 5 + 23 * t + nth_set_bit(m, k - below);
 }
 // the uniform-random playout policy (see hz_random_actions in harmonies_b200.h)
-__device__ __forceinline__ int random_action(const State& s, const Legal& L) {
+__device__ __forceinline__ int random_action(const State& s, const Legal& L, const uint64_t* rtab = nullptr) {
     int n = legal_count(L);
     if (n == 0) return -1;
-    uint64_t r = rand64(key_of(s) ^ HZ_PLAYOUT_SALT, (uint64_t)s.w[HZ_W_MOVES]);
+    uint64_t r = rand64_t(rtab, key_of(s) ^ HZ_PLAYOUT_SALT, (uint64_t)s.w[HZ_W_MOVES]);
     int k = (int)(((r >> 32) * (uint64_t)n) >> 32);
     return kth_action(L, k);
 }
@@ -237,41 +256,36 @@ __device__ __forceinline__ void score_board(const NbrLut* lut, const Board& b, i
     uint32_t tp = top_plant(t);
     uint32_t l0_wood = b.p[0] & b.p[1] & ~b.p[2], l1_wood = b.p[3] & b.p[4] & ~b.p[5];
     terms[0] = __popc(tp & h1) + 3 * __popc(tp & h2 & l0_wood) + 7 * __popc(tp & h3 & l0_wood & l1_wood);
+    // One neighbour expansion per top type serves every term: n_X = hexes adjacent to an X-top.
+    uint32_t tw = top_water(t), twd = top_wood(t), ts = top_stone(t), tbl = top_building(t), tf = top_field(t);
+    uint32_t n_w = nbr(lut, tw), n_p = nbr(lut, tp), n_wd = nbr(lut, twd), n_s = nbr(lut, ts);
+    uint32_t n_b = nbr(lut, tbl), n_f = nbr(lut, tf);
     // mountains :392-413
-    uint32_t ts = top_stone(t);
-    uint32_t adj = ts & nbr(lut, ts);
+    uint32_t adj = ts & n_s;
     terms[1] = __popc(adj & h1) + 3 * __popc(adj & h2) + 7 * __popc(adj & h3);
-    // fields :424-443
+    // buildings :454-469 — >= 3 distinct top types among the neighbours, for all hexes at once:
+    // bit-sliced count of the six adjacency masks (two full adders), no per-hex loop
+    uint32_t s1 = n_w ^ n_p ^ n_wd, c1 = (n_w & n_p) | (n_wd & (n_w ^ n_p));
+    uint32_t s2 = n_s ^ n_b ^ n_f, c2 = (n_s & n_b) | (n_f & (n_s ^ n_b));
+    uint32_t atleast3 = (c1 & c2) | ((c1 | c2) & (s1 | s2));
+    terms[3] = 5 * __popc(tbl & h2 & atleast3);
+    // fields :424-443 — isolated hexes (size-1 components) are dropped up front, so every
+    // flood below is a component of size >= 2
     int sc = 0;
-    uint32_t rem = top_field(t);
+    uint32_t rem = tf & n_f;
     while (rem) {
         uint32_t comp = flood(lut, rem & (0u - rem), rem);
         rem &= ~comp;
-        sc += (comp & (comp - 1)) ? 5 : 0;                           // size >= 2
+        sc += 5;
     }
     terms[2] = sc;
-    // buildings :454-469
-    sc = 0;
-    uint32_t tb = top_building(t) & h2;
-    if (tb) {
-        uint32_t tw = top_water(t), twd = top_wood(t), tf = top_field(t), tbl = top_building(t);
-        while (tb) {
-            uint32_t bit = tb & (0u - tb);
-            tb ^= bit;
-            uint32_t nb = nbr(lut, bit);
-            int kinds = ((tw & nb) != 0) + ((tp & nb) != 0) + ((twd & nb) != 0) + ((ts & nb) != 0) +
-                        ((tbl & nb) != 0) + ((tf & nb) != 0);
-            sc += kinds >= 3 ? 5 : 0;
-        }
-    }
-    terms[3] = sc;
     // water :480-518 — per component of size >= 2: (BFS diameter + 1) -> table
     sc = 0;
-    rem = top_water(t);
+    rem = tw & n_w;
     while (rem) {
         uint32_t comp = flood(lut, rem & (0u - rem), rem);
         rem &= ~comp;
-        if (!(comp & (comp - 1))) continue;
+        if (__popc(comp) == 2) { sc += 2; continue; }                 // diameter 1 -> length 2
         int diameter = 0;
         uint32_t src = comp;
         while (src) {
@@ -372,9 +386,10 @@ __device__ __forceinline__ void finalize_scores(State& s, const NbrLut* lut) {
     uint32_t wc = s0 > s1 ? 1u : s1 > s0 ? 2u : 3u;                       // :348-354
     s.w[HZ_W_BAG1META] = (s.w[HZ_W_BAG1META] & ~(3u << 29)) | (wc << 29);
 }
-template <bool DEFER_SCORE = false>
+template <bool DEFER_SCORE = false, bool REL = false>
 __device__ __forceinline__ int apply_move(State& s, int a, uint32_t explicit_code, uint64_t dkey,
-                                          uint32_t devent, bool bump_event, const NbrLut* lut) {
+                                          uint32_t devent, bool bump_event, const NbrLut* lut,
+                                          const uint64_t* rtab = nullptr) {
     int ph = phase_of(s);
     if (ph == HZ_PHASE_CHOOSE) {
         int np = n_piles_of(s);
@@ -398,7 +413,7 @@ __device__ __forceinline__ int apply_move(State& s, int a, uint32_t explicit_cod
     uint32_t hand = hand_of(s);
     if (((hand >> (2 * tile)) & 3u) == 0) return HZ_MOVE_NOT_IN_HAND;   // :244-248
     int pl = player_of(s);
-    Board b = board_of(s, pl);
+    Board b = board_of(s, REL ? 0 : pl);
     Tops t = tops_of(b);
     uint32_t bit = 1u << hex;
     uint32_t ok = ~t.occ0;                                            // :255-257
@@ -420,7 +435,7 @@ __device__ __forceinline__ int apply_move(State& s, int a, uint32_t explicit_cod
         uint32_t on = (code >> k) & 1u ? 0xFFFFFFFFu : 0u;
         b.p[k] |= at0 & on; b.p[3 + k] |= at1 & on; b.p[6 + k] |= at2 & on;
     }
-    set_board(s, pl, b);
+    set_board(s, REL ? 0 : pl, b);
     hand -= 1u << (2 * tile);                                         // hand.remove, :250
     s.w[HZ_W_PILE4H] = (s.w[HZ_W_PILE4H] & 0xFFFFu) | (hand << 16);
     s.w[HZ_W_MOVES]++;
@@ -436,7 +451,7 @@ __device__ __forceinline__ int apply_move(State& s, int a, uint32_t explicit_cod
     for (int k = 0; np < 5; k++) {                                    // _replenish_piles :132-137
         uint32_t pc;
         if (k == 0 && use_explicit) { pc = explicit_code; bag = bag_minus(bag, pc); }
-        else pc = draw_pile(bag, rand64(dkey, (uint64_t)devent * 8 + (uint64_t)k));
+        else pc = draw_pile(bag, rand64_t(rtab, dkey, (uint64_t)devent * 8 + (uint64_t)k));
         if (pc == 0) break;                                           // :135-136
 #pragma unroll
         for (int j = 0; j < 5; j++) P.p[j] = (j == np) ? pc : P.p[j];
@@ -450,12 +465,14 @@ __device__ __forceinline__ int apply_move(State& s, int a, uint32_t explicit_cod
     uint32_t m = meta(s) & 1u;                                        // keep player
     if (triggered && !ending && pl == 0) {                            // :314-318
         m = 1u | (HZ_PHASE_CHOOSE << 1) | (1u << 4);
+        if (REL) swap_boards(s);
     } else if ((triggered && !ending) || ending) {                    // :319-326
         set_meta(s, m | (HZ_PHASE_OVER << 1) | (1u << 4));            // :320,324 (winner still None)
         if (!DEFER_SCORE) finalize_scores(s, lut);                    // :321-322,325-326
         return HZ_MOVE_OK;
     } else {                                                          // :327-329
         m = (m ^ 1u) | (HZ_PHASE_CHOOSE << 1);
+        if (REL) swap_boards(s);
     }
     set_meta(s, m);
     return HZ_MOVE_OK;

@@ -111,19 +111,23 @@ constexpr int PTPB = 64;   // 65,536 games -> 1024 blocks: 6.9 per SM, <2 % tail
 __global__ void __launch_bounds__(PTPB) k_playout(void* states, int64_t n, int max_steps, uint32_t* steps,
                                                   unsigned long long* total_steps) {
     __shared__ NbrLut lut;
+    __shared__ uint64_t rtab[RTAB_N];
     build_nbr_lut(&lut);
+    build_rand_table(rtab);
     __syncthreads();
     int64_t g = (int64_t)blockIdx.x * PTPB + threadIdx.x;
     uint32_t k = 0;
     if (g < n) {
         State s;
         load_state(s, states, g);
+        if (player_of(s)) swap_boards(s);   // mover-relative board order inside the loop (see REL)
         while ((int)k < max_steps && phase_of(s) != HZ_PHASE_OVER) {
-            int a = random_action(s, legal_of(s));
+            int a = random_action(s, legal_of<true>(s), rtab);
             if (a < 0) break;  // stuck position (no legal move, not over): harmonies_engine.py:205-208
-            if (apply_move<true>(s, a, HZ_NO_DRAW, key_of(s), s.w[HZ_W_EVENT], true, &lut) != HZ_MOVE_OK) break;
+            if (apply_move<true, true>(s, a, HZ_NO_DRAW, key_of(s), s.w[HZ_W_EVENT], true, &lut, rtab) != HZ_MOVE_OK) break;
             k++;
         }
+        if (player_of(s)) swap_boards(s);   // back to absolute order
         // final scoring deferred to here: the lanes of the warp are converged again
         if (phase_of(s) == HZ_PHASE_OVER && winner_code(s) == 0) finalize_scores(s, &lut);
         store_state(s, states, g);
