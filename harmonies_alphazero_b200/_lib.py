@@ -36,6 +36,7 @@ SIGNATURES = {
     "hz_tree_choose": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "hz_tree_stats": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "hz_tree_root_edges": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "hz_net_heads": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
 }
 
 

@@ -1,0 +1,155 @@
+// hz_heads.cu — fused policy/value heads of the reference network (model.py:340-355) for the
+// batched leaf evaluation: ONE kernel instead of ~10 library launches per simulation step.
+//
+//   x      [n, 35, C]  bf16, NHWC output of the residual tower (C = cnn_filters)
+//   glob   [n, 42]     bf16 global features
+//   -> 1x1 convs (2 policy + 1 value channel, BatchNorm folded) + ReLU          (model.py:340-343,349-351)
+//   -> policy: flatten (channel-major, as .view on NCHW) ++ glob -> FC 112->143  (:344-347)
+//   -> value : flatten ++ glob -> FC 77->H -> ReLU -> FC H->1 -> tanh            (:352-355)
+//   logits [n,143] fp32, value [n] fp32.  All accumulation in fp32.
+//
+// The tower stays cuDNN (north_star: "the network stays PyTorch"); this tail is ~0.1 MFLOP
+// and 9 KB of reads per position, i.e. HBM/launch-bound glue that is cheaper fused.
+// Mapping: a block of 256 threads takes 7 positions at a time: thread = (position, cell) for
+// the 1x1 convs, then thread = output unit for the FC layers with the 7 positions held as 7
+// accumulators, so each weight is read once per 7 positions (weights stay in L1/L2).
+#include <math.h>
+
+#include "hz_common.cuh"
+
+namespace hz {
+
+constexpr int HP = 7;          // positions per block iteration (7*35 = 245 <= 256 threads)
+constexpr int HTPB = 256;
+constexpr int CELLS = 35;
+constexpr int NGLOB = 42;
+constexpr int NPOL = 143;
+constexpr int PIN = 2 * CELLS + NGLOB;   // 112
+constexpr int VIN = CELLS + NGLOB;       // 77
+
+struct HeadParams {
+    const float* w_conv;   // [3][C]   rows: policy ch0, policy ch1, value ch0
+    const float* b_conv;   // [3]
+    const float* w_pol_t;  // [112][143]  transposed policy_fc weight
+    const float* b_pol;    // [143]
+    const float* w_v1_t;   // [77][H]     transposed value_fc1 weight
+    const float* b_v1;     // [H]
+    const float* w_v2;     // [H]
+    float b_v2;
+    int C, H;
+};
+
+__global__ void __launch_bounds__(HTPB) k_heads(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ glob,
+                                                int64_t n, HeadParams P, float* __restrict__ logits,
+                                                float* __restrict__ value) {
+    extern __shared__ float smem[];
+    float* s_wc = smem;                         // [3][C]
+    float* s_pin = s_wc + 3 * P.C;              // [HP][112]  policy FC input per position
+    float* s_vin = s_pin + HP * PIN;            // [HP][80]   value FC input per position (77 used)
+    float* s_red = s_vin + HP * 80;             // [HP][8]    per-warp partial sums of the last FC
+    for (int i = threadIdx.x; i < 3 * P.C; i += HTPB) s_wc[i] = P.w_conv[i];
+    const float bc0 = P.b_conv[0], bc1 = P.b_conv[1], bc2 = P.b_conv[2];
+    const int C = P.C, H = P.H;
+    int64_t n_groups = (n + HP - 1) / HP;
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        int64_t base = grp * HP;
+        int cnt = (int)min((int64_t)HP, n - base);
+        __syncthreads();
+        // ---- 1x1 convs + ReLU: thread = (position, cell); one contiguous C-row of bf16 each
+        int t = threadIdx.x;
+        if (t < cnt * CELLS) {
+            int p = t / CELLS, cell = t - CELLS * p;
+            const uint4* row = reinterpret_cast<const uint4*>(x + ((base + p) * CELLS + cell) * (int64_t)C);
+            float a0 = bc0, a1 = bc1, a2 = bc2;
+            for (int v = 0; v < C / 8; v++) {
+                uint4 q = row[v];
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float2 f = __bfloat1622float2(h[j]);
+                    int c = v * 8 + 2 * j;
+                    // explicit fmaf: the library is built with --fmad=false for the search arithmetic
+                    a0 = fmaf(f.y, s_wc[c + 1], fmaf(f.x, s_wc[c], a0));
+                    a1 = fmaf(f.y, s_wc[C + c + 1], fmaf(f.x, s_wc[C + c], a1));
+                    a2 = fmaf(f.y, s_wc[2 * C + c + 1], fmaf(f.x, s_wc[2 * C + c], a2));
+                }
+            }
+            s_pin[p * PIN + cell] = fmaxf(a0, 0.0f);            // channel-major flatten (model.py:343)
+            s_pin[p * PIN + CELLS + cell] = fmaxf(a1, 0.0f);
+            s_vin[p * 80 + cell] = fmaxf(a2, 0.0f);
+        }
+        for (int i = threadIdx.x; i < cnt * NGLOB; i += HTPB) {   // ++ global features (:344-346,352)
+            int p = i / NGLOB, g = i - NGLOB * p;
+            float gv = __bfloat162float(glob[(base + p) * NGLOB + g]);
+            s_pin[p * PIN + 2 * CELLS + g] = gv;
+            s_vin[p * 80 + CELLS + g] = gv;
+        }
+        __syncthreads();
+        // ---- policy FC 112 -> 143: thread = action, 7 positions as 7 accumulators
+        if (t < NPOL) {
+            float acc[HP];
+#pragma unroll
+            for (int p = 0; p < HP; p++) acc[p] = P.b_pol[t];
+            for (int j = 0; j < PIN; j++) {
+                float w = __ldg(P.w_pol_t + j * NPOL + t);
+#pragma unroll
+                for (int p = 0; p < HP; p++) acc[p] = fmaf(w, s_pin[p * PIN + j], acc[p]);
+            }
+#pragma unroll
+            for (int p = 0; p < HP; p++)
+                if (p < cnt) logits[(base + p) * NPOL + t] = acc[p];
+        }
+        // ---- value FC 77 -> H -> ReLU -> dot w2: thread = hidden unit (strided if H > 256)
+        float part[HP];
+#pragma unroll
+        for (int p = 0; p < HP; p++) part[p] = 0.0f;
+        for (int u = t; u < H; u += HTPB) {
+            float acc[HP];
+#pragma unroll
+            for (int p = 0; p < HP; p++) acc[p] = P.b_v1[u];
+            for (int j = 0; j < VIN; j++) {
+                float w = __ldg(P.w_v1_t + j * H + u);
+#pragma unroll
+                for (int p = 0; p < HP; p++) acc[p] = fmaf(w, s_vin[p * 80 + j], acc[p]);
+            }
+            float w2 = P.w_v2[u];
+#pragma unroll
+            for (int p = 0; p < HP; p++) part[p] = fmaf(fmaxf(acc[p], 0.0f), w2, part[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < HP; p++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part[p] += __shfl_xor_sync(0xFFFFFFFFu, part[p], o);
+        }
+        if ((t & 31) == 0) {
+#pragma unroll
+            for (int p = 0; p < HP; p++) s_red[p * 8 + (t >> 5)] = part[p];
+        }
+        __syncthreads();
+        if (t < cnt) {
+            float s = P.b_v2;
+#pragma unroll
+            for (int w = 0; w < HTPB / 32; w++) s += s_red[t * 8 + w];
+            value[base + t] = tanhf(s);                         // model.py:355
+        }
+    }
+}
+
+}  // namespace hz
+
+extern "C" int hz_net_heads(const void* x, const void* glob, int64_t n, int C, int H, const float* w_conv,
+                            const float* b_conv, const float* w_pol_t, const float* b_pol, const float* w_v1_t,
+                            const float* b_v1, const float* w_v2, float b_v2, float* logits, float* value,
+                            void* stream) {
+    if (n == 0) return HZ_OK;
+    if (!x || !glob || !w_conv || !b_conv || !w_pol_t || !b_pol || !w_v1_t || !b_v1 || !w_v2 || !logits || !value)
+        return HZ_ERR_ARG;
+    if (n < 0 || C <= 0 || (C % 8) != 0 || H <= 0 || ((uintptr_t)x & 15)) return HZ_ERR_ARG;
+    hz::HeadParams P{w_conv, b_conv, w_pol_t, b_pol, w_v1_t, b_v1, w_v2, b_v2, C, H};
+    size_t smem = sizeof(float) * (size_t)(3 * C + hz::HP * hz::PIN + hz::HP * 80 + hz::HP * 8);
+    int64_t groups = (n + hz::HP - 1) / hz::HP;
+    int grid = (int)(groups < 148 * 4 ? groups : 148 * 4);
+    hz::k_heads<<<grid, hz::HTPB, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)glob, n, P,
+                                                                logits, value);
+    return hz_launched(1);
+}

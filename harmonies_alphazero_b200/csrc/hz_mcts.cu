@@ -92,14 +92,19 @@ __global__ void __launch_bounds__(TTPB) k_tree_reset(hz_tree T, const uint4* roo
 }
 
 // ---- warp-level state encoding (shared with hz_encode's definition of the tensors) -----------
-template <typename T, bool NHWC>
+// LAYOUT: HZ_LAYOUT_NCHW, HZ_LAYOUT_NHWC, or HZ_LAYOUT_NHWC40 (channel stride 40, channels 38
+// and 39 written as zero: the stem convolution then needs no cuDNN input-padding kernel)
+template <int LAYOUT> struct RowElems { static constexpr int value = LAYOUT == HZ_LAYOUT_NHWC40 ? 1400 : 1330; };
+template <typename T, int LAYOUT>
 __device__ __forceinline__ void warp_encode(const uint32_t* w, uint32_t* smask, T* board, T* glob, int lane) {
-    for (int c = lane; c < 38; c += 32) smask[c] = channel_mask(w, c);
+    for (int c = lane; c < 40; c += 32) smask[c] = c < 38 ? channel_mask(w, c) : 0u;
     __syncwarp();
     float phase_val = (float)((double)((w[HZ_W_BAG1META] >> 25) & 7u) / 3.0);
-    for (int e = lane; e < 1330; e += 32) {
+    for (int e = lane; e < RowElems<LAYOUT>::value; e += 32) {
         int c, cell;
-        if (NHWC) { cell = e / 38; c = e - 38 * cell; } else { c = e / 35; cell = e - 35 * c; }
+        if (LAYOUT == HZ_LAYOUT_NHWC40) { cell = e / 40; c = e - 40 * cell; }
+        else if (LAYOUT == HZ_LAYOUT_NHWC) { cell = e / 38; c = e - 38 * cell; }
+        else { c = e / 35; cell = e - 35 * c; }
         uint32_t bit = (smask[c] >> CELL_HEX[cell]) & 1u;
         board[e] = cvt<T>(bit ? (c == 37 ? phase_val : 1.0f) : 0.0f);
     }
@@ -108,7 +113,7 @@ __device__ __forceinline__ void warp_encode(const uint32_t* w, uint32_t* smask, 
 }
 
 // ---- select: move_to_leaf (MCTS.py:63-149) + create_state_tensors(leaf) (MCTS.py:299) ---------
-template <typename OT, bool NHWC>
+template <typename OT, int LAYOUT>
 __global__ void __launch_bounds__(TTPB) k_tree_select(hz_tree T, float cpuct, uint4* leaf_states, OT* board, OT* glob) {
     __shared__ uint32_t sm_words[WPB][32];
     __shared__ uint32_t sm_mask[WPB][40];
@@ -166,7 +171,7 @@ __global__ void __launch_bounds__(TTPB) k_tree_select(hz_tree T, float cpuct, ui
     if (lane == 0) { T.leaf[t] = node; T.depth[t] = depth; }
     warp_load_words(sm_words[warp], v.node_state, node, lane);
     if (leaf_states) reinterpret_cast<uint32_t*>(leaf_states + (size_t)t * 8)[lane] = sm_words[warp][lane];
-    if (board) warp_encode<OT, NHWC>(sm_words[warp], sm_mask[warp], board + (size_t)t * 1330, glob + (size_t)t * 42, lane);
+    if (board) warp_encode<OT, LAYOUT>(sm_words[warp], sm_mask[warp], board + (size_t)t * RowElems<LAYOUT>::value, glob + (size_t)t * 42, lane);
 }
 
 // ---- transposition lookup (MCTS.py:184-186) ------------------------------------------------------
@@ -514,15 +519,20 @@ int hz_tree_select(hz_tree* t, float cpuct, void* leaf_states, void* board, void
     cudaStream_t st = (cudaStream_t)stream;
     int grid = tree_blocks(t->n_trees, WPB);
     uint4* ls = (uint4*)leaf_states;
+    if (layout != HZ_LAYOUT_NCHW && layout != HZ_LAYOUT_NHWC && layout != HZ_LAYOUT_NHWC40) return HZ_ERR_ARG;
+#define HZ_SELECT(T, L) k_tree_select<T, L><<<grid, TTPB, 0, st>>>(*t, cpuct, ls, (T*)board, (T*)glob)
     if (dtype == HZ_DTYPE_F32) {
-        if (layout == HZ_LAYOUT_NHWC) k_tree_select<float, true><<<grid, TTPB, 0, st>>>(*t, cpuct, ls, (float*)board, (float*)glob);
-        else k_tree_select<float, false><<<grid, TTPB, 0, st>>>(*t, cpuct, ls, (float*)board, (float*)glob);
+        if (layout == HZ_LAYOUT_NHWC40) HZ_SELECT(float, HZ_LAYOUT_NHWC40);
+        else if (layout == HZ_LAYOUT_NHWC) HZ_SELECT(float, HZ_LAYOUT_NHWC);
+        else HZ_SELECT(float, HZ_LAYOUT_NCHW);
     } else if (dtype == HZ_DTYPE_BF16) {
-        if (layout == HZ_LAYOUT_NHWC) k_tree_select<__nv_bfloat16, true><<<grid, TTPB, 0, st>>>(*t, cpuct, ls, (__nv_bfloat16*)board, (__nv_bfloat16*)glob);
-        else k_tree_select<__nv_bfloat16, false><<<grid, TTPB, 0, st>>>(*t, cpuct, ls, (__nv_bfloat16*)board, (__nv_bfloat16*)glob);
+        if (layout == HZ_LAYOUT_NHWC40) HZ_SELECT(__nv_bfloat16, HZ_LAYOUT_NHWC40);
+        else if (layout == HZ_LAYOUT_NHWC) HZ_SELECT(__nv_bfloat16, HZ_LAYOUT_NHWC);
+        else HZ_SELECT(__nv_bfloat16, HZ_LAYOUT_NCHW);
     } else {
         return HZ_ERR_ARG;
     }
+#undef HZ_SELECT
     return hz_launched(1);
 }
 

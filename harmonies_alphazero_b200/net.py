@@ -89,9 +89,10 @@ def _fold(conv, bn):
 class InferenceNet:
     """Folded, channels-last inference copy of an AlphaZeroNet on one device."""
 
-    def __init__(self, model, device="cuda", dtype=torch.bfloat16, fused=True):
+    def __init__(self, model, device="cuda", dtype=torch.bfloat16, fused=True, fused_heads=True):
         self.device, self.dtype = torch.device(device), dtype
         self.fused = fused and self.device.type == "cuda"
+        self.use_fused_heads = fused_heads
         self.load(model)
 
     def load(self, model):
@@ -103,11 +104,18 @@ class InferenceNet:
             return (w.to(dev, dt).contiguous(memory_format=torch.channels_last), b.to(dev, dt))
 
         self.stem = conv_params(model.conv, model.bn)
+        # same stem for a 40-channel input (channels 38, 39 are zero): C % 8 == 0 lets cuDNN run
+        # the bf16 tensor-op kernel without its input-padding pre-pass (HZ_LAYOUT_NHWC40)
+        w38, b38 = _fold(model.conv, model.bn)
+        w40 = torch.zeros((w38.shape[0], 40, 3, 3), dtype=w38.dtype)
+        w40[:, : w38.shape[1]] = w38
+        self.stem40 = (w40.to(dev, dt).contiguous(memory_format=torch.channels_last), b38.to(dev, dt))
         self.blocks = [(conv_params(b.conv1, b.bn1), conv_params(b.conv2, b.bn2)) for b in model.residual_blocks]
         self.phead = conv_params(model.policy_conv, model.policy_bn)
         self.vhead = conv_params(model.value_conv, model.value_bn)
         lin = lambda l: (l.weight.detach().to(dev, dt).contiguous(), l.bias.detach().to(dev, dt))  # noqa: E731
         self.policy_fc, self.value_fc1, self.value_fc2 = lin(model.policy_fc), lin(model.value_fc1), lin(model.value_fc2)
+        self._build_fused_heads(model)
         if self.fused:
             # the fused cuDNN entry points do not cover every dtype/arch combination: probe once
             # and use conv2d + relu (still cuDNN) if they refuse
@@ -131,15 +139,68 @@ class InferenceNet:
             y = y + residual
         return F.relu(y)
 
+    def _build_fused_heads(self, model):
+        """fp32 weights for hz_net_heads (csrc/hz_heads.cu): both 1x1 head convolutions with
+        BatchNorm folded, FC weights transposed so that threads read them coalesced."""
+        self.heads = None
+        if not (self.device.type == "cuda" and self.dtype == torch.bfloat16):
+            return
+        if model.policy_conv.out_channels != 2 or model.value_conv.out_channels != 1 or model.policy_fc.out_features != 143:
+            return
+        C = model.policy_conv.in_channels
+        if C % 8 or model.policy_fc.in_features != 112 or model.value_fc1.in_features != 77:
+            return
+        dev = self.device
+        wp, bp = _fold(model.policy_conv, model.policy_bn)
+        wv, bv = _fold(model.value_conv, model.value_bn)
+        f32 = lambda t: t.detach().float().contiguous().to(dev)  # noqa: E731
+        self.heads = dict(
+            C=C, H=model.value_fc1.out_features,
+            w_conv=f32(torch.cat((wp.view(2, C), wv.view(1, C)))), b_conv=f32(torch.cat((bp, bv))),
+            w_pol_t=f32(model.policy_fc.weight.t()), b_pol=f32(model.policy_fc.bias),
+            w_v1_t=f32(model.value_fc1.weight.t()), b_v1=f32(model.value_fc1.bias),
+            w_v2=f32(model.value_fc2.weight.view(-1)), b_v2=float(model.value_fc2.bias.item()),
+        )
+
+    def _fused_heads(self, x, glob, out):
+        from . import _lib
+
+        h = self.heads
+        B = x.shape[0]
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.contiguous(memory_format=torch.channels_last)
+        glob = glob.contiguous()
+        if out is None:
+            out = (torch.empty((B, 143), dtype=torch.float32, device=x.device), torch.empty(B, dtype=torch.float32, device=x.device))
+        logits, value = out
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            _lib.check(lib.hz_net_heads(
+                x.data_ptr(), glob.data_ptr(), B, h["C"], h["H"], h["w_conv"].data_ptr(), h["b_conv"].data_ptr(),
+                h["w_pol_t"].data_ptr(), h["b_pol"].data_ptr(), h["w_v1_t"].data_ptr(), h["b_v1"].data_ptr(),
+                h["w_v2"].data_ptr(), h["b_v2"], logits.data_ptr(), value.data_ptr(),
+                torch.cuda.current_stream(x.device).cuda_stream), "hz_net_heads")
+        return logits, value
+
     @torch.no_grad()
-    def forward(self, board, glob):
+    def forward(self, board, glob, out=None):
         """board [B,38,5,7] (channels-last preferred), glob [B,42], both ``dtype``.
-        Returns (logits fp32 [B,143], value fp32 [B])."""
-        x = self._conv_relu(board, self.stem, 1)
+        Returns (logits fp32 [B,143], value fp32 [B]); ``out`` = preallocated pair to fill."""
+        x = self._conv_relu(board, self.stem40 if board.shape[1] == 40 else self.stem, 1)
         for c1, c2 in self.blocks:
             y = self._conv_relu(x, c1, 1)
             x = self._conv_relu(y, c2, 1, residual=x)
         B = x.shape[0]
+        if self.heads is not None and self.use_fused_heads:
+            return self._fused_heads(x, glob, out)
+        if out is not None:
+            logits, value = self._torch_heads(x, glob, B)
+            out[0].copy_(logits)
+            out[1].copy_(value)
+            return out
+        return self._torch_heads(x, glob, B)
+
+    def _torch_heads(self, x, glob, B):
         p = self._conv_relu(x, self.phead, 0).contiguous(memory_format=torch.contiguous_format).view(B, -1)
         logits = F.linear(torch.cat((p, glob), dim=1), *self.policy_fc)
         v = self._conv_relu(x, self.vhead, 0).contiguous(memory_format=torch.contiguous_format).view(B, -1)

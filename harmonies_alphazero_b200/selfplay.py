@@ -38,6 +38,7 @@ class SelfPlayConfig:
     seed: int = 0
     first_game_id: int = 0         # global id of this rank's first game (sharding)
     use_cuda_graph: bool = True
+    n_streams: int = 1             # >1: split the slots into groups on separate streams (overlap tree kernels with convs)
     max_nodes: int = 0             # per-tree node arena; 0 = worst case 1 + 69*sims
     max_moves: int = 200           # hard cap per game (structural maximum is 160 actions)
 
@@ -92,66 +93,132 @@ class Trajectories:
                             self.game_id.to(device), self.move_no.to(device), dict(self.stats))
 
 
+class _Group:
+    """A contiguous range of slots with its own trees, static network buffers, CUDA graph and
+    stream.  Two groups on two streams let one group's tree kernels (HBM/latency-bound) run
+    under the other group's convolutions (tensor-bound)."""
+
+    def __init__(self, owner, lo, hi):
+        cfg, net, dev = owner.cfg, owner.net, owner.device
+        self.o, self.lo, self.hi = owner, lo, hi
+        n = hi - lo
+        self.tree = BatchedMCTS(n, cfg.num_simulations, device=dev, key_mode=cfg.key_mode, max_nodes=cfg.max_nodes)
+        dt, cl = net.dtype, owner.channels_last
+        self.board = torch.empty((n, 40 if owner.pad40 else 38, 5, 7), dtype=dt, device=dev,
+                                 memory_format=torch.channels_last if cl else torch.contiguous_format).zero_()
+        self.glob = torch.zeros((n, 42), dtype=dt, device=dev)
+        self.logits = torch.zeros((n, 143), dtype=torch.float32, device=dev)
+        self.value = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.noise = None if cfg.testing else torch.ones((n, 143), dtype=torch.float32, device=dev)
+        self.alpha = None if cfg.testing else torch.full((n, 143), cfg.dirichlet_alpha, dtype=torch.float32, device=dev)
+        self.graph = None
+        self.stream = torch.cuda.Stream(device=dev) if owner.n_groups > 1 else None
+
+    def sim_step(self):
+        """one simulation for every tree of the group: select -> network -> expand+backup"""
+        o, t = self.o, self.tree
+        t.select(o.cfg.cpuct, self.board, self.glob, dtype=o.net.dtype, channels_last=o.channels_last, pad40=o.pad40)
+        if o._net_takes_out:          # InferenceNet writes straight into the static buffers
+            o.net(self.board, self.glob, out=(self.logits, self.value))
+        else:
+            logits, value = o.net(self.board, self.glob)
+            self.logits.copy_(logits)
+            self.value.copy_(value)
+        t.expand_backup(self.logits, self.value, is_logits=True, noise=self.noise, eps=o.cfg.dirichlet_epsilon)
+
+    def capture(self):
+        """Warm up (cuDNN algorithm selection must happen outside capture) and capture one
+        simulation step in a CUDA graph."""
+        dev = self.o.device
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self.sim_step()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.sim_step()
+        self.graph = g
+
+    def prepare(self, states):
+        self.tree.reset(states[self.lo:self.hi])
+        if self.noise is not None:
+            # unnormalised Dirichlet: i.i.d. Gamma(alpha); the expand kernel normalises over
+            # the legal root moves (MCTS.py:314-316)
+            self.noise.copy_(torch._standard_gamma(self.alpha)).clamp_min_(1e-30)
+
+
 class BatchedSelfPlay:
     def __init__(self, net, cfg: SelfPlayConfig, device="cuda"):
         self.net, self.cfg = net, cfg
         self.device = torch.device(device)
         B = cfg.n_slots
-        self.tree = BatchedMCTS(B, cfg.num_simulations, device=self.device, key_mode=cfg.key_mode, max_nodes=cfg.max_nodes)
-        dt = net.dtype
-        cl = net.device.type == "cuda"
-        self.board = torch.empty((B, 38, 5, 7), dtype=dt, device=self.device,
-                                 memory_format=torch.channels_last if cl else torch.contiguous_format).zero_()
-        self.glob = torch.zeros((B, 42), dtype=dt, device=self.device)
-        self.logits = torch.zeros((B, 143), dtype=torch.float32, device=self.device)
-        self.value = torch.zeros(B, dtype=torch.float32, device=self.device)
-        self.noise = None if cfg.testing else torch.ones((B, 143), dtype=torch.float32, device=self.device)
-        self.alpha = None if cfg.testing else torch.full((B, 143), cfg.dirichlet_alpha, dtype=torch.float32, device=self.device)
-        self.graph = None
+        self.channels_last = net.device.type == "cuda"
+        self.pad40 = self.channels_last and hasattr(net, "stem40")   # 40-channel input: no cuDNN padding pre-pass
+        try:
+            import inspect
+
+            self._net_takes_out = "out" in inspect.signature(net.__call__).parameters
+        except (TypeError, ValueError):
+            self._net_takes_out = False
+        self.n_groups = max(1, min(int(cfg.n_streams), B))
+        cuts = [B * g // self.n_groups for g in range(self.n_groups + 1)]
+        self.groups = [_Group(self, cuts[g], cuts[g + 1]) for g in range(self.n_groups)]
         self.sims_run = 0
 
-    # ---- one simulation for every tree --------------------------------------------------
-    def _sim_step(self):
-        t = self.tree
-        t.select(self.cfg.cpuct, self.board, self.glob, dtype=self.net.dtype, channels_last=True)
-        logits, value = self.net(self.board, self.glob)
-        self.logits.copy_(logits)
-        self.value.copy_(value)
-        t.expand_backup(self.logits, self.value, is_logits=True, noise=self.noise, eps=self.cfg.dirichlet_epsilon)
+    # single-group conveniences (profiling harnesses, tests)
+    @property
+    def tree(self):
+        return self.groups[0].tree
 
-    def _capture(self):
-        """Warm up (cuDNN algorithm selection must happen outside capture) and capture one
-        simulation step in a CUDA graph."""
-        s = torch.cuda.Stream(device=self.device)
-        s.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(s):
-            for _ in range(3):
-                self._sim_step()
-        torch.cuda.current_stream(self.device).wait_stream(s)
-        torch.cuda.synchronize(self.device)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._sim_step()
-        self.graph = g
+    @property
+    def graph(self):
+        return self.groups[0].graph
+
+    def _sim_step(self):
+        for g in self.groups:
+            g.sim_step()
 
     def search(self, states):
         """One full search per slot from ``states`` (get_best_action_and_pi up to the root
         statistics, MCTS.py:288-352)."""
         cfg = self.cfg
-        self.tree.reset(states)
-        if self.noise is not None:
-            # unnormalised Dirichlet: i.i.d. Gamma(alpha); the expand kernel normalises over
-            # the legal root moves (MCTS.py:314-316)
-            self.noise.copy_(torch._standard_gamma(self.alpha)).clamp_min_(1e-30)
-        if cfg.use_cuda_graph and self.graph is None:
-            self._capture()
-            self.tree.reset(states)   # the warm-up/capture advanced the trees
+        main = torch.cuda.current_stream(self.device)
+        for g in self.groups:
+            g.prepare(states)
+            if cfg.use_cuda_graph and g.graph is None:
+                g.capture()
+                g.tree.reset(states[g.lo:g.hi])   # the warm-up/capture advanced the trees
+        for g in self.groups:
+            if g.stream is not None:
+                g.stream.wait_stream(main)
         for _ in range(cfg.num_simulations):
-            if self.graph is not None:
-                self.graph.replay()
-            else:
-                self._sim_step()
+            for g in self.groups:
+                if g.stream is None:
+                    g.graph.replay() if g.graph is not None else g.sim_step()
+                else:
+                    with torch.cuda.stream(g.stream):
+                        g.graph.replay() if g.graph is not None else g.sim_step()
+        for g in self.groups:
+            if g.stream is not None:
+                main.wait_stream(g.stream)
         self.sims_run += cfg.num_simulations
+
+    def root_policy(self):
+        parts = [g.tree.root_policy() for g in self.groups]
+        return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+
+    def choose(self, u01=None, exploratory=None):
+        return torch.cat([
+            g.tree.choose(None if u01 is None else u01[g.lo:g.hi].contiguous(),
+                          None if exploratory is None else exploratory[g.lo:g.hi].contiguous())
+            for g in self.groups])
+
+    def check_status(self):
+        for g in self.groups:
+            g.tree.check_status()
 
     # ---- whole games ---------------------------------------------------------------------
     def play(self, num_games, progress=None):
@@ -193,13 +260,13 @@ class BatchedSelfPlay:
                 raise RuntimeError("a game exceeded max_moves without ending")
             snap = states.clone()
             self.search(states)
-            visits, _ = self.tree.root_policy()
+            visits, _ = self.root_policy()
             expl = None
             u01 = None
             if not cfg.testing and cfg.turns_until_tau0 > 0:
                 expl = (move_no < cfg.turns_until_tau0).to(torch.uint8)   # MCTS.py:399-402
                 u01 = torch.rand(B, device=dev, dtype=torch.float32)
-            actions = self.tree.choose(u01, expl)
+            actions = self.choose(u01, expl)
             actions = torch.where(live, actions, torch.full_like(actions, -1))
             status = hb.apply(states, actions)                   # the real move re-draws independently (trainer.py:502)
             bad_status = torch.maximum(bad_status, torch.where(live, status, torch.zeros_like(status)).max())
@@ -207,10 +274,10 @@ class BatchedSelfPlay:
             live_sims += n_live * cfg.num_simulations
             step += 1
             if step % 8 == 0:
-                self.tree.check_status()
+                self.check_status()
             if progress:
                 progress(step, int(finished.sum().item()), num_games)
-        self.tree.check_status()
+        self.check_status()
         if int(bad_status.item()) != 0:
             raise RuntimeError(f"engine rejected a searched move (status {int(bad_status.item())})")
         torch.cuda.synchronize(dev)

@@ -49,14 +49,18 @@ class BatchedMCTS:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.hz_tree_reset(self.handle, _ptr(root_states), _ptr(search_keys), self._stream()), "hz_tree_reset")
 
-    def select(self, cpuct, board=None, glob=None, leaf_states=None, dtype=torch.float32, channels_last=False):
-        """move_to_leaf for every tree + encoding of the leaves into (board, glob)."""
+    def select(self, cpuct, board=None, glob=None, leaf_states=None, dtype=torch.float32, channels_last=False, pad40=False):
+        """move_to_leaf for every tree + encoding of the leaves into (board, glob).
+        pad40: board is [n,40,5,7] channels-last (HZ_LAYOUT_NHWC40, two zero channels)."""
         code = {torch.float32: F32, torch.bfloat16: BF16}[dtype]
+        layout = 2 if pad40 else (NHWC if channels_last else NCHW)
+        if board is not None:
+            assert board.shape[1] == (40 if pad40 else 38)
         with torch.cuda.device(self.device):
             _lib.check(
                 self.lib.hz_tree_select(
                     self.handle, float(cpuct), _ptr(leaf_states), _ptr(board), _ptr(glob), code,
-                    NHWC if channels_last else NCHW, self._stream(),
+                    layout, self._stream(),
                 ),
                 "hz_tree_select",
             )

@@ -127,6 +127,7 @@ extern "C" {
 #define HZ_DTYPE_BF16 1
 #define HZ_LAYOUT_NCHW 0
 #define HZ_LAYOUT_NHWC 1
+#define HZ_LAYOUT_NHWC40 2  /* hz_tree_select only: [n,5,7,40], channels 38,39 = 0 (8-aligned C for the stem conv) */
 
 /* node-key modes (hz_canon_hash, hz_tree_create):
  *  HZ_KEY_EXACT     identity = equality of get_canonical_tuple (harmonies_engine.py:81-118)
@@ -257,6 +258,18 @@ int hz_tree_stats(hz_tree *t, int32_t *n_nodes, int32_t *n_edges, uint8_t *statu
  * all [n,143] indexed by action (absent edges: N=0,W=0,P=0,child=-1). Any may be NULL. */
 int hz_tree_root_edges(hz_tree *t, int32_t *N, double *W, float *P, int32_t *child,
                        void *stream);
+
+/* ---- network tail (model.py) ----------------------------------------------------------- */
+
+/* Fused policy/value heads of AlphaZeroModel.forward (model.py:340-355) on the residual
+ * tower's output: x [n,35,C] bf16 NHWC, glob [n,42] bf16 -> logits [n,143] fp32, value [n] fp32.
+ * Weights fp32 with BatchNorm folded: w_conv [3][C] (policy ch0, policy ch1, value ch0),
+ * b_conv [3], w_pol_t [112][143] (policy_fc weight transposed), b_pol [143], w_v1_t [77][H]
+ * (value_fc1 transposed), b_v1 [H], w_v2 [H], b_v2.  C multiple of 8, x 16-byte aligned. */
+int hz_net_heads(const void *x, const void *glob, int64_t n, int C, int H, const float *w_conv,
+                 const float *b_conv, const float *w_pol_t, const float *b_pol,
+                 const float *w_v1_t, const float *b_v1, const float *w_v2, float b_v2,
+                 float *logits, float *value, void *stream);
 
 #define HZ_PLAYOUT_SALT 0xA5A5F00DC0FFEE11ull
 #define HZ_SEARCH_SALT  0x5EA2C47EE5A17B00ull

@@ -109,6 +109,11 @@ def test_select_outputs_leaf_encoding(mods, oracle):
             if dtype == torch.float32:
                 ob, og = oracle.encode(leaf.cpu().numpy().view(np.uint32))
                 assert np.array_equal(board.cpu().numpy(), ob) and np.array_equal(glob.cpu().numpy(), og)
+        # 40-channel padded NHWC variant (two zero channels) used by the self-play stem
+        b40 = torch.full((n, 40, 5, 7), 7.0, dtype=torch.bfloat16, device="cuda").contiguous(memory_format=torch.channels_last)
+        g40 = torch.empty((n, 42), dtype=torch.bfloat16, device="cuda")
+        t.select(2.0, b40, g40, leaf, dtype=torch.bfloat16, channels_last=True, pad40=True)
+        assert torch.equal(b40[:, :38].contiguous(), board.contiguous()) and (b40[:, 38:] == 0).all() and torch.equal(g40, glob)
         t.fake_eval(policy, value)
         # synthetic evaluator == packed.fake_eval of the leaf's exact hash
         if s == 3:

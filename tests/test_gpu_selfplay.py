@@ -48,6 +48,44 @@ def test_inference_net_matches_module(mods):
     assert (v16 - v_ref.view(-1)).abs().max() < 0.1
 
 
+@pytest.mark.parametrize("cfg_name", ["TEST_MODEL_CONFIG", "DEFAULT_MODEL_CONFIG"])
+def test_fused_heads_kernel_matches_torch_heads(mods, cfg_name):
+    """hz_net_heads (model.py:340-355 in one kernel) vs the same tail computed by torch in
+    fp32 from the same bf16 tower output; tolerance: fp32 accumulation-order noise."""
+    hb, net, _, _ = mods
+    torch.manual_seed(1)
+    m = net.AlphaZeroNet.from_config(getattr(net, cfg_name))
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.3); mod.running_var.uniform_(0.5, 1.5)
+            mod.weight.data.uniform_(0.5, 1.5); mod.bias.data.normal_(0, 0.2)
+    m.eval()
+    inf = net.InferenceNet(m, device="cuda", dtype=torch.bfloat16)
+    assert inf.heads is not None
+    C = inf.heads["C"]
+    for B in (1, 6, 7, 8, 300):
+        x = (torch.randn((B, C, 5, 7), device="cuda") * 0.7).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        glob = torch.rand((B, 42), device="cuda").to(torch.bfloat16)
+        logits, value = inf._fused_heads(x, glob, None)
+        mm = m.cuda().float()
+        xf, gf = x.float().contiguous(), glob.float()
+        with torch.no_grad():
+            p = torch.relu(mm.policy_bn(mm.policy_conv(xf))).flatten(1)
+            want_l = mm.policy_fc(torch.cat((p, gf), 1))
+            v = torch.relu(mm.value_bn(mm.value_conv(xf))).flatten(1)
+            want_v = torch.tanh(mm.value_fc2(torch.relu(mm.value_fc1(torch.cat((v, gf), 1))))).view(-1)
+        assert torch.allclose(logits, want_l, atol=2e-4, rtol=1e-4), (B, (logits - want_l).abs().max())
+        assert torch.allclose(value, want_v, atol=1e-4), (B, (value - want_v).abs().max())
+    # the whole forward with fused heads agrees with the torch-head path at bf16 precision
+    st = hb.init_states(64, seed=2)
+    hb.playout(st, max_steps=20)
+    b16, g16 = hb.encode(st, dtype=torch.bfloat16, channels_last=True)
+    l1, v1 = inf(b16, g16)
+    inf.use_fused_heads = False
+    l2, v2 = inf(b16, g16)
+    assert (torch.softmax(l1, 1) - torch.softmax(l2, 1)).abs().max() < 0.02 and (v1 - v2).abs().max() < 0.05
+
+
 def test_search_with_real_net_matches_oracle(mods, oracle):
     """64 games x first 8 moves x 24 simulations, fp32 network, testing=True: the GPU tree
     and the reference-semantics oracle see identical (P, v) per leaf and must produce
