@@ -402,6 +402,27 @@ def run_b200(args):
         dist.all_reduce(s2, op=dist.ReduceOp.SUM)
     e2e_value = int(s2.item()) / (float(t2.item()) * 1e-3)
 
+    # ---- the same wave with unfused per-step kernels (K1 legal_mask + policy + K2 apply): the
+    # state makes an HBM/L2 round trip every step, which is what the 258 B/step roofline models
+    st = fresh(20_000)
+    abuf = torch.empty(n, dtype=torch.int16, device=dev)
+    sbuf = torch.empty(n, dtype=torch.uint8, device=dev)
+    mbuf = torch.empty((n, 5), dtype=torch.int32, device=dev)
+    for _ in range(3):
+        hb.legal_mask(st, out=mbuf); hb.random_actions(st, out=abuf); hb.apply(st, abuf, status=sbuf)
+    st = fresh(20_001)
+    torch.cuda.synchronize()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record(stream)
+    for _ in range(76):
+        hb.legal_mask(st, out=mbuf)
+        hb.random_actions(st, out=abuf)
+        hb.apply(st, abuf, status=sbuf)      # finished games reject the move and stay untouched
+    u1.record(stream)
+    torch.cuda.synchronize()
+    unfused_steps = int(st[:, 27].sum().item())
+    unfused_ms = u0.elapsed_time(u1)
+
     pk, pk_src = peaks()
     avg_launch_s = (ms / K) * 1e-3
     algo_bytes = ALGO_BYTES_PER_STEP * (steps_done / K)
@@ -417,10 +438,16 @@ def run_b200(args):
         "gpu_launches": launches_all,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src + " (burst copy)",
+                     "frac": achieved / pk["hbm_gbs"],
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch at 65,536 games, ncu --set full
+                     # (profiles/r01_playout_ncu.txt): the initial records only; results stay in L2
+                     "traffic": 8410880 if n == 65536 else None, "peak_source": pk_src + " (burst copy)",
                      "kernel": "hz::k_playout", "note": "algorithmic 258 B/step x steps per launch / CUDA-event launch time; "
                      "the fused kernel keeps the state on chip, so DRAM traffic is ~256 B per GAME"},
         "wall_s": wall,
+        "unfused": {"value": unfused_steps / (unfused_ms * 1e-3), "unit": UNIT, "launches": 76 * 3, "ms": unfused_ms,
+                    "achieved_GBps": unfused_steps * ALGO_BYTES_PER_STEP / (unfused_ms * 1e-3) / 1e9,
+                    "note": "one wave with hz_legal_mask + hz_random_actions + hz_apply per step (rank 0)"},
     }
     if not args.no_mcts:
         # second half of BASELINE.json's metric: MCTS sims/s (configs[3]), reported alongside

@@ -1,0 +1,72 @@
+"""Batched arena evaluation: the candidate-vs-best match of
+Trainer.evaluate_model / play_one_eval_game (trainer.py:293-431) with all evaluation games
+played concurrently on the GPU.
+
+Reference semantics kept: the candidate plays player 0 in even games and player 1 in odd
+games (trainer.py:318-324); every move is a fresh search with the network OF THE SIDE TO MOVE
+(trainer.py:395-401) under ``mcts_config_eval`` (testing=True: no noise, greedy move,
+config.py:67-78); the result is counted from the candidate's perspective and the win rate
+excludes draws (trainer.py:338-342).
+"""
+
+import torch
+
+from . import batched as hb
+from .tree import BatchedMCTS
+
+
+def _search(tree, net, states, sims, cpuct, bufs):
+    board, glob, logits, value = bufs
+    tree.reset(states)
+    pad40 = board.shape[1] == 40
+    for _ in range(sims):
+        tree.select(cpuct, board, glob, dtype=net.dtype, channels_last=True, pad40=pad40)
+        net(board, glob, out=(logits, value))
+        tree.expand_backup(logits, value, is_logits=True)
+
+
+def play_match(candidate_net, best_net, num_games, mcts_config_eval, device="cuda", seed=0, key_mode=hb.KEY_REFERENCE):
+    """Returns dict(candidate_wins, best_wins, draws, win_rate, games).  Both nets are
+    InferenceNet instances on ``device``."""
+    dev = torch.device(device)
+    sims, cpuct = int(mcts_config_eval["num_simulations"]), float(mcts_config_eval["cpuct"])
+    # group 0: candidate is player 0 (even game indices); group 1: candidate is player 1
+    sizes = [(num_games + 1) // 2, num_games // 2]
+    result = {"candidate_wins": 0, "best_wins": 0, "draws": 0}
+    for g, n in enumerate(sizes):
+        if n == 0:
+            continue
+        states = hb.init_states(n, device=dev, seed=seed, first_id=0 if g == 0 else num_games)   # distinct games per group
+        tree = BatchedMCTS(n, sims, device=dev, key_mode=key_mode)
+        dt = candidate_net.dtype
+        C = 40 if hasattr(candidate_net, "stem40") else 38
+        bufs = (
+            torch.empty((n, C, 5, 7), dtype=dt, device=dev, memory_format=torch.channels_last).zero_(),
+            torch.zeros((n, 42), dtype=dt, device=dev),
+            torch.zeros((n, 143), dtype=torch.float32, device=dev),
+            torch.zeros(n, dtype=torch.float32, device=dev),
+        )
+        for _ in range(200):
+            over, oc = hb.outcome(states)
+            if bool(over.all()):
+                break
+            live = ~over.bool()
+            # all live games of a group are in lockstep: same player to move
+            mover = int(((states[live][:, 22] >> 24) & 1)[0].item())
+            net = candidate_net if mover == g else best_net
+            _search(tree, net, states, sims, cpuct, bufs)
+            actions = tree.choose()                                  # greedy: testing=True
+            actions = torch.where(live, actions, torch.full_like(actions, -1))
+            hb.apply(states, actions)
+        tree.check_status()
+        over, oc = hb.outcome(states)
+        if not bool(over.all()):
+            raise RuntimeError("arena game did not finish")
+        cand = oc.to(torch.int32) * (1 if g == 0 else -1)            # outcome is from player 0's view
+        result["candidate_wins"] += int((cand > 0).sum().item())
+        result["best_wins"] += int((cand < 0).sum().item())
+        result["draws"] += int((cand == 0).sum().item())
+    decided = result["candidate_wins"] + result["best_wins"]
+    result["win_rate"] = result["candidate_wins"] / decided if decided else 0.0   # trainer.py:338-342
+    result["games"] = num_games
+    return result

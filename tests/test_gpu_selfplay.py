@@ -171,6 +171,23 @@ def test_selfplay_games_and_example_contract(mods, oracle):
     assert np.array_equal(b.numpy(), ob[0]) and np.array_equal(gl.numpy(), og[0])
 
 
+def test_arena_match(mods):
+    """candidate-vs-best evaluation (trainer.py:293-431) batched over all eval games"""
+    hb, net, _, _ = mods
+    from harmonies_alphazero_b200 import arena
+
+    _, cand = _small_net(net, torch.bfloat16, seed=1)
+    _, best = _small_net(net, torch.bfloat16, seed=2)
+    cfg = {"num_simulations": 6, "cpuct": 2, "dirichlet_alpha": 0.1, "dirichlet_epsilon": 0,
+           "turns_until_tau0": 0, "action_size": 143, "testing": True}
+    r1 = arena.play_match(cand, best, 9, cfg, seed=5)
+    assert r1["candidate_wins"] + r1["best_wins"] + r1["draws"] == 9 and 0.0 <= r1["win_rate"] <= 1.0
+    assert arena.play_match(cand, best, 9, cfg, seed=5) == r1          # deterministic in testing mode
+    # swapping the roles mirrors the tally
+    r2 = arena.play_match(best, cand, 9, cfg, seed=5)
+    assert r2["games"] == 9 and r2["candidate_wins"] + r2["best_wins"] + r2["draws"] == 9
+
+
 def test_selfplay_is_independent_of_slot_count_in_testing_mode(mods):
     """deterministic mode: the same game ids give the same trajectories whatever the batch
     shape (keys are per game id, search keys per (game, move))."""
