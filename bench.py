@@ -226,12 +226,15 @@ def mcts_measure(args, dev, world, rank, dist):
         dist.barrier()
     torch.cuda.synchronize()
     l0 = hb.launch_count()
+    sampler = ClockSampler(dev.index if dev.index is not None else 0)
+    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):
         one_move()
     e1.record()
     torch.cuda.synchronize()
+    mcts_clocks = sampler.stop()
     if dist is not None:
         dist.barrier()
     direct_launches = hb.launch_count() - l0
@@ -276,7 +279,7 @@ def mcts_measure(args, dev, world, rank, dist):
             "config": {"workload": "MCTS self-play, model.py net 128f x 8 blocks random-init, bf16, "
                                    f"{S} sims/move, {B} concurrent games per GPU (configs[3])",
                        "fused_conv": inf.fused, "fused_heads": inf.heads is not None, "cuda_graph": drv.graph is not None, "streams": drv.n_groups},
-            "dtype": "bf16", "collectives": collectives,
+            "dtype": "bf16", "collectives": collectives, "clocks": mcts_clocks,
             # direct C-ABI launches + the two tree kernels replayed inside the CUDA graph per simulation
             "gpu_launches_own": (direct_launches + ((2 + (inf.heads is not None)) * drv.n_groups * S * K if drv.graph is not None else 0)) * world,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
@@ -410,14 +413,18 @@ def run_b200(args):
     mbuf = torch.empty((n, 5), dtype=torch.int32, device=dev)
     for _ in range(3):
         hb.legal_mask(st, out=mbuf); hb.random_actions(st, out=abuf); hb.apply(st, abuf, status=sbuf)
-    st = fresh(20_001)
+    torch.cuda.synchronize()
+    ugraph = torch.cuda.CUDAGraph()          # 228 launches in one graph: device time, not Python launch overhead
+    with torch.cuda.graph(ugraph):
+        for _ in range(76):
+            hb.legal_mask(st, out=mbuf)
+            hb.random_actions(st, out=abuf)
+            hb.apply(st, abuf, status=sbuf)  # finished games reject the move and stay untouched
+    st.copy_(fresh(20_001))
     torch.cuda.synchronize()
     u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     u0.record(stream)
-    for _ in range(76):
-        hb.legal_mask(st, out=mbuf)
-        hb.random_actions(st, out=abuf)
-        hb.apply(st, abuf, status=sbuf)      # finished games reject the move and stay untouched
+    ugraph.replay()
     u1.record(stream)
     torch.cuda.synchronize()
     unfused_steps = int(st[:, 27].sum().item())

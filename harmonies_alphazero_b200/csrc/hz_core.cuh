@@ -42,18 +42,16 @@ __constant__ int INIT_BAG[6] = {23, 19, 21, 23, 15, 19};
 struct NbrLut {
     uint32_t t[3][256];
 };
+// The table is a compile-time constant in global memory (generated from the geometry by
+// gen_tables.py).  Kernels that score a lot copy it to shared memory with coalesced loads
+// (6 per thread at 128 threads); kernels that score rarely (the search tree: only children
+// that end the game) read it in place through L1 via global_nbr_lut().
+#include "hz_tables.inc"
 __device__ __forceinline__ void build_nbr_lut(NbrLut* lut) {
-    for (int e = threadIdx.x; e < 768; e += blockDim.x) {
-        int c = e >> 8, v = e & 255;
-        uint32_t m = 0;
-#pragma unroll
-        for (int b = 0; b < 8; b++) {
-            int i = c * 8 + b;
-            if (((v >> b) & 1) && i < 23) m |= NBR[i];
-        }
-        lut->t[c][v] = m;
-    }
+    uint32_t* dst = &lut->t[0][0];
+    for (int e = threadIdx.x; e < 768; e += blockDim.x) dst[e] = NBR_LUT_G[e];
 }
+__device__ __forceinline__ const NbrLut* global_nbr_lut() { return reinterpret_cast<const NbrLut*>(NBR_LUT_G); }
 __device__ __forceinline__ uint32_t nbr(const NbrLut* lut, uint32_t m) {
     return lut->t[0][m & 255] | lut->t[1][(m >> 8) & 255] | lut->t[2][(m >> 16) & 127];
 }
@@ -551,18 +549,22 @@ __device__ __forceinline__ uint32_t channel_mask(const uint32_t* w, int c) {
     return (ph >= 1 && ph <= 3) ? VALID : 0u;                        // :74-81 (phase 0 and game_over -> 0)
 }
 __device__ __forceinline__ float global_feature(const uint32_t* w, int g) {
-    const float third[4] = {0.0f, (float)(1.0 / 3.0), (float)(2.0 / 3.0), 1.0f};
+    // fp32(k / 3.0) for k = 0..3 by selects (a local array would live in local memory)
+    auto third = [](uint32_t k) { return k == 0 ? 0.0f : k == 1 ? (float)(1.0 / 3.0) : k == 2 ? (float)(2.0 / 3.0) : 1.0f; };
     if (g < 30) {                                                    // :98-107
         int i = g / 6, t = g - 6 * i;
         uint32_t np = (w[HZ_W_BAG1META] >> 16) & 0xFFu;
         uint32_t word = w[HZ_W_PILES01 + (i >> 1)];
         uint32_t code = (i & 1) ? (word >> 16) : (word & 0xFFFFu);
-        return (uint32_t)i < np ? third[(code >> (2 * t)) & 3u] : 0.0f;
+        return (uint32_t)i < np ? third((code >> (2 * t)) & 3u) : 0.0f;
     }
-    if (g < 36) return third[((w[HZ_W_PILE4H] >> 16) >> (2 * (g - 30))) & 3u];   // :112-118
+    if (g < 36) return third(((w[HZ_W_PILE4H] >> 16) >> (2 * (g - 30))) & 3u);   // :112-118
     int t = g - 36;                                                  // :122-130
     uint32_t cnt = t < 4 ? (w[HZ_W_BAG0] >> (8 * t)) & 0xFFu : (w[HZ_W_BAG1META] >> (8 * (t - 4))) & 0xFFu;
-    return (float)((double)cnt / (double)INIT_BAG[t]);
+    // The reference divides in double and stores to fp32.  A correctly rounded fp32 division of
+    // the two small integers gives the same bits: c/init is exact or has a binary period of at
+    // most 22 bits (init <= 23), so its 53-bit rounding can never land on an fp32 midpoint.
+    return __fdiv_rn((float)cnt, (float)INIT_BAG[t]);
 }
 
 

@@ -175,7 +175,13 @@ __global__ void __launch_bounds__(TTPB) k_tree_select(hz_tree T, float cpuct, ui
 }
 
 // ---- transposition lookup (MCTS.py:184-186) ------------------------------------------------------
-// returns node index or -1.  Full-key compare on hash match.
+// returns node index or -1.  Identity = equality of the 64-bit key, exactly as the reference
+// (MCTS.py:185 looks `hash(state)` up in a dict of ids and never compares states); building
+// with -DHZ_TREE_FULL_COMPARE=1 additionally compares the 23 key words on a hash match, which
+// costs a dependent 128-byte gather per hit and only guards against a 2^-64 collision.
+#ifndef HZ_TREE_FULL_COMPARE
+#define HZ_TREE_FULL_COMPARE 0
+#endif
 __device__ __forceinline__ int table_find(const hz_tree& T, const TreeView& v, uint64_t h, const uint32_t* key) {
     uint32_t mask = (uint32_t)T.table_size - 1u;
     uint32_t slot = (uint32_t)h & mask;
@@ -184,6 +190,7 @@ __device__ __forceinline__ int table_find(const hz_tree& T, const TreeView& v, u
         if (e == 0) return -1;
         int idx = (int)e - 1;
         if (v.node_hash[idx] == h) {
+            if (!HZ_TREE_FULL_COMPARE) return idx;
             State o;
             load_state(o, v.node_state, idx);
             uint32_t ok[HZ_CANON_WORDS];
@@ -205,10 +212,10 @@ __device__ __forceinline__ void table_insert(const hz_tree& T, const TreeView& v
 // ---- expand_leaf + terminal value + back_fill (MCTS.py:151-264, 297-352) -------------------------
 __global__ void __launch_bounds__(TTPB) k_tree_expand_backup(hz_tree T, const float* policy, const float* value,
                                                              int is_logits, const float* noise, double eps) {
-    __shared__ NbrLut lut;
     __shared__ uint32_t sm_words[WPB][32];
-    build_nbr_lut(&lut);
-    __syncthreads();
+    // scoring happens only for children that end the game: read the neighbour LUT in place
+    // (global memory, L1-cached) instead of staging 3 KB per block
+    const NbrLut* lut = global_nbr_lut();
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t = blockIdx.x * WPB + warp;
     if (t >= T.n_trees) return;
@@ -259,7 +266,7 @@ __global__ void __launch_bounds__(TTPB) k_tree_expand_backup(hz_tree T, const fl
             uint32_t key[HZ_CANON_WORDS];
             int found = -1;
             if (active) {
-                apply_move(cs, a, HZ_NO_DRAW, skey, ((uint32_t)sim << 8) | (uint32_t)a, false, &lut);   // :176
+                apply_move(cs, a, HZ_NO_DRAW, skey, ((uint32_t)sim << 8) | (uint32_t)a, false, lut);   // :176
                 key_words(cs, T.key_mode, key);
                 h = hash_key_words(key);                             // :177
                 found = table_find(T, v, h, key);                    // :185

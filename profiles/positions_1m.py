@@ -41,7 +41,8 @@ def synth_positions(n, dev, seed=31337):
 def timeit(fn, iters, flush):
     ms = []
     for _ in range(iters):
-        flush.fill_(1)
+        flush.fill_(1)       # evict everything ...
+        flush.max()          # ... then a read pass, so the timed kernel does not pay for write-backs of dirty flush lines
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record()
         torch.cuda.synchronize()
@@ -81,4 +82,10 @@ if __name__ == "__main__":
         out[name] = {"ms": ms, "units_per_s": units / (ms * 1e-3), "algorithmic_GBps": units * bpu / (ms * 1e-3) / 1e9,
                      "frac_of_hbm_6455.6": units * bpu / (ms * 1e-3) / 1e9 / 6455.6, "bytes_per_unit": bpu, "units": units}
     torch.cuda.profiler.stop()
+    # write-only reference: the encoders only store, and a pure store stream does not reach the
+    # read+write copy figure of MEASURED_PEAKS.json; torch.fill_ of the same bytes is the yardstick
+    for name, buf in (("fill_same_bytes_as_encode_f32", b32), ("fill_same_bytes_as_encode_bf16", b16)):
+        ms = timeit(lambda: buf.fill_(1.0), a.iters, flush)
+        nbytes = buf.numel() * buf.element_size()
+        out[name] = {"ms": ms, "GBps": nbytes / (ms * 1e-3) / 1e9}
     print(json.dumps(out))

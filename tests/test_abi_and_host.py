@@ -69,6 +69,17 @@ def test_device_tables_match_reference_geometry():
         cell_hex[y * 7 + x] = i
     assert table("CELL_HEX") == cell_hex
     assert table("INIT_BAG") == K.INITIAL_BAG_BY_TYPE
+    # the generated neighbour-expansion LUT is in sync with the geometry
+    from harmonies_alphazero_b200 import gen_tables
+
+    assert open(gen_tables.PATH).read() == gen_tables.render()
+    lut = gen_tables.table()
+    for m in (0x1, 0x7FFFFF, 0x155555, 0x0A0A0A):
+        want = 0
+        for i in range(23):
+            if (m >> i) & 1:
+                want |= K.NEIGHBOR_MASKS[i]
+        assert lut[m & 255] | lut[256 + ((m >> 8) & 255)] | lut[512 + (m >> 16)] == want
     # neighbourhood is symmetric, degree histogram of the 5-4-5-4-5 grid
     deg = [bin(m).count("1") for m in K.NEIGHBOR_MASKS]
     assert sorted(deg) == sorted([2] * 4 + [3] * 2 + [4] * 6 + [5] * 4 + [6] * 7)
