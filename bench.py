@@ -378,24 +378,23 @@ def run_b200(args):
     ms_max, steps_all, launches_all = float(t.item()), int(s[0].item()), int(s[1].item())
     value = steps_all / (ms_max * 1e-3)
 
-    # ---- end to end through the C-ABI with host buffers (pinned H2D + D2H inside the region)
-    init_host = [fresh(10_000 + k).cpu() for k in range(min(K, 4))]
+    # ---- end to end through the public host-buffer API (HostPlayout.run): every step copies its
+    # inputs from pinned host memory (H2D) and reads the final records back (D2H) inside the
+    # timed region; the call pipelines 4 chunks on 4 streams so copies overlap the kernel
+    host_api = hb.HostPlayout(n, device=dev, chunks=4)
+    pinned_inputs = [fresh(10_000 + k).cpu().pin_memory() for k in range(min(K, 4))]
     for w in range(2):
-        pinned_in.copy_(init_host[0]); states.copy_(pinned_in, non_blocking=True)
-        hb.playout(states, steps=steps_buf, total=total); pinned_out.copy_(states, non_blocking=True)
+        host_api.run(pinned_inputs[0], pinned_out)
     torch.cuda.synchronize()
-    total.zero_()
+    host_api.total.zero_()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for k in range(K):
-        pinned_in.copy_(init_host[k % len(init_host)])           # host-side staging of this step's input
-        states.copy_(pinned_in, non_blocking=True)               # H2D
-        hb.playout(states, steps=steps_buf, total=total)
-        pinned_out.copy_(states, non_blocking=True)              # D2H of the results (final states + scores)
-        stream.synchronize()
+        host_api.run(pinned_inputs[k % len(pinned_inputs)], pinned_out)   # returns after the D2H completed
     e1.record(stream)
     barrier()
+    total.copy_(host_api.total)
     e2e_ms = e0.elapsed_time(e1)
     e2e_steps = int(total.item())
     t2 = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
@@ -403,7 +402,33 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         dist.all_reduce(s2, op=dist.ReduceOp.SUM)
-    e2e_value = int(s2.item()) / (float(t2.item()) * 1e-3)
+    e2e_full_value = int(s2.item()) / (float(t2.item()) * 1e-3)
+
+    # ---- end to end, the natural call for this workload: fresh games are defined by their 64-bit
+    # keys (HarmoniesGameState() takes no input), so each step sends n keys from pinned host
+    # memory and reads back (winner/meta, final scores, length) per game: HostPlayout.run_keys
+    import numpy as np
+
+    rng = np.random.default_rng(1234 + rank)
+    pinned_keys = [torch.from_numpy(rng.integers(-2**63, 2**63 - 1, size=n, dtype=np.int64)).pin_memory() for _ in range(min(K, 4))]
+    pinned_res = torch.empty((n, 3), dtype=torch.int32).pin_memory()
+    for w in range(2):
+        host_api.run_keys(pinned_keys[0], pinned_res)
+    host_api.total.zero_()
+    barrier()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record(stream)
+    for k in range(K):
+        host_api.run_keys(pinned_keys[k % len(pinned_keys)], pinned_res)   # returns after the D2H completed
+    k1.record(stream)
+    barrier()
+    t3 = torch.tensor([k0.elapsed_time(k1)], dtype=torch.float64, device=dev)
+    s3 = host_api.total.clone()
+    if world > 1:
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s3, op=dist.ReduceOp.SUM)
+    e2e_value = int(s3.item()) / (float(t3.item()) * 1e-3)
+    assert int((pinned_res[:, 0] >> 29).min()) >= 1, "every game must have a winner code"
 
     # ---- the same wave with unfused per-step kernels (K1 legal_mask + policy + K2 apply): the
     # state makes an HBM/L2 round trip every step, which is what the 258 B/step roofline models
@@ -441,7 +466,10 @@ def run_b200(args):
         "config": {"workload": "random playouts, 65,536 concurrent 2-player games per GPU, engine only (configs[1])",
                    "games_per_gpu": n, "engine_steps_per_wave": steps_all // K,
                    "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"games sharded x{world}, no collective"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 128, "d2h_bytes_per_step": n * 128},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 12,
+                "api": "HostPlayout.run_keys: pinned host keys in, (meta, scores, length) per game out"},
+        "e2e_full_records": {"value": e2e_full_value, "unit": UNIT, "h2d_bytes_per_step": n * 128, "d2h_bytes_per_step": n * 128,
+                             "api": "HostPlayout.run: 128-byte records in and out, 4 chunks on 4 streams (PCIe-bound)"},
         "gpu_launches": launches_all,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",

@@ -161,5 +161,64 @@ def playout(states, max_steps=1000, steps=None, total=None):
     return steps, total
 
 
+class HostPlayout:
+    """Playouts on HOST buffers: ``run(states_in, states_out)`` takes pinned int32[n,32] host
+    tensors, plays every game to the end on the GPU and returns the final records in
+    ``states_out``.  The batch is cut into chunks that travel on separate CUDA streams, so the
+    H2D copy of one chunk, the kernel of another and the D2H copy of a third overlap (PCIe is
+    full duplex); device staging buffers are allocated once."""
+
+    def __init__(self, n, device="cuda", chunks=4, max_steps=1000):
+        self.n, self.max_steps = int(n), int(max_steps)
+        self.device = torch.device(device)
+        self.chunks = max(1, min(int(chunks), self.n))
+        self.bounds = [self.n * c // self.chunks for c in range(self.chunks + 1)]
+        self.dev_states = torch.empty((self.n, 32), dtype=torch.int32, device=self.device)
+        self.steps = torch.empty(self.n, dtype=torch.int32, device=self.device)
+        self.total = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.chunks)]
+
+    def run(self, states_in, states_out):
+        if not (states_in.is_pinned() and states_out.is_pinned()):
+            raise ValueError("host buffers must be pinned")
+        if states_in.shape != (self.n, 32) or states_out.shape != (self.n, 32) or states_in.dtype != torch.int32:
+            raise TypeError("host buffers must be int32[n, 32]")
+        main = torch.cuda.current_stream(self.device)
+        for c, st in enumerate(self.streams):
+            lo, hi = self.bounds[c], self.bounds[c + 1]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                d = self.dev_states[lo:hi]
+                d.copy_(states_in[lo:hi], non_blocking=True)
+                playout(d, self.max_steps, steps=self.steps[lo:hi], total=self.total)
+                states_out[lo:hi].copy_(d, non_blocking=True)
+        for st in self.streams:
+            main.wait_stream(st)
+        main.synchronize()
+        return states_out
+
+    def run_keys(self, keys_in, results_out):
+        """Fresh games from their 64-bit keys: ``keys_in`` pinned int64[n] (one draw-stream key
+        per game: HarmoniesGameState.__init__ is hz_init_states on the device), plays them to
+        the end and fills ``results_out`` pinned int32[n, 3] with (meta word incl. winner,
+        final_scores word, number of actions).  12 bytes back per game instead of 128."""
+        if not (keys_in.is_pinned() and results_out.is_pinned()):
+            raise ValueError("host buffers must be pinned")
+        if keys_in.shape != (self.n,) or keys_in.dtype != torch.int64 or results_out.shape != (self.n, 3):
+            raise TypeError("keys int64[n], results int32[n, 3]")
+        lib = _lib.load()
+        main = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "dev_keys"):
+            self.dev_keys = torch.empty(self.n, dtype=torch.int64, device=self.device)
+            self.cols = torch.tensor([22, 23, 27], device=self.device)
+        self.dev_keys.copy_(keys_in, non_blocking=True)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.hz_init_states(_ptr(self.dev_states), self.n, _ptr(self.dev_keys), 0, 0, main.cuda_stream), "hz_init_states")
+        playout(self.dev_states, self.max_steps, steps=self.steps, total=self.total)
+        results_out.copy_(self.dev_states.index_select(1, self.cols), non_blocking=True)
+        main.synchronize()
+        return results_out
+
+
 def launch_count():
     return int(_lib.load().hz_launch_count())

@@ -189,6 +189,21 @@ def test_fused_playout_equals_unfused_and_oracle(hb, oracle):
     assert torch.equal(st2, st3)
 
 
+def test_host_buffer_api_equals_device_path(hb):
+    """HostPlayout.run (pinned host in/out, chunked over streams) == hz_playout on device"""
+    n = 10000
+    st = hb.init_states(n, seed=321)
+    pin_in = st.cpu().pin_memory()
+    pin_out = torch.empty((n, 32), dtype=torch.int32).pin_memory()
+    api = hb.HostPlayout(n, chunks=3)
+    out = api.run(pin_in, pin_out)
+    steps, total = hb.playout(st)
+    assert torch.equal(out, st.cpu()) and int(api.total.item()) == int(total.item())
+    assert torch.equal(api.steps.cpu(), steps.cpu())
+    with pytest.raises(ValueError):
+        api.run(st.cpu(), pin_out)          # not pinned
+
+
 def test_score_encode_hash_vs_oracle_on_random_positions(hb, oracle):
     n = 30000
     st = hb.init_states(n, seed=9)
