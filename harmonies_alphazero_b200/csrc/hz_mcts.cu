@@ -112,11 +112,63 @@ __device__ __forceinline__ void warp_encode(const uint32_t* w, uint32_t* smask, 
     __syncwarp();
 }
 
+// Fast leaf encoder for the self-play layout (bf16, NHWC40): the 40 channels of a cell are
+// 5 bytes of bits (<= 3+3 tile codes + player + phase), and 8 bits expand to a 16-byte vector
+// of bf16 0.0/1.0 by one table lookup: 35 cells x 5 vectors = 175 16-byte stores per leaf
+// instead of 1,400 scalar ones.
+__device__ __forceinline__ void warp_encode_fast40(const uint32_t* w, uint8_t* sbytes, const uint4* vlut8,
+                                                   const uint8_t* scell, __nv_bfloat16* board, __nv_bfloat16* glob, int lane) {
+    uint32_t m = w[HZ_W_BAG1META] >> 24, ph = (m >> 1) & 7u;
+    bool player1 = (m & 1u) != 0, phase_on = ph >= 1 && ph <= 3;
+    for (int cell = lane; cell < 35; cell += 32) {
+        int hx = scell[cell];
+        uint64_t bits = 0;
+        if (hx < 23) {
+#pragma unroll
+            for (int pl = 0; pl < 6; pl++) {
+                uint32_t code = ((w[pl * 3] >> hx) & 1u) | (((w[pl * 3 + 1] >> hx) & 1u) << 1) | (((w[pl * 3 + 2] >> hx) & 1u) << 2);
+                int p = pl / 3, l = pl - 3 * p;
+                if (code) bits |= 1ull << (p * 18 + ((int)code - 1) * 3 + l);
+            }
+            if (player1) bits |= 1ull << 36;
+            if (phase_on) bits |= 1ull << 37;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) sbytes[cell * 5 + k] = (uint8_t)(bits >> (8 * k));
+    }
+    __syncwarp();
+    float pv = ph == 1 ? (float)(1.0 / 3.0) : ph == 2 ? (float)(2.0 / 3.0) : 1.0f;
+    uint32_t pb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(pv));
+    uint4* out = reinterpret_cast<uint4*>(board);
+    for (int v = lane; v < 175; v += 32) {
+        uint32_t byte = sbytes[v];
+        uint4 o = vlut8[byte];
+        if (v % 5 == 4 && (byte & 0x20u)) o.z = (o.z & 0x0000FFFFu) | (pb << 16);   // channel 37 = phase/3
+        out[v] = o;
+    }
+    for (int g = lane; g < 42; g += 32) glob[g] = __float2bfloat16_rn(global_feature(w, g));
+    __syncwarp();
+}
+
 // ---- select: move_to_leaf (MCTS.py:63-149) + create_state_tensors(leaf) (MCTS.py:299) ---------
 template <typename OT, int LAYOUT>
 __global__ void __launch_bounds__(TTPB) k_tree_select(hz_tree T, float cpuct, uint4* leaf_states, OT* board, OT* glob) {
     __shared__ uint32_t sm_words[WPB][32];
     __shared__ uint32_t sm_mask[WPB][40];
+    constexpr bool FAST40 = LAYOUT == HZ_LAYOUT_NHWC40 && sizeof(OT) == 2;
+    __shared__ uint4 vlut8[FAST40 ? 256 : 1];
+    __shared__ uint8_t sbytes[FAST40 ? WPB : 1][176];
+    __shared__ uint8_t scell[36];
+    if (FAST40) {
+        for (int i = threadIdx.x; i < 256; i += TTPB) {
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) o[j] = (((i >> (2 * j)) & 1) ? 0x3F80u : 0u) | (((i >> (2 * j + 1)) & 1) ? 0x3F800000u : 0u);
+            vlut8[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        if (threadIdx.x < 35) scell[threadIdx.x] = CELL_HEX[threadIdx.x];
+        __syncthreads();
+    }
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t = blockIdx.x * WPB + warp;
     if (t >= T.n_trees) return;
@@ -171,7 +223,13 @@ __global__ void __launch_bounds__(TTPB) k_tree_select(hz_tree T, float cpuct, ui
     if (lane == 0) { T.leaf[t] = node; T.depth[t] = depth; }
     warp_load_words(sm_words[warp], v.node_state, node, lane);
     if (leaf_states) reinterpret_cast<uint32_t*>(leaf_states + (size_t)t * 8)[lane] = sm_words[warp][lane];
-    if (board) warp_encode<OT, LAYOUT>(sm_words[warp], sm_mask[warp], board + (size_t)t * RowElems<LAYOUT>::value, glob + (size_t)t * 42, lane);
+    if (board) {
+        if constexpr (FAST40)
+            warp_encode_fast40(sm_words[warp], sbytes[warp], vlut8, scell, (__nv_bfloat16*)board + (size_t)t * 1400,
+                               (__nv_bfloat16*)glob + (size_t)t * 42, lane);
+        else
+            warp_encode<OT, LAYOUT>(sm_words[warp], sm_mask[warp], board + (size_t)t * RowElems<LAYOUT>::value, glob + (size_t)t * 42, lane);
+    }
 }
 
 // ---- transposition lookup (MCTS.py:184-186) ------------------------------------------------------
@@ -210,7 +268,7 @@ __device__ __forceinline__ void table_insert(const hz_tree& T, const TreeView& v
 }
 
 // ---- expand_leaf + terminal value + back_fill (MCTS.py:151-264, 297-352) -------------------------
-__global__ void __launch_bounds__(TTPB) k_tree_expand_backup(hz_tree T, const float* policy, const float* value,
+__global__ void __launch_bounds__(TTPB, 4) k_tree_expand_backup(hz_tree T, const float* policy, const float* value,
                                                              int is_logits, const float* noise, double eps) {
     __shared__ uint32_t sm_words[WPB][32];
     // scoring happens only for children that end the game: read the neighbour LUT in place

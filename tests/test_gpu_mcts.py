@@ -87,6 +87,36 @@ def test_many_roots_vs_oracle(mods, oracle, key_mode):
         assert nn[i] == r["n_nodes"] and ne[i] == r["n_edges"], i
 
 
+def test_full_size_config3_properties_and_oracle_subsample(mods, oracle):
+    """BASELINE.json configs[3] sizes: 4,096 trees x 100 simulations (synthetic evaluator).
+    Size-independent properties on all trees, identical visit counts vs the oracle on a
+    192-tree subsample, default (derived) search keys."""
+    hb, tr = mods
+    n, sims = 4096, 100
+    st = hb.init_states(n, seed=4040)
+    hb.playout(st, max_steps=10)
+    t = tr.BatchedMCTS(n, sims)
+    t.reset(st)                                   # keys = rand(game key ^ SEARCH_SALT, moves)
+    t.run_synthetic(sims, 2.0)
+    t.check_status()
+    N, W, P, child = (x.cpu().numpy() for x in t.root_edges())
+    nn, ne, _ = (x.cpu().numpy() for x in t.stats())
+    assert (N.sum(axis=1) == sims - 1).all()                       # MCTS.py:355-381: sum N = S - 1
+    legal = hb.legal_mask(st).cpu().numpy().view(np.uint32)
+    for i in range(0, n, 97):
+        acts = pk.mask_to_actions(legal[i])
+        assert set(np.nonzero(child[i] >= 0)[0].tolist()) == set(acts)     # one root edge per legal move
+        assert set(np.nonzero(N[i])[0].tolist()) <= set(acts)
+    assert (np.abs(W) <= N + 1e-9).all() and (nn <= 1 + 69 * sims).all() and (ne >= nn - 1).all()
+    words = st.cpu().numpy().view(np.uint32)
+    for i in range(0, n, 22)[:192]:
+        f = pk.unpack_fields(words[i])
+        skey = pk.rand(f["rng_key"] ^ pk.SEARCH_SALT, f["moves"])
+        r = oracle.search(words[i], skey, sims, 2.0)
+        assert np.array_equal(N[i], r["N"]) and np.array_equal(W[i], r["W"]), i
+        assert nn[i] == r["n_nodes"] and ne[i] == r["n_edges"], i
+
+
 def test_select_outputs_leaf_encoding(mods, oracle):
     """the tensors handed to the network are create_state_tensors(leaf) (MCTS.py:299)"""
     hb, tr = mods

@@ -171,6 +171,38 @@ def test_selfplay_games_and_example_contract(mods, oracle):
     assert np.array_equal(b.numpy(), ob[0]) and np.array_equal(gl.numpy(), og[0])
 
 
+def test_replay_ring_matches_reference_deque_semantics(mods, oracle):
+    """f2: packed GPU ring == deque(maxlen) of the reference tuples (buffer.py, trainer.py:127)"""
+    hb, net, sp, _ = mods
+    from collections import deque
+
+    from harmonies_alphazero_b200.replay import ReplayRing
+
+    _, inf = _small_net(net, torch.bfloat16, seed=4)
+    cfg = sp.SelfPlayConfig(n_slots=32, num_simulations=5, testing=True, seed=21)
+    ring, ref = ReplayRing(500), deque(maxlen=500)
+    for it in range(3):                                   # 3 x 6 games ~ 1100 examples > capacity
+        traj = sp.BatchedSelfPlay(inf, sp.SelfPlayConfig(n_slots=32, num_simulations=5, testing=True, seed=21 + it)).play(6)
+        ring.extend(traj)
+        ref.extend(traj.to_reference_examples())
+    assert len(ring) == len(ref) == 500
+    got = ring.to_reference_buffer()
+    assert got.maxlen == 500 and len(got) == 500
+    for k in (0, 1, 250, 499):
+        for a, b in zip(got[k], ref[k]):
+            assert torch.equal(a, b)
+    board, glob, pi, z = ring.sample(64)
+    assert board.shape == (64, 38, 5, 7) and glob.shape == (64, 42) and pi.shape == (64, 143) and z.shape == (64, 1)
+    assert board.is_cuda and torch.allclose(pi.sum(1), torch.ones(64, device="cuda"), atol=1e-6)
+    seen = sum(b.shape[0] for b, _, _, _ in ring.epoch(128))
+    assert seen == 500
+    ring2 = ReplayRing(500)
+    ring2.load_state_dict(ring.state_dict())
+    for a, b in zip(ring2.to_reference_buffer()[123], got[123]):
+        assert torch.equal(a, b)
+    del cfg
+
+
 def test_arena_match(mods):
     """candidate-vs-best evaluation (trainer.py:293-431) batched over all eval games"""
     hb, net, _, _ = mods
