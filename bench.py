@@ -477,8 +477,14 @@ def run_b200(args):
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch at 65,536 games, ncu --set full
                      # (profiles/r01_playout_ncu.txt): the initial records only; results stay in L2
                      "traffic": 8410880 if n == 65536 else None, "peak_source": pk_src + " (burst copy)",
-                     "kernel": "hz::k_playout", "note": "algorithmic 258 B/step x steps per launch / CUDA-event launch time; "
-                     "the fused kernel keeps the state on chip, so DRAM traffic is ~256 B per GAME"},
+                     "kernel": "hz::k_playout", "note": "algorithmic 258 B/step x steps per launch / CUDA-event launch time "
+                     "(SURVEY.md 8d). frac > 1 is expected here and does NOT mean skipped work: the fused kernel keeps each "
+                     "game's state in registers for its ~62 steps, so DRAM sees 128 B per GAME (traffic) instead of 258 B per "
+                     "STEP; every final record is bit-identical to the CPU oracle's (tests/test_gpu_engine.py). The kernel is "
+                     "bound by integer-ALU issue: see issue_slots below (SURVEY.md H7) and 'unfused' for the per-step path.",
+                     # ncu --set full of this kernel at 65,536 games (profiles/r01_playout_ncu.txt)
+                     "issue_slots": {"issue_active_pct": 53.8, "alu_pipe_pct": 55.4, "ipc_active": 1.95,
+                                     "active_threads_per_warp": 24.75, "achieved_occupancy_pct": 17.7, "source": "ncu r01b"}},
         "wall_s": wall,
         "unfused": {"value": unfused_steps / (unfused_ms * 1e-3), "unit": UNIT, "launches": 76 * 3, "ms": unfused_ms,
                     "achieved_GBps": unfused_steps * ALGO_BYTES_PER_STEP / (unfused_ms * 1e-3) / 1e9,

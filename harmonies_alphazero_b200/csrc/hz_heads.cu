@@ -42,7 +42,7 @@ struct HeadParams {
 __global__ void __launch_bounds__(HTPB) k_heads(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ glob,
                                                 int64_t n, HeadParams P, float* __restrict__ logits,
                                                 float* __restrict__ value) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     float* s_wc = smem;                         // [3][C]
     float* s_pin = s_wc + 3 * P.C;              // [HP][112]  policy FC input per position
     float* s_vin = s_pin + HP * PIN;            // [HP][80]   value FC input per position (77 used)
@@ -61,18 +61,23 @@ __global__ void __launch_bounds__(HTPB) k_heads(const __nv_bfloat16* __restrict_
             int p = t / CELLS, cell = t - CELLS * p;
             const uint4* row = reinterpret_cast<const uint4*>(x + ((base + p) * CELLS + cell) * (int64_t)C);
             float a0 = bc0, a1 = bc1, a2 = bc2;
+            const float4* w0 = reinterpret_cast<const float4*>(s_wc);
+            const float4* w1 = reinterpret_cast<const float4*>(s_wc + C);
+            const float4* w2 = reinterpret_cast<const float4*>(s_wc + 2 * C);
+#pragma unroll 4
             for (int v = 0; v < C / 8; v++) {
                 uint4 q = row[v];
                 const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    float2 f = __bfloat1622float2(h[j]);
-                    int c = v * 8 + 2 * j;
-                    // explicit fmaf: the library is built with --fmad=false for the search arithmetic
-                    a0 = fmaf(f.y, s_wc[c + 1], fmaf(f.x, s_wc[c], a0));
-                    a1 = fmaf(f.y, s_wc[C + c + 1], fmaf(f.x, s_wc[C + c], a1));
-                    a2 = fmaf(f.y, s_wc[2 * C + c + 1], fmaf(f.x, s_wc[2 * C + c], a2));
-                }
+                float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+                float2 f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+                // explicit fmaf: the library is built with --fmad=false for the search arithmetic
+#define HZ_DOT8(acc, W)                                                                              \
+                { float4 wa = W[2 * v], wb = W[2 * v + 1];                                               \
+                  acc = fmaf(f0.x, wa.x, acc); acc = fmaf(f0.y, wa.y, acc); acc = fmaf(f1.x, wa.z, acc); \
+                  acc = fmaf(f1.y, wa.w, acc); acc = fmaf(f2.x, wb.x, acc); acc = fmaf(f2.y, wb.y, acc); \
+                  acc = fmaf(f3.x, wb.z, acc); acc = fmaf(f3.y, wb.w, acc); }
+                HZ_DOT8(a0, w0) HZ_DOT8(a1, w1) HZ_DOT8(a2, w2)
+#undef HZ_DOT8
             }
             s_pin[p * PIN + cell] = fmaxf(a0, 0.0f);            // channel-major flatten (model.py:343)
             s_pin[p * PIN + CELLS + cell] = fmaxf(a1, 0.0f);
@@ -85,36 +90,80 @@ __global__ void __launch_bounds__(HTPB) k_heads(const __nv_bfloat16* __restrict_
             s_vin[p * 80 + CELLS + g] = gv;
         }
         __syncthreads();
-        // ---- policy FC 112 -> 143: thread = action, 7 positions as 7 accumulators
-        if (t < NPOL) {
-            float acc[HP];
-#pragma unroll
-            for (int p = 0; p < HP; p++) acc[p] = P.b_pol[t];
-            for (int j = 0; j < PIN; j++) {
-                float w = __ldg(P.w_pol_t + j * NPOL + t);
-#pragma unroll
-                for (int p = 0; p < HP; p++) acc[p] = fmaf(w, s_pin[p * PIN + j], acc[p]);
-            }
-#pragma unroll
-            for (int p = 0; p < HP; p++)
-                if (p < cnt) logits[(base + p) * NPOL + t] = acc[p];
-        }
-        // ---- value FC 77 -> H -> ReLU -> dot w2: thread = hidden unit (strided if H > 256)
+        // The two FC stacks run side by side: warps 0-2 the policy FC, warps 3-7 the value FCs.
+        // Each thread owns TWO output units x 7 positions (14 accumulators) and reads the
+        // inputs as float4 along j, so an inner step is 7 LDS.128 + 8 LDG + 56 FMA.
         float part[HP];
 #pragma unroll
         for (int p = 0; p < HP; p++) part[p] = 0.0f;
-        for (int u = t; u < H; u += HTPB) {
-            float acc[HP];
+        if (t < 96) {
+            // ---- policy FC 112 -> 143 (model.py:344-347)
+            if (t < 72) {
+                int a0i = t, a1i = t + 72;
+                bool has1 = a1i < NPOL;
+                int a1c = has1 ? a1i : a0i;
+                float acc0[HP], acc1[HP];
 #pragma unroll
-            for (int p = 0; p < HP; p++) acc[p] = P.b_v1[u];
-            for (int j = 0; j < VIN; j++) {
-                float w = __ldg(P.w_v1_t + j * H + u);
+                for (int p = 0; p < HP; p++) { acc0[p] = P.b_pol[a0i]; acc1[p] = P.b_pol[a1c]; }
+#pragma unroll 2
+                for (int j = 0; j < PIN; j += 4) {
+                    float wa[4], wb[4];
 #pragma unroll
-                for (int p = 0; p < HP; p++) acc[p] = fmaf(w, s_vin[p * 80 + j], acc[p]);
+                    for (int k = 0; k < 4; k++) { wa[k] = __ldg(P.w_pol_t + (j + k) * NPOL + a0i); wb[k] = __ldg(P.w_pol_t + (j + k) * NPOL + a1c); }
+#pragma unroll
+                    for (int p = 0; p < HP; p++) {
+                        float4 in = *reinterpret_cast<const float4*>(s_pin + p * PIN + j);
+                        acc0[p] = fmaf(wa[0], in.x, acc0[p]); acc0[p] = fmaf(wa[1], in.y, acc0[p]);
+                        acc0[p] = fmaf(wa[2], in.z, acc0[p]); acc0[p] = fmaf(wa[3], in.w, acc0[p]);
+                        acc1[p] = fmaf(wb[0], in.x, acc1[p]); acc1[p] = fmaf(wb[1], in.y, acc1[p]);
+                        acc1[p] = fmaf(wb[2], in.z, acc1[p]); acc1[p] = fmaf(wb[3], in.w, acc1[p]);
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < HP; p++) {
+                    if (p < cnt) {
+                        logits[(base + p) * NPOL + a0i] = acc0[p];
+                        if (has1) logits[(base + p) * NPOL + a1i] = acc1[p];
+                    }
+                }
             }
-            float w2 = P.w_v2[u];
+        } else {
+            // ---- value FC 77 -> H -> ReLU -> dot w2 (model.py:352-354): units u and u + H/2
+            int half = H / 2;
+            for (int u = t - 96; u < half; u += HTPB - 96) {
+                int u1 = u + half;
+                float acc0[HP], acc1[HP];
 #pragma unroll
-            for (int p = 0; p < HP; p++) part[p] = fmaf(fmaxf(acc[p], 0.0f), w2, part[p]);
+                for (int p = 0; p < HP; p++) { acc0[p] = P.b_v1[u]; acc1[p] = P.b_v1[u1]; }
+#pragma unroll 2
+                for (int j = 0; j < 76; j += 4) {
+                    float wa[4], wb[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { wa[k] = __ldg(P.w_v1_t + (j + k) * H + u); wb[k] = __ldg(P.w_v1_t + (j + k) * H + u1); }
+#pragma unroll
+                    for (int p = 0; p < HP; p++) {
+                        float4 in = *reinterpret_cast<const float4*>(s_vin + p * 80 + j);
+                        acc0[p] = fmaf(wa[0], in.x, acc0[p]); acc0[p] = fmaf(wa[1], in.y, acc0[p]);
+                        acc0[p] = fmaf(wa[2], in.z, acc0[p]); acc0[p] = fmaf(wa[3], in.w, acc0[p]);
+                        acc1[p] = fmaf(wb[0], in.x, acc1[p]); acc1[p] = fmaf(wb[1], in.y, acc1[p]);
+                        acc1[p] = fmaf(wb[2], in.z, acc1[p]); acc1[p] = fmaf(wb[3], in.w, acc1[p]);
+                    }
+                }
+                {   // j = 76 (VIN = 77)
+                    float wa = __ldg(P.w_v1_t + 76 * H + u), wb = __ldg(P.w_v1_t + 76 * H + u1);
+#pragma unroll
+                    for (int p = 0; p < HP; p++) {
+                        float in = s_vin[p * 80 + 76];
+                        acc0[p] = fmaf(wa, in, acc0[p]); acc1[p] = fmaf(wb, in, acc1[p]);
+                    }
+                }
+                float w2a = P.w_v2[u], w2b = P.w_v2[u1];
+#pragma unroll
+                for (int p = 0; p < HP; p++) {
+                    part[p] = fmaf(fmaxf(acc0[p], 0.0f), w2a, part[p]);
+                    part[p] = fmaf(fmaxf(acc1[p], 0.0f), w2b, part[p]);
+                }
+            }
         }
 #pragma unroll
         for (int p = 0; p < HP; p++) {
@@ -144,7 +193,7 @@ extern "C" int hz_net_heads(const void* x, const void* glob, int64_t n, int C, i
     if (n == 0) return HZ_OK;
     if (!x || !glob || !w_conv || !b_conv || !w_pol_t || !b_pol || !w_v1_t || !b_v1 || !w_v2 || !logits || !value)
         return HZ_ERR_ARG;
-    if (n < 0 || C <= 0 || (C % 8) != 0 || H <= 0 || ((uintptr_t)x & 15)) return HZ_ERR_ARG;
+    if (n < 0 || C <= 0 || (C % 8) != 0 || H <= 0 || (H % 2) != 0 || ((uintptr_t)x & 15)) return HZ_ERR_ARG;
     hz::HeadParams P{w_conv, b_conv, w_pol_t, b_pol, w_v1_t, b_v1, w_v2, b_v2, C, H};
     size_t smem = sizeof(float) * (size_t)(3 * C + hz::HP * hz::PIN + hz::HP * 80 + hz::HP * 8);
     int64_t groups = (n + hz::HP - 1) / hz::HP;

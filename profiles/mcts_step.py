@@ -41,4 +41,37 @@ for _ in range(a.steps):
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 drv.tree.check_status()
-print("ok")
+
+# CUDA-event timing of the four parts of one simulation step (eager, warm L2), median of 20
+g = drv.groups[0]
+
+
+def timed(fn, reps=20):
+    ms = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1) * 1e3)
+    return sorted(ms)[len(ms) // 2]
+
+
+parts = {}
+for _ in range(3):
+    parts["select_us"] = timed(lambda: g.tree.select(cfg.cpuct, g.board, g.glob, dtype=inf.dtype, channels_last=True, pad40=drv.pad40), 1)
+    x = inf._conv_relu(g.board, inf.stem40 if drv.pad40 else inf.stem, 1)
+
+    def tower():
+        global x
+        x = inf._conv_relu(g.board, inf.stem40 if drv.pad40 else inf.stem, 1)
+        for c1, c2 in inf.blocks:
+            y = inf._conv_relu(x, c1, 1)
+            x = inf._conv_relu(y, c2, 1, residual=x)
+
+    parts["tower_us"] = timed(tower, 5)
+    parts["heads_us"] = timed(lambda: inf._fused_heads(x, g.glob, (g.logits, g.value)), 5)
+    parts["expand_us"] = timed(lambda: g.tree.expand_backup(g.logits, g.value, is_logits=True, noise=g.noise, eps=cfg.dirichlet_epsilon), 1)
+parts["step_sum_us"] = sum(v for k, v in parts.items())
+import json  # noqa: E402
+
+print(json.dumps(parts))
