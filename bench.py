@@ -483,8 +483,8 @@ def run_b200(args):
                      "STEP; every final record is bit-identical to the CPU oracle's (tests/test_gpu_engine.py). The kernel is "
                      "bound by integer-ALU issue: see issue_slots below (SURVEY.md H7) and 'unfused' for the per-step path.",
                      # ncu --set full of this kernel at 65,536 games (profiles/r01_playout_ncu.txt)
-                     "issue_slots": {"issue_active_pct": 53.8, "alu_pipe_pct": 55.4, "ipc_active": 1.95,
-                                     "active_threads_per_warp": 24.75, "achieved_occupancy_pct": 17.7, "source": "ncu r01b"}},
+                     "issue_slots": {"issue_active_pct": 57.9, "alu_pipe_pct": 50.6, "ipc_active": 2.12,
+                                     "active_threads_per_warp": 25.76, "achieved_occupancy_pct": 18.6, "source": "ncu r01c"}},
         "wall_s": wall,
         "unfused": {"value": unfused_steps / (unfused_ms * 1e-3), "unit": UNIT, "launches": 76 * 3, "ms": unfused_ms,
                     "achieved_GBps": unfused_steps * ALGO_BYTES_PER_STEP / (unfused_ms * 1e-3) / 1e9,
