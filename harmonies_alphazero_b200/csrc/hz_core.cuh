@@ -456,7 +456,7 @@ __device__ __forceinline__ int apply_move(State& s, int a, uint32_t explicit_cod
         np++;
     }
     set_bag(s, bag);
-    set_piles(s, P, 0, np);
+    set_piles(s, P, hand, np);   // the reference does not clear a (non-standard) leftover hand at end of turn
     if (bump_event) s.w[HZ_W_EVENT]++;
     bool triggered = player_trigger || (bag_empty_before && np == 0);  // :309-311
     bool ending = ending_of(s);

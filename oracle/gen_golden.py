@@ -363,9 +363,79 @@ def gen_mcts():
     print(f"mcts: {len(cases)} searches, {tot} sims in {dt:.1f}s ({tot / dt:.0f} sims/s reference+fake eval)")
 
 
+# --------------------------------------------------------------------------------------
+_ERR = [("Invalid pile index", 1), ("Invalid move format", 2), ("Invalid coordinate", 3),
+        ("not found in hand", 4), ("Cannot place", 5), ("Invalid turn phase", 6)]
+
+
+def gen_weird(n=1500, per_state=8):
+    """States the standard game never reaches but the reference code accepts (via
+    initial_state, harmonies_engine.py:67-68): 0-5 piles of 1-3 tiles, hands of 0-3 tiles in
+    any phase, nearly empty bags (partial piles, several piles drawn in one replenish, bag-empty
+    end trigger), arbitrary stacks, stray `game_over` flags.  For each state: the reference's
+    legal moves and, for a handful of actions (legal or not), the resulting state or the
+    ValueError site — with the library's stream draws (key/event of the state)."""
+    ref = rh.load_reference()
+    G, gai = ref["G"], ref["pgs"].get_action_index
+    rng = random.Random(777)
+    phases = ["choose_pile", "place_tile_1", "place_tile_2", "place_tile_3", "game_over"]
+    states, legal, actions, status, after = [], [], [], [], []
+    for i in range(n):
+        boards = []
+        for p in (0, 1):
+            occ = rng.choice([0.0, 0.3, 0.7, 0.9, 1.0])
+            b = {}
+            for c in sorted_coords:
+                if rng.random() < occ:
+                    b[c] = [rng.choice(TILE_TYPES) for _ in range(rng.choice([1, 1, 2, 3]))]
+            boards.append(b)
+        phase = rng.choice(phases)
+        over = phase == "game_over"
+        fields = {
+            "player_boards": boards,
+            "tile_bag": {t: rng.choice([0, 0, 1, 2, 4]) for t in ["water", "plant", "wood", "stone", "field", "building"]},
+            "available_piles": [[rng.choice(TILE_TYPES) for _ in range(rng.choice([1, 2, 3, 3]))] for _ in range(rng.randrange(6))],
+            "current_player": rng.randrange(2),
+            "tiles_in_hand": [rng.choice(TILE_TYPES) for _ in range(rng.randrange(4))],
+            "turn_phase": phase,
+            "game_over": over or rng.random() < 0.3,
+            "winner": rng.choice([0, 1, -1]) if over else None,
+            "final_scores": [rng.randrange(40), rng.randrange(40)] if over else [0, 0],
+        }
+        key, event, moves = pk.rand(0xC0DE, i), rng.randrange(1, 30), rng.randrange(100)
+        base = G(initial_state=fields)
+        w = pk.pack_state(base, rng_key=key, rng_event=event, moves=moves)
+        lm = base.get_legal_moves()
+        legal_idx = [gai(m) for m in lm]
+        cand = set(rng.sample(legal_idx, min(len(legal_idx), per_state // 2)))
+        while len(cand) < per_state:
+            cand.add(rng.randrange(0, 143))
+        for a in sorted(cand):
+            rh.ctx.mode, rh.ctx.key, rh.ctx.event, rh.ctx.k = "stream", key, event, 0
+            try:
+                nxt = base.apply_move(pk.action_to_move(a))
+                st = 0
+                aw = pk.pack_state(nxt, rng_key=key, rng_event=rh.ctx.event, moves=moves + 1)
+            except ValueError as e:
+                st = next(code for msg, code in _ERR if msg in str(e))
+                aw = w
+            states.append(w); legal.append(pk.actions_to_mask(legal_idx)); actions.append(a); status.append(st); after.append(aw)
+    rh.ctx.mode = "python"
+    np.savez_compressed(
+        os.path.join(OUT, "weird.npz"),
+        states=np.array(states, dtype=np.uint32), legal=np.array(legal, dtype=np.uint32),
+        action=np.array(actions, dtype=np.int16), status=np.array(status, dtype=np.uint8),
+        after=np.array(after, dtype=np.uint32),
+    )
+    st = np.array(status)
+    print(f"weird: {len(states)} (state, action) pairs, status histogram {np.bincount(st, minlength=7).tolist()}")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["engine", "scoring", "encode", "equiv", "mcts"]
+    which = sys.argv[1:] or ["engine", "scoring", "encode", "equiv", "mcts", "weird"]
+    if "weird" in which:
+        gen_weird()
     tb = ta = ss = None
     if "engine" in which or "encode" in which:
         tb, ta = gen_engine()

@@ -102,6 +102,26 @@ def test_golden_encode_fp32_bit_exact(hb):
         assert torch.equal(b3.contiguous(), b.to(torch.bfloat16)) and torch.equal(gl3, gl.to(torch.bfloat16))
 
 
+def test_golden_weird_states(hb):
+    """non-standard states the reference accepts through initial_state: ragged piles, leftover
+    hands, nearly empty bags (partial piles, multi-pile replenish, bag-empty end), stray flags"""
+    g = load_golden("weird")
+    st = dev(g["states"])
+    assert np.array_equal(host(hb.legal_mask(st)), g["legal"])
+    status = hb.apply(st, i16(g["action"]))
+    assert np.array_equal(status.cpu().numpy(), g["status"])
+    assert np.array_equal(host(st)[:, :28], g["after"][:, :28])
+    # the fused playout must agree with the unfused kernels from these states too
+    live = g["status"] == 0
+    a, b = dev(g["after"][live]), dev(g["after"][live])
+    hb.playout(a, max_steps=7)
+    for _ in range(7):
+        act = hb.random_actions(b)
+        hb.apply(b, torch.where(act >= 0, act, torch.zeros_like(act)))
+    stuck_ok = host(a)[:, :28] == host(b)[:, :28]
+    assert stuck_ok.all()
+
+
 def test_golden_equivalence_classes(hb):
     g = load_golden("equiv")
     st = dev(g["states"])

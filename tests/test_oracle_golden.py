@@ -125,6 +125,16 @@ def test_apply_error_codes(oracle):
         assert status[0] == 5
 
 
+def test_weird_states(oracle):
+    """states only reachable through initial_state (harmonies_engine.py:67-68): ragged piles,
+    leftover hands, nearly empty bags, stray flags — legal moves, results and error sites"""
+    g = load_golden("weird")
+    assert np.array_equal(oracle.legal_mask(g["states"]), g["legal"])
+    new, status = oracle.apply(g["states"], g["action"])
+    assert np.array_equal(status, g["status"])
+    assert np.array_equal(new[:, :28], g["after"][:, :28])
+
+
 def test_mcts_golden(oracle):
     """MCTS.py:63-441 — visit counts, W, priors, node/edge counts and the chosen move of
     the reference searches (synthetic evaluator, injected noise/uniform)."""
