@@ -299,6 +299,15 @@ def gen_mcts():
             cases.append((traj[m][0], key, m, traj[m][2]))
         if g == 0:
             cases.append((traj[L][0], key, L, traj[L][2]))  # terminal root
+    # non-standard roots (tests/golden/weird.npz): stuck positions, ragged piles, nearly empty
+    # bags -> trees with dead-end leaves, bag-empty endings and multi-pile replenishes
+    wpath = os.path.join(OUT, "weird.npz")
+    if os.path.exists(wpath):
+        ws = np.load(wpath)["states"]
+        for i in range(0, len(ws), len(ws) // 14):
+            f = pk.unpack_fields(ws[i])
+            key, ev, mv = f.pop("rng_key"), f.pop("rng_event"), f.pop("moves")
+            cases.append((ref["G"](initial_state=f), key, mv, ev))
     out = {k: [] for k in "root skey sims cpuct testing eps noise choice_u move_no tau0 N W P pi action n_nodes n_edges".split()}
     t0 = time.time()
     for i, (state, key, m, ev) in enumerate(cases):
