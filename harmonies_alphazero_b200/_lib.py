@@ -24,6 +24,7 @@ SIGNATURES = {
     "hz_canon_hash": (_i, [_vp, _i64, _i, _vp, _vp]),
     "hz_outcome": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "hz_random_actions": (_i, [_vp, _i64, _vp, _vp]),
+    "hz_greedy_actions": (_i, [_vp, _i64, _vp, _vp]),
     "hz_playout": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
     "hz_tree_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
     "hz_tree_create": (_i, [C.POINTER(_vp), _vp, C.c_size_t, _i, _i, _i, _i]),

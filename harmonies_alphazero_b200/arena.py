@@ -25,9 +25,13 @@ def _search(tree, net, states, sims, cpuct, bufs):
         tree.expand_backup(logits, value, is_logits=True)
 
 
+GREEDY = "greedy"   # pass as either side to play the 1-ply greedy agent of evaluation.py instead of a network
+
+
 def play_match(candidate_net, best_net, num_games, mcts_config_eval, device="cuda", seed=0, key_mode=hb.KEY_REFERENCE):
-    """Returns dict(candidate_wins, best_wins, draws, win_rate, games).  Both nets are
-    InferenceNet instances on ``device``."""
+    """Returns dict(candidate_wins, best_wins, draws, win_rate, games).  Each side is an
+    InferenceNet on ``device`` or ``arena.GREEDY`` (run_tournament of evaluation.py:7-65:
+    AlphaZero vs the greedy agent, sides alternating by game index)."""
     dev = torch.device(device)
     sims, cpuct = int(mcts_config_eval["num_simulations"]), float(mcts_config_eval["cpuct"])
     # group 0: candidate is player 0 (even game indices); group 1: candidate is player 1
@@ -38,8 +42,11 @@ def play_match(candidate_net, best_net, num_games, mcts_config_eval, device="cud
             continue
         states = hb.init_states(n, device=dev, seed=seed, first_id=0 if g == 0 else num_games)   # distinct games per group
         tree = BatchedMCTS(n, sims, device=dev, key_mode=key_mode)
-        dt = candidate_net.dtype
-        C = 40 if hasattr(candidate_net, "stem40") else 38
+        anynet = candidate_net if candidate_net is not GREEDY else best_net
+        if anynet is GREEDY:
+            anynet = None
+        dt = anynet.dtype if anynet is not None else torch.float32
+        C = 40 if anynet is not None and hasattr(anynet, "stem40") else 38
         bufs = (
             torch.empty((n, C, 5, 7), dtype=dt, device=dev, memory_format=torch.channels_last).zero_(),
             torch.zeros((n, 42), dtype=dt, device=dev),
@@ -54,8 +61,11 @@ def play_match(candidate_net, best_net, num_games, mcts_config_eval, device="cud
             # all live games of a group are in lockstep: same player to move
             mover = int(((states[live][:, 22] >> 24) & 1)[0].item())
             net = candidate_net if mover == g else best_net
-            _search(tree, net, states, sims, cpuct, bufs)
-            actions = tree.choose()                                  # greedy: testing=True
+            if net is GREEDY:                                        # evaluation.py:137-196, one kernel
+                actions = hb.greedy_actions(states)
+            else:
+                _search(tree, net, states, sims, cpuct, bufs)
+                actions = tree.choose()                              # first max N: testing=True
             actions = torch.where(live, actions, torch.full_like(actions, -1))
             hb.apply(states, actions)
         tree.check_status()

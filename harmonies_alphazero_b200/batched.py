@@ -148,6 +148,16 @@ def random_actions(states, out=None):
     return out
 
 
+def greedy_actions(states, out=None):
+    """int16[n]: the 1-ply greedy agent's action (choose_move_greedy, evaluation.py:137-196)."""
+    lib = _lib.load()
+    n = _check_states(states)
+    out = torch.empty(n, dtype=torch.int16, device=states.device) if out is None else out
+    with torch.cuda.device(states.device):
+        _lib.check(lib.hz_greedy_actions(_ptr(states), n, _ptr(out), _stream(states)), "hz_greedy_actions")
+    return out
+
+
 def playout(states, max_steps=1000, steps=None, total=None):
     """Fused random playout in place.  Returns (steps int32[n], total int64[1]) tensors."""
     lib = _lib.load()

@@ -104,6 +104,60 @@ __global__ void __launch_bounds__(TPB) k_random_actions(const void* states, int6
     actions[g] = (int16_t)random_action(s, legal_of(s));
 }
 
+// choose_move_greedy (evaluation.py:137-196): one warp per game, one lane per legal move; a lane
+// places its tile on a copy of the mover's board, scores it (K2+K3 fused) and the warp keeps the
+// first strict maximum in ascending action order.  Taking a pile never changes the mover's
+// score, so in the choose phase the first pile wins, as in the reference's loop.
+constexpr int GWPB = 4;
+__global__ void __launch_bounds__(GWPB * 32) k_greedy(const void* states, int64_t n, int16_t* actions) {
+    __shared__ NbrLut lut;
+    __shared__ uint32_t sw[GWPB][32];
+    build_nbr_lut(&lut);
+    __syncthreads();
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t g = (int64_t)blockIdx.x * GWPB + warp;
+    if (g >= n) return;
+    sw[warp][lane] = reinterpret_cast<const uint32_t*>(states)[g * 32 + lane];
+    __syncwarp();
+    State s;
+#pragma unroll
+    for (int i = 0; i < SW; i++) s.w[i] = sw[warp][i];
+    Legal L = legal_of(s);
+    int nl = legal_count(L), best_k = -1, best_score = -1000000;
+    if (L.n_piles > 0) {
+        best_k = 0;
+    } else {
+        Board b0 = board_of(s, player_of(s));
+        Tops t = tops_of(b0);
+        for (int base = 0; base < nl; base += 32) {
+            int k = base + lane;
+            if (k < nl) {
+                int a = kth_action(L, k);
+                int tile = (a - 5) / 23, hex = (a - 5) - 23 * tile;
+                uint32_t bit = 1u << hex, code = (uint32_t)tile + 1u;
+                uint32_t at0 = bit & ~t.occ0, at1 = bit & t.occ0 & ~t.occ1, at2 = bit & t.occ1;
+                Board b = b0;
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    uint32_t on = (code >> q) & 1u ? 0xFFFFFFFFu : 0u;
+                    b.p[q] |= at0 & on; b.p[3 + q] |= at1 & on; b.p[6 + q] |= at2 & on;
+                }
+                int tm[5];
+                score_board(&lut, b, tm);
+                int sc = tm[0] + tm[1] + tm[2] + tm[3] + tm[4];
+                if (sc > best_score) { best_score = sc; best_k = k; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            int os = __shfl_xor_sync(0xFFFFFFFFu, best_score, o), ok = __shfl_xor_sync(0xFFFFFFFFu, best_k, o);
+            bool take = ok >= 0 && (best_k < 0 || os > best_score || (os == best_score && ok < best_k));
+            if (take) { best_score = os; best_k = ok; }
+        }
+    }
+    if (lane == 0) actions[g] = (int16_t)(best_k < 0 ? -1 : kth_action(L, best_k));
+}
+
 // Fused playout (K9): the whole game stays in registers; HBM sees one load and one store of
 // the state per game.  Threads of a warp run different games and diverge only on the phase
 // (choose / place / end of turn); scoring runs once per game.
@@ -522,6 +576,13 @@ int hz_random_actions(const void* states, int64_t n, int16_t* actions, void* str
     if (!states || !actions || n < 0) return HZ_ERR_ARG;
     if (n == 0) return HZ_OK;
     k_random_actions<<<blocks_for(n, TPB), TPB, 0, (cudaStream_t)stream>>>(states, n, actions);
+    return hz_launched(1);
+}
+
+int hz_greedy_actions(const void* states, int64_t n, int16_t* actions, void* stream) {
+    if (n == 0) return HZ_OK;
+    if (!states || !actions || n < 0) return HZ_ERR_ARG;
+    k_greedy<<<blocks_for(n, GWPB), GWPB * 32, 0, (cudaStream_t)stream>>>(states, n, actions);
     return hz_launched(1);
 }
 

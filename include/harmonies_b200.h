@@ -191,6 +191,11 @@ int hz_outcome(const void *states, int64_t n, uint8_t *over, int8_t *outcome, vo
  * k = ((rand(key ^ HZ_PLAYOUT_SALT, moves) >> 32) * n_legal) >> 32.  -1 if none. */
 int hz_random_actions(const void *states, int64_t n, int16_t *actions, void *stream);
 
+/* The 1-ply greedy agent of evaluation.py:137-196 (choose_move_greedy): the legal action whose
+ * successor has the highest score for the mover, first strict maximum in ascending action
+ * order; -1 if there is no legal action. */
+int hz_greedy_actions(const void *states, int64_t n, int16_t *actions, void *stream);
+
 /* Fused playout: repeat {legal -> random action -> apply} on-chip until the game is over
  * or max_steps actions were applied.  steps (nullable): actions applied per game.
  * total_steps (nullable): device uint64 to which the launch adds its step total. */

@@ -440,8 +440,39 @@ def gen_weird(n=1500, per_state=8):
     print(f"weird: {len(states)} (state, action) pairs, status histogram {np.bincount(st, minlength=7).tolist()}")
 
 
+def gen_greedy(n_trace=700, n_weird=300):
+    """choose_move_greedy (evaluation.py:137-196) on trace states and non-standard states."""
+    import contextlib
+    import io
+
+    ref = rh.load_reference()
+    sys.path.insert(0, rh.REF_ROOT)
+    try:
+        import evaluation as ev
+    finally:
+        sys.path.remove(rh.REF_ROOT)
+    G, gai = ref["G"], ref["pgs"].get_action_index
+    rng = np.random.default_rng(11)
+    tr = np.load(os.path.join(OUT, "engine.npz"))["before"]
+    wd = np.load(os.path.join(OUT, "weird.npz"))["states"]
+    sel = np.concatenate([tr[rng.choice(len(tr), n_trace, replace=False)], wd[rng.choice(len(wd), n_weird, replace=False)]])
+    acts = []
+    rh.ctx.mode = "python"
+    for w in sel:
+        f = pk.unpack_fields(w)
+        for k in ("rng_key", "rng_event", "moves"):
+            f.pop(k)
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = ev.choose_move_greedy(G(initial_state=f))
+        acts.append(-1 if r is None else gai(r[0]))
+    np.savez_compressed(os.path.join(OUT, "greedy.npz"), states=sel.astype(np.uint32), action=np.array(acts, dtype=np.int16))
+    print(f"greedy: {len(sel)} states, {sum(a < 0 for a in acts)} without a legal move")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "greedy" in (sys.argv[1:] or ["greedy"]):
+        gen_greedy()
     which = sys.argv[1:] or ["engine", "scoring", "encode", "equiv", "mcts", "weird"]
     if "weird" in which:
         gen_weird()

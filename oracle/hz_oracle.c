@@ -524,6 +524,23 @@ void hzo_random_actions(const uint32_t *states, int64_t n, int16_t *actions) {
     }
 }
 
+/* choose_move_greedy (evaluation.py:137-196): the legal move whose successor state has the
+ * highest score for the mover; first strict maximum in legal (ascending action) order. */
+void hzo_greedy_actions(const uint32_t *states, int64_t n, int16_t *actions) {
+    geometry();
+    for (int64_t g = 0; g < n; g++) {
+        ostate s; unpack(states + g * 32, &s);
+        int acts[HZ_ACTION_SIZE], k = legal_actions(&s, acts), best = -1, best_score = -1000000;
+        for (int i = 0; i < k; i++) {
+            ostate c = s;
+            if (apply_action(&c, acts[i], HZ_NO_DRAW) != HZ_MOVE_OK) continue;    /* evaluation.py:172-178 */
+            int sc = score_player(&c, s.player);                                  /* :162 */
+            if (sc > best_score) { best_score = sc; best = acts[i]; }             /* :167-169 */
+        }
+        actions[g] = (int16_t)best;
+    }
+}
+
 typedef struct { uint32_t *states; int64_t lo, hi; int max_steps; uint32_t *steps; uint64_t total; } playout_job;
 
 static void *playout_worker(void *arg) {

@@ -109,6 +109,13 @@ def random_actions(states):
     return out
 
 
+def greedy_actions(states):
+    s = _states(states)
+    out = np.zeros(len(s), dtype=np.int16)
+    lib().hzo_greedy_actions(_p(s), C.c_int64(len(s)), _p(out))
+    return out
+
+
 def playout(states, max_steps=1000, n_threads=1):
     """Returns (final_states, steps_per_game, total_steps)."""
     s = _states(states).copy()

@@ -122,6 +122,29 @@ def test_golden_weird_states(hb):
     assert stuck_ok.all()
 
 
+def test_greedy_agent(hb, oracle):
+    """hz_greedy_actions = choose_move_greedy (evaluation.py:137-196): reference goldens, then
+    20,000 mid-game positions against the oracle, then whole greedy-vs-greedy games"""
+    g = load_golden("greedy")
+    assert np.array_equal(hb.greedy_actions(dev(g["states"])).cpu().numpy(), g["action"])
+    st = hb.init_states(20000, seed=8)
+    for lo, hi, d in [(0, 5000, 3), (5000, 10000, 18), (10000, 15000, 37), (15000, 20000, 55)]:
+        sl = st[lo:hi].clone()
+        hb.playout(sl, max_steps=d)
+        st[lo:hi] = sl
+    assert np.array_equal(hb.greedy_actions(st).cpu().numpy(), oracle.greedy_actions(host(st)))
+    games = hb.init_states(512, seed=9)
+    for _ in range(200):
+        a = hb.greedy_actions(games)
+        if bool((a < 0).all()):
+            break
+        hb.apply(games, torch.where(a >= 0, a, torch.zeros_like(a)))
+    over, _ = hb.outcome(games)
+    assert over.all()
+    sc = hb.score(games).cpu().numpy()
+    assert sc.mean() > 25          # greedy play scores far above random play (mean ~17)
+
+
 def test_golden_equivalence_classes(hb):
     g = load_golden("equiv")
     st = dev(g["states"])

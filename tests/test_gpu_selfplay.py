@@ -218,6 +218,12 @@ def test_arena_match(mods):
     # swapping the roles mirrors the tally
     r2 = arena.play_match(best, cand, 9, cfg, seed=5)
     assert r2["games"] == 9 and r2["candidate_wins"] + r2["best_wins"] + r2["draws"] == 9
+    # run_tournament (evaluation.py:7-65): network vs the 1-ply greedy agent; an untrained net
+    # with 6 simulations loses to greedy play; greedy vs greedy is a legal, complete match
+    r3 = arena.play_match(cand, arena.GREEDY, 10, cfg, seed=7)
+    assert r3["candidate_wins"] + r3["best_wins"] + r3["draws"] == 10 and r3["best_wins"] >= 8
+    r4 = arena.play_match(arena.GREEDY, arena.GREEDY, 6, cfg, seed=7)
+    assert r4["candidate_wins"] + r4["best_wins"] + r4["draws"] == 6
 
 
 def test_selfplay_is_independent_of_slot_count_in_testing_mode(mods):

@@ -135,6 +135,12 @@ def test_weird_states(oracle):
     assert np.array_equal(new[:, :28], g["after"][:, :28])
 
 
+def test_greedy_agent(oracle):
+    """choose_move_greedy (evaluation.py:137-196)"""
+    g = load_golden("greedy")
+    assert np.array_equal(oracle.greedy_actions(g["states"]), g["action"])
+
+
 def test_mcts_golden(oracle):
     """MCTS.py:63-441 — visit counts, W, priors, node/edge counts and the chosen move of
     the reference searches (synthetic evaluator, injected noise/uniform)."""
