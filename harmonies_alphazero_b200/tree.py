@@ -24,7 +24,7 @@ class BatchedMCTS:
         if nbytes == 0:
             raise ValueError("bad tree dimensions")
         # caller-owned workspace (a torch allocation is >=512 B aligned)
-        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)   # zeroed: counters/status are defined before the first reset
         h = C.c_void_p()
         _lib.check(
             self.lib.hz_tree_create(C.byref(h), self.workspace.data_ptr(), nbytes, self.n, self.max_sims, max_nodes, key_mode),
