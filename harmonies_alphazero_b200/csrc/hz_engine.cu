@@ -4,8 +4,9 @@
 //
 // Mapping: one thread per game, state held in registers (7 x LDG.128 in, 8 x STG.128 out),
 // hex-parallel work done as 23-bit bit-board arithmetic; the neighbour expansion LUT lives in
-// 3 KB of shared memory per block.  hz_encode uses a block-cooperative layout instead
-// (write-bound: 5.5 KB out per 128 B in).
+// 3 KB of shared memory per block.  hz_encode is write-bound (5.5 KB out per 128 B in): a warp
+// renders a group of records as a bit stream and stores 16-byte vectors through a lookup table
+// (k_encode_w); hz_greedy_actions is warp-per-game with one lane per legal move.
 #include "hz_common.cuh"
 #include "hz_core.cuh"
 

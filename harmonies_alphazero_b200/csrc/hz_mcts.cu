@@ -8,8 +8,9 @@
 //   edges : SoA child / N / W(fp64) / P(fp32) / (action | mover<<8); a node's edges are
 //           contiguous and in ascending action order, so a warp reads them coalesced and
 //           "first strict maximum" (MCTS.py:102,118) is a lowest-lane tie-break
-//   table : open-addressing hash set (node index + 1) keyed by the canonical hash, full-key
-//           compare on hit: the transposition DAG of MCTS.py:184-186
+//   table : open-addressing hash set (node index + 1) keyed by the 64-bit canonical key;
+//           identity = key equality, as the reference's dict of hash(state) ids
+//           (MCTS.py:184-186; -DHZ_TREE_FULL_COMPARE=1 adds a 23-word compare on hits)
 // Parity mode is one in-flight simulation per tree (the reference is strictly sequential,
 // MCTS.py:291-352); parallelism comes from thousands of concurrent trees.
 #include <math.h>
