@@ -320,6 +320,17 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # harness convenience: (re)build a missing/stale library once per node; the ops themselves never do
+    from harmonies_alphazero_b200 import build as hz_build
+
+    if hz_build.needs_build():
+        if local == 0:
+            hz_build.build()
+        else:
+            for _ in range(240):
+                if not hz_build.needs_build():
+                    break
+                time.sleep(0.5)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)

@@ -30,6 +30,20 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _cuda_library_is_current():
+    """(Re)build libharmonies_b200.so when it is missing or older than its sources (nvcc is in
+    the image on both the dev container and the GPU box).  The product never builds or falls
+    back on its own: without the library it raises."""
+    try:
+        from harmonies_alphazero_b200 import build
+
+        build.build()
+    except Exception as e:  # noqa: BLE001
+        print(f"[conftest] could not build the CUDA library: {e}")
+    yield
+
+
 def load_golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 
