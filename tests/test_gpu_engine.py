@@ -245,6 +245,16 @@ def test_host_buffer_api_equals_device_path(hb):
     assert torch.equal(api.steps.cpu(), steps.cpu())
     with pytest.raises(ValueError):
         api.run(st.cpu(), pin_out)          # not pinned
+    # key-based call: fresh games from host keys, compact results back
+    rng = np.random.default_rng(2)
+    keys = rng.integers(-2**63, 2**63 - 1, size=n, dtype=np.int64)
+    pin_keys = torch.from_numpy(keys).pin_memory()
+    pin_res = torch.empty((n, 3), dtype=torch.int32).pin_memory()
+    res = api.run_keys(pin_keys, pin_res).numpy().view(np.uint32)
+    ref = hb.init_states(n, keys=keys.view(np.uint64))
+    hb.playout(ref)
+    w = host(ref)
+    assert np.array_equal(res[:, 0], w[:, 22]) and np.array_equal(res[:, 1], w[:, 23]) and np.array_equal(res[:, 2], w[:, 27])
 
 
 def test_score_encode_hash_vs_oracle_on_random_positions(hb, oracle):
