@@ -81,7 +81,7 @@ class ClockSampler:
                 self.samples.append((time.perf_counter(), sm, [k for k, bit in R.items() if rs & bit]))
             except Exception:
                 break
-            time.sleep(0.001)
+            time.sleep(0.0002)
 
     def start(self):
         if self.nvml:
@@ -306,7 +306,35 @@ def cpu_mcts_baseline(budget_s=10.0):
     t0 = time.perf_counter()
     orc.search_batch(roots, keys, 100, 2.0, n_threads=threads)
     dt = time.perf_counter() - t0
-    return {"value": n * 100 / dt, "unit": "sims/s", "cores": threads, "kind": "port",
+    tree_rate = n * 100 / dt
+    # the reference evaluates its network on the CPU at batch 1 once per simulation
+    # (MCTS.py:302, trainer.py:104-107: one model per worker process, one thread each): time
+    # that forward here and combine it with the tree-only rate into a whole-simulation estimate
+    import torch
+
+    from harmonies_alphazero_b200 import net as hznet
+
+    old_threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        torch.manual_seed(0)
+        m = hznet.AlphaZeroNet.from_config(hznet.DEFAULT_MODEL_CONFIG).eval()
+        b, g = torch.zeros(1, 38, 5, 7), torch.zeros(1, 42)
+        with torch.no_grad():
+            for _ in range(3):
+                m(b, g)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                m(b, g)
+            net_s = (time.perf_counter() - t0) / 20
+    finally:
+        torch.set_num_threads(old_threads)
+    per_core_tree_s = threads / tree_rate
+    with_net = threads / (per_core_tree_s + net_s)
+    return {"value": tree_rate, "unit": "sims/s", "cores": threads, "kind": "port",
+            "with_network_estimate": {"value": with_net, "unit": "sims/s", "net_forward_ms_batch1_1thread": net_s * 1e3,
+                                      "how": "cores / (tree seconds per sim per core + fp32 forward at batch 1 on one thread), "
+                                             "the reference's worker layout"},
             "sample": f"{n} searches x 100 sims, synthetic evaluator (no network), oracle/hz_oracle.c on {threads} pthreads; "
                       "the Python reference with its net on CPU does ~75 sims/s/core (BASELINE.md §2)"}
 

@@ -37,12 +37,12 @@ __global__ void __launch_bounds__(TPB) k_legal(const void* states, int64_t n, ui
 __global__ void __launch_bounds__(TPB) k_apply(void* states, int64_t n, const int16_t* actions,
                                                const uint16_t* draws, uint8_t* status) {
     __shared__ NbrLut lut;
+    int64_t g = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    State s;
+    if (g < n) load_state(s, states, g);      // issue the record loads first: the LUT copy overlaps them
     build_nbr_lut(&lut);
     __syncthreads();
-    int64_t g = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (g >= n) return;
-    State s;
-    load_state(s, states, g);
     uint32_t ex = draws ? (uint32_t)draws[g] : (uint32_t)HZ_NO_DRAW;
     int st = apply_move(s, (int)actions[g], ex, key_of(s), s.w[HZ_W_EVENT], true, &lut);
     if (st == HZ_MOVE_OK) store_state(s, states, g);
@@ -52,18 +52,21 @@ __global__ void __launch_bounds__(TPB) k_apply(void* states, int64_t n, const in
 __global__ void __launch_bounds__(TPB) k_score(const void* states, int64_t n, int16_t* scores,
                                                int16_t* terms) {
     __shared__ NbrLut lut;
+    int64_t g = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    // only the 18 board words are needed: 92 -> 80 B of traffic per position; the loads are
+    // issued before the LUT copy so that the two overlap
+    uint32_t w[20];
+    if (g < n) {
+        const uint4* p = reinterpret_cast<const uint4*>(states) + g * 8;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            uint4 v = p[k];
+            w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+        }
+    }
     build_nbr_lut(&lut);
     __syncthreads();
-    int64_t g = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (g >= n) return;
-    // only the 18 board words are needed: 92 -> 72 B of traffic per position
-    const uint4* p = reinterpret_cast<const uint4*>(states) + g * 8;
-    uint32_t w[20];
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        uint4 v = p[k];
-        w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
-    }
 #pragma unroll
     for (int pl = 0; pl < 2; pl++) {
         Board b;
