@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--mcts-games", type=int, default=4096, help="concurrent games (trees) per GPU")
     ap.add_argument("--mcts-sims", type=int, default=100)
     ap.add_argument("--mcts-streams", type=int, default=1, help="slot groups on separate CUDA streams")
+    ap.add_argument("--mcts-leaves", type=int, default=1, help="simulations in flight per tree and step (1 = reference-exact; >1 = virtual loss)")
     ap.add_argument("--mcts-steps", type=int, default=5, help="timed moves (each = games x sims simulations)")
     return ap.parse_args()
 
@@ -209,7 +210,7 @@ def mcts_measure(args, dev, world, rank, dist):
     inf = hznet.InferenceNet(model, device=dev, dtype=torch.bfloat16)
     B, S = args.mcts_games, args.mcts_sims
     cfg = sp.SelfPlayConfig(n_slots=B, num_simulations=S, cpuct=2.0, dirichlet_alpha=0.4, dirichlet_epsilon=0.25,
-                            turns_until_tau0=15, seed=77, first_game_id=rank * B, n_streams=args.mcts_streams)
+                            turns_until_tau0=15, seed=77, first_game_id=rank * B, n_streams=args.mcts_streams, leaves_per_step=args.mcts_leaves)
     drv = sp.BatchedSelfPlay(inf, cfg, device=dev)
     states = hb.init_states(B, device=dev, seed=77, first_id=rank * B)
     hb.playout(states, max_steps=8)                 # a few moves in: realistic branching
@@ -278,7 +279,7 @@ def mcts_measure(args, dev, world, rank, dist):
     return {"metric": "mcts_sims_per_sec", "value": v, "unit": "sims/s", "ms_per_move": ms / K,
             "config": {"workload": "MCTS self-play, model.py net 128f x 8 blocks random-init, bf16, "
                                    f"{S} sims/move, {B} concurrent games per GPU (configs[3])",
-                       "fused_conv": inf.fused, "fused_heads": inf.heads is not None, "cuda_graph": drv.graph is not None, "streams": drv.n_groups},
+                       "fused_conv": inf.fused, "fused_heads": inf.heads is not None, "cuda_graph": drv.graph is not None, "streams": drv.n_groups, "leaves_per_step": args.mcts_leaves},
             "dtype": "bf16", "collectives": collectives, "clocks": mcts_clocks,
             # direct C-ABI launches + the two tree kernels replayed inside the CUDA graph per simulation
             "gpu_launches_own": (direct_launches + ((2 + (inf.heads is not None)) * drv.n_groups * S * K if drv.graph is not None else 0)) * world,

@@ -19,7 +19,7 @@ def _search(tree, net, states, sims, cpuct, bufs):
     board, glob, logits, value = bufs
     tree.reset(states)
     pad40 = board.shape[1] == 40
-    for _ in range(sims):
+    for _ in range(sims // tree.leaves):
         tree.select(cpuct, board, glob, dtype=net.dtype, channels_last=True, pad40=pad40)
         net(board, glob, out=(logits, value))
         tree.expand_backup(logits, value, is_logits=True)
@@ -28,10 +28,12 @@ def _search(tree, net, states, sims, cpuct, bufs):
 GREEDY = "greedy"   # pass as either side to play the 1-ply greedy agent of evaluation.py instead of a network
 
 
-def play_match(candidate_net, best_net, num_games, mcts_config_eval, device="cuda", seed=0, key_mode=hb.KEY_REFERENCE):
+def play_match(candidate_net, best_net, num_games, mcts_config_eval, device="cuda", seed=0, key_mode=hb.KEY_REFERENCE, leaves=1):
     """Returns dict(candidate_wins, best_wins, draws, win_rate, games).  Each side is an
     InferenceNet on ``device`` or ``arena.GREEDY`` (run_tournament of evaluation.py:7-65:
-    AlphaZero vs the greedy agent, sides alternating by game index)."""
+    AlphaZero vs the greedy agent, sides alternating by game index).  leaves > 1 switches the
+    searches to the virtual-loss mode (K simulations in flight per tree): not the reference's
+    visit counts any more, but a 30-game match then fills the network batch K times better."""
     dev = torch.device(device)
     sims, cpuct = int(mcts_config_eval["num_simulations"]), float(mcts_config_eval["cpuct"])
     # group 0: candidate is player 0 (even game indices); group 1: candidate is player 1
@@ -41,17 +43,20 @@ def play_match(candidate_net, best_net, num_games, mcts_config_eval, device="cud
         if n == 0:
             continue
         states = hb.init_states(n, device=dev, seed=seed, first_id=0 if g == 0 else num_games)   # distinct games per group
-        tree = BatchedMCTS(n, sims, device=dev, key_mode=key_mode)
+        if sims % leaves:
+            raise ValueError("num_simulations must be a multiple of leaves")
+        tree = BatchedMCTS(n, sims, device=dev, key_mode=key_mode, leaves=leaves)
+        rows = n * leaves
         anynet = candidate_net if candidate_net is not GREEDY else best_net
         if anynet is GREEDY:
             anynet = None
         dt = anynet.dtype if anynet is not None else torch.float32
         C = 40 if anynet is not None and hasattr(anynet, "stem40") else 38
         bufs = (
-            torch.empty((n, C, 5, 7), dtype=dt, device=dev, memory_format=torch.channels_last).zero_(),
-            torch.zeros((n, 42), dtype=dt, device=dev),
-            torch.zeros((n, 143), dtype=torch.float32, device=dev),
-            torch.zeros(n, dtype=torch.float32, device=dev),
+            torch.empty((rows, C, 5, 7), dtype=dt, device=dev, memory_format=torch.channels_last).zero_(),
+            torch.zeros((rows, 42), dtype=dt, device=dev),
+            torch.zeros((rows, 143), dtype=torch.float32, device=dev),
+            torch.zeros(rows, dtype=torch.float32, device=dev),
         )
         for _ in range(200):
             over, oc = hb.outcome(states)

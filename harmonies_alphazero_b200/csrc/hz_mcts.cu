@@ -20,6 +20,7 @@
 
 struct hz_tree {
     int n_trees, max_sims, max_nodes, max_edges, table_size, key_mode;
+    int leaves;             // K simulations in flight per tree and step (1 = the reference's sequential search)
     uint4* node_state;      // [n_trees * max_nodes * 8]
     uint64_t* node_hash;    // [n_trees * max_nodes]
     uint32_t* node_edge0;   // [n_trees * max_nodes]
@@ -29,10 +30,11 @@ struct hz_tree {
     double* edge_W;
     float* edge_P;
     uint16_t* edge_am;      // action | mover << 8
+    int32_t* edge_V;        // in-flight (virtual-loss) visits, non-zero only between select and backup
     uint32_t* table;        // [n_trees * table_size]
-    uint32_t* path;         // [n_trees * (max_sims + 1)]
-    int32_t* depth;         // [n_trees]
-    int32_t* leaf;
+    uint32_t* path;         // [n_trees * leaves * (max_sims + 1)]
+    int32_t* depth;         // [n_trees * leaves]
+    int32_t* leaf;          // [n_trees * leaves]
     int32_t* sim;
     int32_t* n_nodes;
     int32_t* n_edges;
@@ -49,8 +51,8 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 
 struct TreeView {                 // device copy of the handle with per-tree offsets applied
     uint4* node_state; uint64_t* node_hash; uint32_t* node_edge0; uint32_t* node_info;
-    uint32_t* edge_child; int32_t* edge_N; double* edge_W; float* edge_P; uint16_t* edge_am;
-    uint32_t* table; uint32_t* path;
+    uint32_t* edge_child; int32_t* edge_N; double* edge_W; float* edge_P; uint16_t* edge_am; int32_t* edge_V;
+    uint32_t* table; uint32_t* path;   // path: [leaves][max_sims + 1]
 };
 __device__ __forceinline__ TreeView view_of(const hz_tree& T, int t) {
     TreeView v;
@@ -58,9 +60,9 @@ __device__ __forceinline__ TreeView view_of(const hz_tree& T, int t) {
     v.node_state = T.node_state + nb * 8; v.node_hash = T.node_hash + nb;
     v.node_edge0 = T.node_edge0 + nb; v.node_info = T.node_info + nb;
     v.edge_child = T.edge_child + eb; v.edge_N = T.edge_N + eb; v.edge_W = T.edge_W + eb;
-    v.edge_P = T.edge_P + eb; v.edge_am = T.edge_am + eb;
+    v.edge_P = T.edge_P + eb; v.edge_am = T.edge_am + eb; v.edge_V = T.edge_V + eb;
     v.table = T.table + (size_t)t * T.table_size;
-    v.path = T.path + (size_t)t * (T.max_sims + 1);
+    v.path = T.path + (size_t)t * T.leaves * (T.max_sims + 1);
     return v;
 }
 
@@ -87,7 +89,8 @@ __global__ void __launch_bounds__(TTPB) k_tree_reset(hz_tree T, const uint4* roo
     v.node_edge0[0] = 0;
     v.node_info[0] = (uint32_t)player_of(s) << 8;
     v.table[h & (uint64_t)(T.table_size - 1)] = 1;
-    T.depth[t] = 0; T.leaf[t] = 0; T.sim[t] = 0; T.n_nodes[t] = 1; T.n_edges[t] = 0; T.status[t] = 0;
+    for (int j = 0; j < T.leaves; j++) { T.depth[t * T.leaves + j] = 0; T.leaf[t * T.leaves + j] = 0; }
+    T.sim[t] = 0; T.n_nodes[t] = 1; T.n_edges[t] = 0; T.status[t] = 0;
     // default key: a stream of its own per (game, move), independent of the game's draw stream
     T.search_key[t] = keys ? keys[t] : rand64(key_of(s) ^ HZ_SEARCH_SALT, (uint64_t)s.w[HZ_W_MOVES]);
 }
@@ -174,62 +177,79 @@ __global__ void __launch_bounds__(TTPB) k_tree_select(hz_tree T, float cpuct, ui
     int t = blockIdx.x * WPB + warp;
     if (t >= T.n_trees) return;
     TreeView v = view_of(T, t);
-    int node = 0, depth = 0;
-    while (true) {
-        uint32_t info = v.node_info[node];
-        int ne = (int)(info & 0xFFu);
-        if (ne == 0) break;                                          // is_leaf, MCTS.py:18-20,76
-        uint32_t e0 = v.node_edge0[node];
-        int N[3]; double W[3]; float P[3];
-        int ns = 0;
+    const int K = T.leaves;
+    // K descents per tree and step.  K == 1 is the reference's move_to_leaf.  For K > 1 every
+    // edge of an already chosen path carries an in-flight visit V: N' = N + V, W' = W - V
+    // (a provisional loss for the mover), so the later descents of the step spread out.
+    for (int j = 0; j < K; j++) {
+        uint32_t* path = v.path + (size_t)j * (T.max_sims + 1);
+        int node = 0, depth = 0;
+        while (true) {
+            uint32_t info = v.node_info[node];
+            int ne = (int)(info & 0xFFu);
+            if (ne == 0) break;                                          // is_leaf, MCTS.py:18-20,76
+            uint32_t e0 = v.node_edge0[node];
+            int N[3]; double W[3]; float P[3];
+            int ns = 0;
 #pragma unroll
-        for (int r = 0; r < 3; r++) {
-            int k = lane + 32 * r;
-            bool on = k < ne;
-            N[r] = on ? v.edge_N[e0 + k] : 0;
-            W[r] = on ? v.edge_W[e0 + k] : 0.0;
-            P[r] = on ? v.edge_P[e0 + k] : 0.0f;
-            ns += N[r];
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(FULL, ns, o);               // :95-97
-        double sqrt_ns = sqrt(ns > 1 ? (double)ns : 1.0);                                  // :99
-        double best = -INFINITY;
-        int best_k = -1;
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            int k = lane + 32 * r;
-            if (k < ne) {
-                float cp = cpuct * P[r];                             // np.float32 product, :107-109
-                double u = (double)cp * sqrt_ns / (double)(1 + N[r]);                      // :110-111
-                double q = N[r] ? W[r] / (double)N[r] : 0.0;         // Q = W/N, :254
-                double sc = q + u;
-                if (sc > best) { best = sc; best_k = k; }            // strict >, ascending k: :118
+            for (int r = 0; r < 3; r++) {
+                int k = lane + 32 * r;
+                bool on = k < ne;
+                N[r] = on ? v.edge_N[e0 + k] : 0;
+                W[r] = on ? v.edge_W[e0 + k] : 0.0;
+                P[r] = on ? v.edge_P[e0 + k] : 0.0f;
+                if (K > 1 && on) {
+                    int vl = v.edge_V[e0 + k];
+                    N[r] += vl;
+                    W[r] -= (double)vl;
+                }
+                ns += N[r];
             }
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double ob = __shfl_xor_sync(FULL, best, o);
-            int ok = __shfl_xor_sync(FULL, best_k, o);
-            bool take = ok >= 0 && (best_k < 0 || ob > best || (ob == best && ok < best_k));
-            if (take) { best = ob; best_k = ok; }
+            for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(FULL, ns, o);               // :95-97
+            double sqrt_ns = sqrt(ns > 1 ? (double)ns : 1.0);                                  // :99
+            double best = -INFINITY;
+            int best_k = -1;
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                int k = lane + 32 * r;
+                if (k < ne) {
+                    float cp = cpuct * P[r];                             // np.float32 product, :107-109
+                    double u = (double)cp * sqrt_ns / (double)(1 + N[r]);                      // :110-111
+                    double q = N[r] ? W[r] / (double)N[r] : 0.0;         // Q = W/N, :254
+                    double sc = q + u;
+                    if (sc > best) { best = sc; best_k = k; }            // strict >, ascending k: :118
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                double ob = __shfl_xor_sync(FULL, best, o);
+                int ok = __shfl_xor_sync(FULL, best_k, o);
+                bool take = ok >= 0 && (best_k < 0 || ob > best || (ob == best && ok < best_k));
+                if (take) { best = ob; best_k = ok; }
+            }
+            if (best_k < 0) break;                                       // :125-133
+            uint32_t e = e0 + (uint32_t)best_k;
+            if (depth > T.max_sims) { if (lane == 0) T.status[t] |= 4; break; }
+            if (lane == 0) {
+                path[depth] = e;
+                if (K > 1) v.edge_V[e] += 1;
+            }
+            depth++;
+            node = (int)v.edge_child[e];                                 // :145-146
         }
-        if (best_k < 0) break;                                       // :125-133
-        uint32_t e = e0 + (uint32_t)best_k;
-        if (depth > T.max_sims) { if (lane == 0) T.status[t] |= 4; break; }
-        if (lane == 0) v.path[depth] = e;
-        depth++;
-        node = (int)v.edge_child[e];                                 // :145-146
-    }
-    if (lane == 0) { T.leaf[t] = node; T.depth[t] = depth; }
-    warp_load_words(sm_words[warp], v.node_state, node, lane);
-    if (leaf_states) reinterpret_cast<uint32_t*>(leaf_states + (size_t)t * 8)[lane] = sm_words[warp][lane];
-    if (board) {
-        if constexpr (FAST40)
-            warp_encode_fast40(sm_words[warp], sbytes[warp], vlut8, scell, (__nv_bfloat16*)board + (size_t)t * 1400,
-                               (__nv_bfloat16*)glob + (size_t)t * 42, lane);
-        else
-            warp_encode<OT, LAYOUT>(sm_words[warp], sm_mask[warp], board + (size_t)t * RowElems<LAYOUT>::value, glob + (size_t)t * 42, lane);
+        if (lane == 0) { T.leaf[t * K + j] = node; T.depth[t * K + j] = depth; }
+        size_t row = (size_t)t * K + j;
+        warp_load_words(sm_words[warp], v.node_state, node, lane);      // (__syncwarp inside: V updates are visible to the next descent)
+        if (leaf_states) reinterpret_cast<uint32_t*>(leaf_states + row * 8)[lane] = sm_words[warp][lane];
+        if (board) {
+            if constexpr (FAST40)
+                warp_encode_fast40(sm_words[warp], sbytes[warp], vlut8, scell, (__nv_bfloat16*)board + row * 1400,
+                                   (__nv_bfloat16*)glob + row * 42, lane);
+            else
+                warp_encode<OT, LAYOUT>(sm_words[warp], sm_mask[warp], board + row * RowElems<LAYOUT>::value, glob + row * 42, lane);
+        }
+        __syncwarp();
     }
 }
 
@@ -279,15 +299,21 @@ __global__ void __launch_bounds__(TTPB, 4) k_tree_expand_backup(hz_tree T, const
     int t = blockIdx.x * WPB + warp;
     if (t >= T.n_trees) return;
     TreeView v = view_of(T, t);
-    int leaf = T.leaf[t], sim = T.sim[t];
+    const int K = T.leaves, sim0 = T.sim[t];
+    // the K leaves of this step are processed in order j = 0..K-1 (K == 1: the reference)
+    for (int j = 0; j < K; j++) {
+    const size_t row = (size_t)t * K + j;
+    int leaf = T.leaf[row], sim = sim0 + j;
     warp_load_words(sm_words[warp], v.node_state, leaf, lane);
     State ls;
     state_from_words(ls, sm_words[warp]);
     int leaf_player = player_of(ls);
     double val;
     if (!is_over(ls)) {                                              // MCTS.py:297
-        val = (double)value[t];                                      // :302-304
-        const float* prow = policy + (size_t)t * HZ_ACTION_SIZE;
+        val = (double)value[row];                                    // :302-304
+        const float* prow = policy + row * HZ_ACTION_SIZE;
+        // K > 1: a leaf reached twice in one step is expanded by its first simulation only
+        bool expand = (v.node_info[leaf] & 0xFFu) == 0;
         float mx = 0.0f, inv_sum = 1.0f;
         if (is_logits) {                                             // fused softmax (model.py:104)
             float m = -INFINITY;
@@ -301,7 +327,7 @@ __global__ void __launch_bounds__(TTPB, 4) k_tree_expand_backup(hz_tree T, const
             mx = m; inv_sum = 1.0f / sum;
         }
         Legal L = legal_of(ls);
-        int n = legal_count(L);
+        int n = expand ? legal_count(L) : 0;
         double noise_sum = 0.0;
         bool mix = noise != nullptr && leaf == 0 && n > 0;           // root Dirichlet, :308-326
         const float* nrow = noise ? noise + (size_t)t * HZ_ACTION_SIZE : nullptr;
@@ -382,6 +408,7 @@ __global__ void __launch_bounds__(TTPB, 4) k_tree_expand_backup(hz_tree T, const
                 }
                 v.edge_child[e] = (uint32_t)id;
                 v.edge_N[e] = 0;
+                v.edge_V[e] = 0;
                 v.edge_W[e] = 0.0;
                 v.edge_P[e] = p;
                 v.edge_am[e] = (uint16_t)(a | (leaf_player << 8));
@@ -389,7 +416,7 @@ __global__ void __launch_bounds__(TTPB, 4) k_tree_expand_backup(hz_tree T, const
             n_new_edges += __popc(valid_mask);
             __syncwarp();
         }
-        if (lane == 0 && !overflow) {
+        if (lane == 0 && !overflow && expand) {
             v.node_edge0[leaf] = (uint32_t)e0;
             v.node_info[leaf] = (uint32_t)n_new_edges | ((uint32_t)leaf_player << 8);
             T.n_nodes[t] = n_nodes;
@@ -400,15 +427,19 @@ __global__ void __launch_bounds__(TTPB, 4) k_tree_expand_backup(hz_tree T, const
         val = oc == 0 ? 0.0 : (leaf_player == 0 ? (double)oc : -(double)oc);
     }
     // back_fill (MCTS.py:220-264): edges of one path are distinct, lanes update them in parallel
-    int depth = T.depth[t];
+    int depth = T.depth[row];
+    const uint32_t* path = v.path + (size_t)j * (T.max_sims + 1);
     for (int d = lane; d < depth; d += 32) {
-        uint32_t e = v.path[d];
+        uint32_t e = path[d];
         int mover = v.edge_am[e] >> 8;
         double dir = mover == leaf_player ? 1.0 : -1.0;              // :242-247
         v.edge_N[e] += 1;                                            // :252
         v.edge_W[e] += val * dir;                                    // :253
+        if (K > 1) v.edge_V[e] -= 1;                                 // the in-flight visit has landed
     }
-    if (lane == 0) T.sim[t] = sim + 1;
+    __syncwarp();                                                    // next leaf sees this one's nodes, edges and statistics
+    }
+    if (lane == 0) T.sim[t] = sim0 + K;
 }
 
 // ---- synthetic evaluator (stands in for ModelManager.predict in tests / tree-only benches) -----
@@ -418,13 +449,17 @@ __global__ void __launch_bounds__(TTPB) k_tree_fake_eval(hz_tree T, float* polic
     int t = blockIdx.x * WPB + warp;
     if (t >= T.n_trees) return;
     TreeView v = view_of(T, t);
-    warp_load_words(sm_words[warp], v.node_state, T.leaf[t], lane);
-    State s;
-    state_from_words(s, sm_words[warp]);
-    uint64_t h = canon_hash(s, HZ_KEY_EXACT);
-    for (int a = lane; a < HZ_ACTION_SIZE; a += 32)
-        policy[(size_t)t * HZ_ACTION_SIZE + a] = (float)(mix64(h ^ (uint64_t)(a + 1)) >> 40) * 0x1p-24f;
-    if (lane == 0) value[t] = (float)((double)(mix64(h ^ 0x5EEDull) >> 40) * 0x1p-23 - 1.0);
+    for (int j = 0; j < T.leaves; j++) {
+        size_t row = (size_t)t * T.leaves + j;
+        warp_load_words(sm_words[warp], v.node_state, T.leaf[row], lane);
+        State s;
+        state_from_words(s, sm_words[warp]);
+        uint64_t h = canon_hash(s, HZ_KEY_EXACT);
+        for (int a = lane; a < HZ_ACTION_SIZE; a += 32)
+            policy[row * HZ_ACTION_SIZE + a] = (float)(mix64(h ^ (uint64_t)(a + 1)) >> 40) * 0x1p-24f;
+        if (lane == 0) value[row] = (float)((double)(mix64(h ^ 0x5EEDull) >> 40) * 0x1p-23 - 1.0);
+        __syncwarp();
+    }
 }
 
 // ---- root statistics (MCTS.py:355-381) and move choice (MCTS.py:394-441) -------------------------
@@ -516,9 +551,9 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Layout {
     int max_nodes, max_edges, table_size;
-    size_t off[18], total;
+    size_t off[19], total;
 };
-static Layout layout_for(int n_trees, int max_sims, int max_nodes) {
+static Layout layout_for(int n_trees, int max_sims, int max_nodes, int leaves) {
     Layout L;
     L.max_nodes = max_nodes > 0 ? max_nodes : 1 + 69 * max_sims;
     L.max_edges = 69 * max_sims + 32;   // <= 69 edges per expansion, one expansion per simulation
@@ -526,10 +561,12 @@ static Layout layout_for(int n_trees, int max_sims, int max_nodes) {
     while (ts < 2 * L.max_nodes) ts <<= 1;
     L.table_size = ts;
     size_t nt = (size_t)n_trees, nn = nt * L.max_nodes, ne = nt * L.max_edges;
-    size_t sizes[18] = {nn * 128, nn * 8, nn * 4, nn * 4, ne * 4, ne * 4, ne * 8, ne * 4, ne * 2,
-                        nt * ts * 4, nt * (size_t)(max_sims + 1) * 4, nt * 4, nt * 4, nt * 4, nt * 4, nt * 4, nt, nt * 8};
+    size_t K = (size_t)leaves;
+    size_t sizes[19] = {nn * 128, nn * 8, nn * 4, nn * 4, ne * 4, ne * 4, ne * 8, ne * 4, ne * 2,
+                        nt * ts * 4, nt * K * (size_t)(max_sims + 1) * 4, nt * K * 4, nt * K * 4, nt * 4, nt * 4, nt * 4, nt, nt * 8,
+                        ne * 4};
     size_t o = 0;
-    for (int i = 0; i < 18; i++) { L.off[i] = o; o += align256(sizes[i]); }
+    for (int i = 0; i < 19; i++) { L.off[i] = o; o += align256(sizes[i]); }
     L.total = o;
     return L;
 }
@@ -538,21 +575,21 @@ static inline int tree_blocks(int n, int per_block) { return (n + per_block - 1)
 
 extern "C" {
 
-size_t hz_tree_workspace_bytes(int n_trees, int max_sims, int max_nodes) {
-    if (n_trees <= 0 || max_sims <= 0) return 0;
-    return layout_for(n_trees, max_sims, max_nodes).total;
+size_t hz_tree_workspace_bytes(int n_trees, int max_sims, int max_nodes, int leaves) {
+    if (n_trees <= 0 || max_sims <= 0 || leaves <= 0 || leaves > 64) return 0;
+    return layout_for(n_trees, max_sims, max_nodes, leaves).total;
 }
 
 int hz_tree_create(hz_tree** out, void* workspace, size_t workspace_bytes, int n_trees, int max_sims, int max_nodes,
-                   int key_mode) {
-    if (!out || !workspace || n_trees <= 0 || max_sims <= 0) return HZ_ERR_ARG;
+                   int key_mode, int leaves) {
+    if (!out || !workspace || n_trees <= 0 || max_sims <= 0 || leaves <= 0 || leaves > 64) return HZ_ERR_ARG;
     if (key_mode != HZ_KEY_EXACT && key_mode != HZ_KEY_REFERENCE) return HZ_ERR_ARG;
-    Layout L = layout_for(n_trees, max_sims, max_nodes);
+    Layout L = layout_for(n_trees, max_sims, max_nodes, leaves);
     if (workspace_bytes < L.total || ((uintptr_t)workspace & 255)) return HZ_ERR_WORKSPACE;
     hz_tree* t = new hz_tree;
     char* b = (char*)workspace;
     t->n_trees = n_trees; t->max_sims = max_sims; t->max_nodes = L.max_nodes; t->max_edges = L.max_edges;
-    t->table_size = L.table_size; t->key_mode = key_mode;
+    t->table_size = L.table_size; t->key_mode = key_mode; t->leaves = leaves;
     t->node_state = (uint4*)(b + L.off[0]); t->node_hash = (uint64_t*)(b + L.off[1]);
     t->node_edge0 = (uint32_t*)(b + L.off[2]); t->node_info = (uint32_t*)(b + L.off[3]);
     t->edge_child = (uint32_t*)(b + L.off[4]); t->edge_N = (int32_t*)(b + L.off[5]);
@@ -561,6 +598,7 @@ int hz_tree_create(hz_tree** out, void* workspace, size_t workspace_bytes, int n
     t->depth = (int32_t*)(b + L.off[11]); t->leaf = (int32_t*)(b + L.off[12]); t->sim = (int32_t*)(b + L.off[13]);
     t->n_nodes = (int32_t*)(b + L.off[14]); t->n_edges = (int32_t*)(b + L.off[15]);
     t->status = (uint8_t*)(b + L.off[16]); t->search_key = (uint64_t*)(b + L.off[17]);
+    t->edge_V = (int32_t*)(b + L.off[18]);
     t->table_bytes = (size_t)n_trees * L.table_size * 4;
     *out = t;
     return HZ_OK;

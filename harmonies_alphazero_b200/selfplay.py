@@ -38,6 +38,7 @@ class SelfPlayConfig:
     seed: int = 0
     first_game_id: int = 0         # global id of this rank's first game (sharding)
     use_cuda_graph: bool = True
+    leaves_per_step: int = 1       # K simulations in flight per tree and step; 1 = reference-exact search, >1 = virtual loss
     n_streams: int = 1             # >1: split the slots into groups on separate streams (overlap tree kernels with convs)
     max_nodes: int = 0             # per-tree node arena; 0 = worst case 1 + 69*sims
     max_moves: int = 200           # hard cap per game (structural maximum is 160 actions)
@@ -102,13 +103,17 @@ class _Group:
         cfg, net, dev = owner.cfg, owner.net, owner.device
         self.o, self.lo, self.hi = owner, lo, hi
         n = hi - lo
-        self.tree = BatchedMCTS(n, cfg.num_simulations, device=dev, key_mode=cfg.key_mode, max_nodes=cfg.max_nodes)
+        K = max(1, int(cfg.leaves_per_step))
+        if cfg.num_simulations % K:
+            raise ValueError("num_simulations must be a multiple of leaves_per_step")
+        self.tree = BatchedMCTS(n, cfg.num_simulations, device=dev, key_mode=cfg.key_mode, max_nodes=cfg.max_nodes, leaves=K)
+        rows = n * K                  # the network sees K leaves per tree and step
         dt, cl = net.dtype, owner.channels_last
-        self.board = torch.empty((n, 40 if owner.pad40 else 38, 5, 7), dtype=dt, device=dev,
+        self.board = torch.empty((rows, 40 if owner.pad40 else 38, 5, 7), dtype=dt, device=dev,
                                  memory_format=torch.channels_last if cl else torch.contiguous_format).zero_()
-        self.glob = torch.zeros((n, 42), dtype=dt, device=dev)
-        self.logits = torch.zeros((n, 143), dtype=torch.float32, device=dev)
-        self.value = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.glob = torch.zeros((rows, 42), dtype=dt, device=dev)
+        self.logits = torch.zeros((rows, 143), dtype=torch.float32, device=dev)
+        self.value = torch.zeros(rows, dtype=torch.float32, device=dev)
         self.noise = None if cfg.testing else torch.ones((n, 143), dtype=torch.float32, device=dev)
         self.alpha = None if cfg.testing else torch.full((n, 143), cfg.dirichlet_alpha, dtype=torch.float32, device=dev)
         self.graph = None
@@ -194,7 +199,7 @@ class BatchedSelfPlay:
         for g in self.groups:
             if g.stream is not None:
                 g.stream.wait_stream(main)
-        for _ in range(cfg.num_simulations):
+        for _ in range(cfg.num_simulations // max(1, int(cfg.leaves_per_step))):
             for g in self.groups:
                 if g.stream is None:
                     g.graph.replay() if g.graph is not None else g.sim_step()

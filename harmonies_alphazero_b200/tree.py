@@ -16,18 +16,21 @@ from .batched import F32, BF16, NCHW, NHWC, KEY_EXACT, KEY_REFERENCE, _ptr  # no
 
 
 class BatchedMCTS:
-    def __init__(self, n_trees, max_sims, device="cuda", key_mode=KEY_REFERENCE, max_nodes=0):
+    def __init__(self, n_trees, max_sims, device="cuda", key_mode=KEY_REFERENCE, max_nodes=0, leaves=1):
+        """leaves = simulations in flight per tree and step: 1 = the reference's sequential search
+        (parity mode); K > 1 = virtual-loss mode, the evaluator then sees n_trees*K rows."""
         self.lib = _lib.load()
-        self.n, self.max_sims, self.key_mode = int(n_trees), int(max_sims), key_mode
+        self.n, self.max_sims, self.key_mode, self.leaves = int(n_trees), int(max_sims), key_mode, int(leaves)
+        self.rows = self.n * self.leaves
         self.device = torch.device(device)
-        nbytes = self.lib.hz_tree_workspace_bytes(self.n, self.max_sims, max_nodes)
+        nbytes = self.lib.hz_tree_workspace_bytes(self.n, self.max_sims, max_nodes, self.leaves)
         if nbytes == 0:
             raise ValueError("bad tree dimensions")
         # caller-owned workspace (a torch allocation is >=512 B aligned)
         self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)   # zeroed: counters/status are defined before the first reset
         h = C.c_void_p()
         _lib.check(
-            self.lib.hz_tree_create(C.byref(h), self.workspace.data_ptr(), nbytes, self.n, self.max_sims, max_nodes, key_mode),
+            self.lib.hz_tree_create(C.byref(h), self.workspace.data_ptr(), nbytes, self.n, self.max_sims, max_nodes, key_mode, self.leaves),
             "hz_tree_create",
         )
         self.handle = h
@@ -55,7 +58,7 @@ class BatchedMCTS:
         code = {torch.float32: F32, torch.bfloat16: BF16}[dtype]
         layout = 2 if pad40 else (NHWC if channels_last else NCHW)
         if board is not None:
-            assert board.shape[1] == (40 if pad40 else 38)
+            assert board.shape[1] == (40 if pad40 else 38) and board.shape[0] == self.rows and glob.shape[0] == self.rows
         with torch.cuda.device(self.device):
             _lib.check(
                 self.lib.hz_tree_select(
@@ -66,8 +69,8 @@ class BatchedMCTS:
             )
 
     def expand_backup(self, policy, value, is_logits=False, noise=None, eps=0.0):
-        assert policy.dtype == torch.float32 and policy.shape == (self.n, 143) and policy.is_contiguous()
-        assert value.dtype == torch.float32 and value.numel() == self.n and value.is_contiguous()
+        assert policy.dtype == torch.float32 and policy.shape == (self.rows, 143) and policy.is_contiguous()
+        assert value.dtype == torch.float32 and value.numel() == self.rows and value.is_contiguous()
         if noise is not None:
             assert noise.dtype == torch.float32 and noise.shape == (self.n, 143) and noise.is_contiguous()
         with torch.cuda.device(self.device):
@@ -121,9 +124,10 @@ class BatchedMCTS:
 
     def run_synthetic(self, sims, cpuct, noise=None, eps=0.0):
         """``sims`` simulations with the synthetic evaluator (tests, tree-only benchmarks)."""
-        policy = torch.empty((self.n, 143), dtype=torch.float32, device=self.device)
-        value = torch.empty(self.n, dtype=torch.float32, device=self.device)
-        for _ in range(sims):
+        policy = torch.empty((self.rows, 143), dtype=torch.float32, device=self.device)
+        value = torch.empty(self.rows, dtype=torch.float32, device=self.device)
+        assert sims % self.leaves == 0
+        for _ in range(sims // self.leaves):
             self.select(cpuct)
             self.fake_eval(policy, value)
             self.expand_backup(policy, value, noise=noise, eps=eps)

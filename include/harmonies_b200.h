@@ -69,7 +69,7 @@
 extern "C" {
 #endif
 
-#define HZ_ABI_VERSION      1
+#define HZ_ABI_VERSION      2
 #define HZ_STATE_WORDS      32
 #define HZ_STATE_BYTES      128
 #define HZ_NUM_HEXES        23
@@ -207,12 +207,17 @@ int hz_playout(void *states, int64_t n, int max_steps, uint32_t *steps,
 typedef struct hz_tree hz_tree;   /* opaque: n_trees independent DAGs in flat arrays */
 
 /* Bytes of device workspace for n_trees searches of at most max_sims simulations.
- * max_nodes == 0 selects the worst case (1 + 69*max_sims nodes per tree). */
-size_t hz_tree_workspace_bytes(int n_trees, int max_sims, int max_nodes);
+ * max_nodes == 0 selects the worst case (1 + 69*max_sims nodes per tree).
+ * leaves = simulations in flight per tree and step: 1 is the reference's strictly sequential
+ * search (MCTS.py:291-352, the parity mode); K > 1 is the virtual-loss throughput mode: every
+ * hz_tree_select call descends K times per tree (edges on already chosen paths count one
+ * provisional visit and one provisional loss: N' = N + V, W' = W - V), the evaluator sees
+ * n_trees*K leaves (row t*K + j) and hz_tree_expand_backup lands them in order j = 0..K-1. */
+size_t hz_tree_workspace_bytes(int n_trees, int max_sims, int max_nodes, int leaves);
 
 /* Node/MCTS construction (MCTS.py:8-61) over caller-owned, 256-byte-aligned workspace. */
 int hz_tree_create(hz_tree **out, void *workspace, size_t workspace_bytes, int n_trees,
-                   int max_sims, int max_nodes, int key_mode);
+                   int max_sims, int max_nodes, int key_mode, int leaves);
 int hz_tree_destroy(hz_tree *t);
 
 /* Start a new search per tree (get_best_action_and_pi, MCTS.py:288-289: no tree reuse).

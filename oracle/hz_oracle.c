@@ -580,7 +580,7 @@ uint64_t hzo_playout(uint32_t *states, int64_t n, int max_steps, uint32_t *steps
 /* ====================================================================================== */
 typedef void (*hzo_eval_fn)(const uint32_t *leaf_state, float *policy143, double *value, void *user);
 
-typedef struct { int child, N, action, mover; double W; float P; } oedge;
+typedef struct { int child, N, action, mover, V; double W; float P; } oedge;   /* V: in-flight (virtual-loss) visits */
 typedef struct { uint32_t w[32]; uint64_t hash; int first_edge, n_edges, player; } onode;   /* hash = tree key */
 typedef struct {
     onode *nodes; int n_nodes, cap_nodes;
@@ -686,7 +686,7 @@ int hzo_search(const uint32_t *root, uint64_t search_key, int sims, double cpuct
                 leaf = &t.nodes[cur];
                 if (child < 0 || t.n_edges == t.cap_edges) { rc = -1; break; }
                 oedge *e = &t.edges[t.n_edges++];
-                e->child = child; e->N = 0; e->W = 0.0; e->P = policy[acts[i]];
+                e->child = child; e->N = 0; e->V = 0; e->W = 0.0; e->P = policy[acts[i]];
                 e->action = acts[i]; e->mover = leaf->player;    /* Edge, MCTS.py:23-39 */
                 cnt++;
             }
@@ -717,6 +717,130 @@ int hzo_search(const uint32_t *root, uint64_t search_key, int sims, double cpuct
     if (out_nodes) *out_nodes = t.n_nodes;
     if (out_edges) *out_edges = t.n_edges;
     free(t.nodes); free(t.edges); free(t.table); free(path);
+    return rc;
+}
+
+
+/* Virtual-loss search (throughput mode; north_star "select, expand and backup kernels using
+ * virtual loss"): `steps` rounds of `leaves` simulations per tree.  Within a round the K
+ * descents run one after the other; every edge on a chosen path carries one in-flight visit
+ * (N' = N + V, W' = W - V: a provisional loss for the mover) so that later descents of the
+ * round spread out.  Then the K leaves are evaluated together and, in order j = 0..K-1,
+ * expanded (if still unexpanded) and backed up (N += 1, W += v*dir, V -= 1).  Simulation
+ * index of leaf j of round r is r*K + j (draw events, node ids).  leaves == 1 is exactly
+ * hzo_search (the reference's sequential search). */
+int hzo_search_vl(const uint32_t *root, uint64_t search_key, int steps, int leaves, double cpuct, int key_mode,
+                  const float *noise, double eps, hzo_eval_fn eval, void *user, int32_t *outN, double *outW,
+                  float *outP, int32_t *out_child, int32_t *out_nodes, int32_t *out_edges) {
+    geometry();
+    if (!eval) eval = fake_eval;
+    int sims = steps * leaves;
+    otree t;
+    t.cap_nodes = 1 + 69 * sims; t.cap_edges = 69 * sims + 1;
+    int tsize = 1; while (tsize < 2 * t.cap_nodes) tsize <<= 1;
+    t.table_mask = tsize - 1;
+    t.nodes = (onode *)malloc(sizeof(onode) * (size_t)t.cap_nodes);
+    t.edges = (oedge *)malloc(sizeof(oedge) * (size_t)t.cap_edges);
+    t.table = (int *)malloc(sizeof(int) * (size_t)tsize);
+    int *path = (int *)malloc(sizeof(int) * (size_t)leaves * (size_t)(sims + 2));
+    int *depth = (int *)malloc(sizeof(int) * (size_t)leaves), *leafs = (int *)malloc(sizeof(int) * (size_t)leaves);
+    for (int i = 0; i < tsize; i++) t.table[i] = -1;
+    t.n_nodes = 0; t.n_edges = 0; t.key_mode = key_mode;
+    int was_new, rc = 0;
+    tree_find_or_add(&t, root, key_hash(root, key_mode), &was_new);
+    float cpuct_f = (float)cpuct;
+    for (int step = 0; step < steps && rc == 0; step++) {
+        for (int j = 0; j < leaves; j++) {                        /* K descents with virtual loss */
+            int *pj = path + (size_t)j * (size_t)(sims + 2);
+            int cur = 0, d = 0;
+            while (t.nodes[cur].n_edges > 0) {
+                onode *nd = &t.nodes[cur];
+                long ns = 0;
+                for (int k = 0; k < nd->n_edges; k++) ns += t.edges[nd->first_edge + k].N + t.edges[nd->first_edge + k].V;
+                double sqrt_ns = sqrt(ns > 1 ? (double)ns : 1.0);
+                double best = -INFINITY; int best_e = -1;
+                for (int k = 0; k < nd->n_edges; k++) {
+                    oedge *e = &t.edges[nd->first_edge + k];
+                    int n_eff = e->N + e->V;
+                    double w_eff = e->W - (double)e->V;
+                    float cp = cpuct_f * e->P;
+                    double u = (double)cp * sqrt_ns / (double)(1 + n_eff);
+                    double q = n_eff ? w_eff / (double)n_eff : 0.0;
+                    if (q + u > best) { best = q + u; best_e = nd->first_edge + k; }
+                }
+                if (best_e < 0) break;
+                pj[d++] = best_e;
+                cur = t.edges[best_e].child;
+            }
+            for (int i = 0; i < d; i++) t.edges[pj[i]].V += 1;
+            depth[j] = d; leafs[j] = cur;
+        }
+        for (int j = 0; j < leaves && rc == 0; j++) {             /* evaluate, expand, back up in order */
+            int sim = step * leaves + j, cur = leafs[j];
+            int *pj = path + (size_t)j * (size_t)(sims + 2);
+            onode *leaf = &t.nodes[cur];
+            ostate ls; unpack(leaf->w, &ls);
+            double value;
+            if (!is_over(&ls)) {
+                float policy[HZ_ACTION_SIZE];
+                eval(leaf->w, policy, &value, user);
+                if (leaf->n_edges == 0) {                         /* not expanded earlier in this round */
+                    int acts[HZ_ACTION_SIZE], k = legal_actions(&ls, acts);
+                    if (cur == 0 && noise && k > 0) {
+                        double sum = 0.0;
+                        for (int i = 0; i < k; i++) sum += (double)noise[acts[i]];
+                        float one_minus = (float)(1.0 - eps);
+                        for (int i = 0; i < k; i++) {
+                            float keep = one_minus * policy[acts[i]];
+                            policy[acts[i]] = (float)((double)keep + eps * ((double)noise[acts[i]] / sum));
+                        }
+                    }
+                    int first = t.n_edges, cnt = 0;
+                    for (int i = 0; i < k; i++) {
+                        ostate cs = ls;
+                        cs.key = search_key; cs.event = ((uint32_t)sim << 8) | (uint32_t)acts[i];
+                        if (apply_action(&cs, acts[i], HZ_NO_DRAW) != HZ_MOVE_OK) continue;
+                        cs.key = ls.key; cs.event = ls.event;
+                        uint32_t cw[32]; pack(&cs, cw);
+                        uint64_t h = key_hash(cw, key_mode);
+                        if (h == leaf->hash) continue;
+                        int child = tree_find_or_add(&t, cw, h, &was_new);
+                        leaf = &t.nodes[cur];
+                        if (child < 0 || t.n_edges == t.cap_edges) { rc = -1; break; }
+                        oedge *e = &t.edges[t.n_edges++];
+                        e->child = child; e->N = 0; e->V = 0; e->W = 0.0; e->P = policy[acts[i]];
+                        e->action = acts[i]; e->mover = leaf->player;
+                        cnt++;
+                    }
+                    leaf->first_edge = first; leaf->n_edges = cnt;
+                }
+            } else {
+                int oc = outcome(&ls);
+                value = oc == 0 ? 0.0 : (leaf->player == 0 ? (double)oc : -(double)oc);
+            }
+            for (int d = depth[j] - 1; d >= 0; d--) {
+                oedge *e = &t.edges[pj[d]];
+                double dir = e->mover == t.nodes[cur].player ? 1.0 : -1.0;
+                e->N += 1; e->W += value * dir; e->V -= 1;
+            }
+        }
+    }
+    for (int a = 0; a < HZ_ACTION_SIZE; a++) {
+        if (outN) outN[a] = 0;
+        if (outW) outW[a] = 0.0;
+        if (outP) outP[a] = 0.0f;
+        if (out_child) out_child[a] = -1;
+    }
+    for (int k = 0; k < t.nodes[0].n_edges; k++) {
+        oedge *e = &t.edges[t.nodes[0].first_edge + k];
+        if (outN) outN[e->action] = e->N;
+        if (outW) outW[e->action] = e->W;
+        if (outP) outP[e->action] = e->P;
+        if (out_child) out_child[e->action] = e->child;
+    }
+    if (out_nodes) *out_nodes = t.n_nodes;
+    if (out_edges) *out_edges = t.n_edges;
+    free(t.nodes); free(t.edges); free(t.table); free(path); free(depth); free(leafs);
     return rc;
 }
 

@@ -34,6 +34,7 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.hzo_playout.restype = C.c_uint64
         _lib.hzo_search.restype = C.c_int
+        _lib.hzo_search_vl.restype = C.c_int
         _lib.hzo_choose.restype = C.c_int
     return _lib
 
@@ -124,7 +125,7 @@ def playout(states, max_steps=1000, n_threads=1):
     return s, steps, int(total)
 
 
-def search(root, search_key, sims, cpuct, noise=None, eps=0.0, eval_fn=None, key_mode=1):
+def search(root, search_key, sims, cpuct, noise=None, eps=0.0, eval_fn=None, key_mode=1, leaves=1):
     """One reference-semantics search.  eval_fn(words[32]) -> (p[143] float32, v float) or
     None for the synthetic evaluator.  Returns dict(N, W, P, child, n_nodes, n_edges, rc)."""
     r = np.ascontiguousarray(root, dtype=np.uint32).reshape(32)
@@ -144,10 +145,17 @@ def search(root, search_key, sims, cpuct, noise=None, eps=0.0, eval_fn=None, key
             vp[0] = float(v)
 
         cb = EVAL_FN(_cb)
-    rc = lib().hzo_search(
-        _p(r), C.c_uint64(int(search_key)), C.c_int(sims), C.c_double(cpuct), C.c_int(key_mode), _p(nz), C.c_double(eps),
-        cb, None, _p(N), _p(W), _p(P), _p(child), C.byref(nn), C.byref(ne),
-    )
+    if leaves == 1:
+        rc = lib().hzo_search(
+            _p(r), C.c_uint64(int(search_key)), C.c_int(sims), C.c_double(cpuct), C.c_int(key_mode), _p(nz), C.c_double(eps),
+            cb, None, _p(N), _p(W), _p(P), _p(child), C.byref(nn), C.byref(ne),
+        )
+    else:   # virtual-loss mode: sims must be a multiple of leaves (sims // leaves rounds)
+        assert sims % leaves == 0
+        rc = lib().hzo_search_vl(
+            _p(r), C.c_uint64(int(search_key)), C.c_int(sims // leaves), C.c_int(leaves), C.c_double(cpuct), C.c_int(key_mode),
+            _p(nz), C.c_double(eps), cb, None, _p(N), _p(W), _p(P), _p(child), C.byref(nn), C.byref(ne),
+        )
     return {"N": N, "W": W, "P": P, "child": child, "n_nodes": nn.value, "n_edges": ne.value, "rc": rc}
 
 

@@ -41,10 +41,12 @@ def test_library_exports_every_declared_symbol(built_lib):
     # the Python binding declares a signature for each of them, and nothing else
     assert sorted(_lib.SIGNATURES) == syms
     loaded = _lib.load()
-    assert loaded.hz_abi_version() == 1
+    assert loaded.hz_abi_version() == 2
     assert loaded.hz_status_string(-4).decode().startswith("workspace")
     assert loaded.hz_launch_count() == 0
-    assert loaded.hz_tree_workspace_bytes(4096, 100, 0) > 4096 * 6901 * 128
+    assert loaded.hz_tree_workspace_bytes(4096, 100, 0, 1) > 4096 * 6901 * 128
+    assert loaded.hz_tree_workspace_bytes(4096, 100, 0, 8) > loaded.hz_tree_workspace_bytes(4096, 100, 0, 1)
+    assert loaded.hz_tree_workspace_bytes(4096, 100, 0, 0) == 0
 
 
 def test_missing_library_fails_loudly(tmp_path):

@@ -117,6 +117,37 @@ def test_full_size_config3_properties_and_oracle_subsample(mods, oracle):
         assert nn[i] == r["n_nodes"] and ne[i] == r["n_edges"], i
 
 
+@pytest.mark.parametrize("leaves", [2, 4, 8])
+def test_virtual_loss_mode_matches_oracle(mods, oracle, leaves):
+    """throughput mode (north_star: select/expand/backup "using virtual loss"): K simulations in
+    flight per tree and step.  Oracle = the reference's search restated with the same
+    virtual-loss schedule (hzo_search_vl; leaves=1 is the pinned sequential search)."""
+    hb, tr = mods
+    n, sims, cpuct, eps = 256, 64, 2.0, 0.25
+    st = hb.init_states(n, seed=909)
+    for lo, hi, d in [(0, 64, 0), (64, 128, 5), (128, 192, 30), (192, 256, 58)]:
+        sl = st[lo:hi].clone()
+        hb.playout(sl, max_steps=d)
+        st[lo:hi] = sl
+    roots = st.cpu().numpy().view(np.uint32)
+    rng = np.random.default_rng(leaves)
+    skeys = rng.integers(0, 2**63, size=n, dtype=np.uint64)
+    noise = rng.gamma(0.4, size=(n, 143)).astype(np.float32) + np.float32(1e-6)
+    t = tr.BatchedMCTS(n, sims, leaves=leaves)
+    t.reset(hb.states_from_numpy(roots), tr.search_keys_tensor(skeys))
+    t.run_synthetic(sims, cpuct, noise=torch.from_numpy(noise).cuda(), eps=eps)
+    t.check_status()
+    N, W, P, _ = (x.cpu().numpy() for x in t.root_edges())
+    nn, ne, _ = (x.cpu().numpy() for x in t.stats())
+    # every in-flight visit has landed: total visits = sims minus the ones that ended at the root
+    for i in range(n):
+        r = oracle.search(roots[i], skeys[i], sims, cpuct, noise[i], eps, leaves=leaves)
+        assert np.array_equal(N[i], r["N"]), i
+        assert np.array_equal(W[i], r["W"]), i
+        assert np.array_equal(P[i].view(np.uint32), r["P"].view(np.uint32)), i
+        assert nn[i] == r["n_nodes"] and ne[i] == r["n_edges"], i
+
+
 def test_select_outputs_leaf_encoding(mods, oracle):
     """the tensors handed to the network are create_state_tensors(leaf) (MCTS.py:299)"""
     hb, tr = mods
