@@ -224,6 +224,25 @@ def test_arena_match(mods):
     assert r3["candidate_wins"] + r3["best_wins"] + r3["draws"] == 10 and r3["best_wins"] >= 8
     r4 = arena.play_match(arena.GREEDY, arena.GREEDY, 6, cfg, seed=7)
     assert r4["candidate_wins"] + r4["best_wins"] + r4["draws"] == 6
+    # virtual-loss searches (3 simulations in flight per tree): a complete, deterministic match
+    r5 = arena.play_match(cand, best, 6, cfg, seed=5, leaves=3)
+    assert r5["candidate_wins"] + r5["best_wins"] + r5["draws"] == 6
+    assert arena.play_match(cand, best, 6, cfg, seed=5, leaves=3) == r5
+
+
+def test_selfplay_with_virtual_loss(mods):
+    """leaves_per_step > 1: whole games complete, sum N = S - K (the K descents of the first
+    step all end at the unexpanded root), examples keep the reference contract"""
+    hb, net, sp, _ = mods
+    _, inf = _small_net(net, torch.bfloat16, seed=6)
+    cfg = sp.SelfPlayConfig(n_slots=48, num_simulations=12, leaves_per_step=4, seed=13)
+    torch.manual_seed(1)
+    traj = sp.BatchedSelfPlay(inf, cfg).play(60)
+    assert traj.stats["games"] == 60
+    assert (traj.visits.sum(dim=1) == 12 - 4).all()
+    assert torch.allclose(traj.pi().sum(dim=1), torch.ones(len(traj), device="cuda"), atol=1e-6)
+    with pytest.raises(ValueError):
+        sp.BatchedSelfPlay(inf, sp.SelfPlayConfig(n_slots=8, num_simulations=10, leaves_per_step=4))
 
 
 def test_selfplay_is_independent_of_slot_count_in_testing_mode(mods):
