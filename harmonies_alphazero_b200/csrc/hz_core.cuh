@@ -267,23 +267,46 @@ __device__ __forceinline__ void score_board(const NbrLut* lut, const Board& b, i
     uint32_t s2 = n_s ^ n_b ^ n_f, c2 = (n_s & n_b) | (n_f & (n_s ^ n_b));
     uint32_t atleast3 = (c1 & c2) | ((c1 | c2) & (s1 | s2));
     terms[3] = 5 * __popc(tbl & h2 & atleast3);
-    // fields :424-443 — isolated hexes (size-1 components) are dropped up front, so every
-    // flood below is a component of size >= 2
-    int sc = 0;
+    // fields :424-443 — 5 points per component of size >= 2.  Isolated hexes are dropped up front;
+    // the component count of what is left comes from the Euler characteristic of the hex cells,
+    // components - holes = V - E + T (hexes, adjacent pairs, mutually adjacent triples), each term a
+    // popcount of masked shifts, so the common case has no data-dependent loop.  A hole needs a
+    // ring of >= 6 field hexes: only then the enclosed regions of the complement are counted.
     uint32_t rem = tf & n_f;
-    while (rem) {
-        uint32_t comp = flood(lut, rem & (0u - rem), rem);
-        rem &= ~comp;
-        sc += 5;
+    uint32_t fe = rem & pull_E(rem);
+    int comps = __popc(rem) - __popc(fe) - __popc(rem & pull_S(rem)) - __popc(rem & pull_NE(rem))
+              + __popc(fe & pull_S(rem)) + __popc(fe & pull_NE(rem));
+    if (__popc(rem) >= 6) {
+        uint32_t c = VALID & ~rem;
+        uint32_t enclosed = c & ~flood(lut, c & BOUNDARY_HEXES, c);
+        while (enclosed) {
+            uint32_t hole = flood(lut, enclosed & (0u - enclosed), enclosed);
+            enclosed &= ~hole;
+            comps++;
+        }
     }
-    terms[2] = sc;
-    // water :480-518 — per component of size >= 2: (BFS diameter + 1) -> table
-    sc = 0;
+    terms[2] = 5 * comps;
+    // water :480-518 — per component of size >= 2: (BFS diameter + 1) -> table.  Size-2 components
+    // (by far the most common) are found without a loop: both hexes have exactly one water
+    // neighbour (bit-sliced count over the six directions) and are adjacent to each other.
+    int sc = 0;
     rem = tw & n_w;
-    while (rem) {
+    {
+        uint32_t one = 0, more = 0, p;
+        p = pull_E(rem);  one ^= p;
+        p = pull_W(rem);  more |= one & p; one ^= p;
+        p = pull_S(rem);  more |= one & p; one ^= p;
+        p = pull_N(rem);  more |= one & p; one ^= p;
+        p = pull_NE(rem); more |= one & p; one ^= p;
+        p = pull_SW(rem); more |= one & p; one ^= p;
+        uint32_t deg1 = rem & one & ~more;
+        uint32_t pairs = deg1 & nbr(lut, deg1);
+        sc = __popc(pairs);                                           // length 2 -> 2 points per pair
+        rem &= ~pairs;
+    }
+    while (rem) {                                                     // components of size >= 3
         uint32_t comp = flood(lut, rem & (0u - rem), rem);
         rem &= ~comp;
-        if (__popc(comp) == 2) { sc += 2; continue; }                 // diameter 1 -> length 2
         int diameter = 0;
         uint32_t src = comp;
         while (src) {
