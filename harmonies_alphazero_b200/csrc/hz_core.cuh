@@ -291,15 +291,15 @@ __device__ __forceinline__ void score_board(const NbrLut* lut, const Board& b, i
     // neighbour (bit-sliced count over the six directions) and are adjacent to each other.
     int sc = 0;
     rem = tw & n_w;
+    uint32_t we = pull_E(rem), ws = pull_S(rem), wne = pull_NE(rem), deg1;
     {
-        uint32_t one = 0, more = 0, p;
-        p = pull_E(rem);  one ^= p;
+        uint32_t one = we, more = 0, p;
         p = pull_W(rem);  more |= one & p; one ^= p;
-        p = pull_S(rem);  more |= one & p; one ^= p;
+        more |= one & ws;  one ^= ws;
         p = pull_N(rem);  more |= one & p; one ^= p;
-        p = pull_NE(rem); more |= one & p; one ^= p;
+        more |= one & wne; one ^= wne;
         p = pull_SW(rem); more |= one & p; one ^= p;
-        uint32_t deg1 = rem & one & ~more;
+        deg1 = rem & one & ~more;
         uint32_t pairs = deg1 & nbr(lut, deg1);
         sc = __popc(pairs);                                           // length 2 -> 2 points per pair
         rem &= ~pairs;
@@ -307,14 +307,23 @@ __device__ __forceinline__ void score_board(const NbrLut* lut, const Board& b, i
     while (rem) {                                                     // components of size >= 3
         uint32_t comp = flood(lut, rem & (0u - rem), rem);
         rem &= ~comp;
-        int diameter = 0;
-        uint32_t src = comp;
-        while (src) {
-            uint32_t f = src & (0u - src), nf;
-            src ^= f;
-            int d = 0;
-            while ((nf = (f | nbr(lut, f)) & comp) != f) { f = nf; d++; }
-            diameter = max(diameter, d);
+        int size = __popc(comp), diameter;
+        if (size <= 4) {
+            // closed forms from the edge count: 3 hexes are a triangle (diameter 1) or a path (2);
+            // 4 hexes have diameter 3 only as a path (3 edges, two ends), every other shape on this
+            // lattice (claw, triangle + tail, rhombus) has diameter 2
+            int edges = __popc(comp & we) + __popc(comp & ws) + __popc(comp & wne);
+            diameter = size == 3 ? 4 - edges : (edges == 3 && __popc(comp & deg1) == 2) ? 3 : 2;
+        } else {
+            diameter = 0;
+            uint32_t src = comp;
+            while (src) {
+                uint32_t f = src & (0u - src), nf;
+                src ^= f;
+                int d = 0;
+                while ((nf = (f | nbr(lut, f)) & comp) != f) { f = nf; d++; }
+                diameter = max(diameter, d);
+            }
         }
         sc += water_points(diameter + 1);
     }
