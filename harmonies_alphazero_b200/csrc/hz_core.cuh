@@ -247,7 +247,35 @@ __device__ __forceinline__ uint32_t flood(const NbrLut* lut, uint32_t seed, uint
 __device__ __forceinline__ int water_points(int len) {              // :18-27
     return len <= 1 ? 0 : len == 2 ? 2 : len <= 5 ? 3 * len - 4 : 15 + (len - 6) * 4;
 }
-__device__ __forceinline__ void score_board(const NbrLut* lut, const Board& b, int terms[5]) {
+// Water components of >= 5 hexes are rare (a few percent of boards) but one of them costs a lane
+// ~20 flood iterations while the other 31 wait.  A caller whose block reconverges after scoring
+// passes a WaterQueue: such components are pushed there instead, and resolve_water() gives each
+// queued component a whole warp, one BFS source per lane.
+template <int CAP, int OWNERS>
+struct WaterQueue {
+    uint32_t comp[CAP];
+    uint16_t owner[CAP];
+    int extra[OWNERS];      // points of the resolved components, per owner slot
+    int count;
+};
+template <int CAP, int OWNERS>
+__device__ __forceinline__ void water_queue_init(WaterQueue<CAP, OWNERS>* q) {   // then __syncthreads()
+    for (int e = threadIdx.x; e < OWNERS; e += blockDim.x) q->extra[e] = 0;
+    if (threadIdx.x == 0) q->count = 0;
+}
+struct NoWaterQueue {};
+__device__ __forceinline__ bool water_push(NoWaterQueue*, uint32_t, int) { return false; }
+template <int CAP, int OWNERS>
+__device__ __forceinline__ bool water_push(WaterQueue<CAP, OWNERS>* q, uint32_t comp, int owner) {
+    int slot = atomicAdd(&q->count, 1);
+    if (slot >= CAP) return false;                                    // full: the caller scores it in place
+    q->comp[slot] = comp;
+    q->owner[slot] = (uint16_t)owner;
+    return true;
+}
+template <typename Q = NoWaterQueue>
+__device__ __forceinline__ void score_board(const NbrLut* lut, const Board& b, int terms[5], Q* wq = nullptr,
+                                            int owner = 0) {
     Tops t = tops_of(b);
     uint32_t h1 = t.occ0 & ~t.occ1, h2 = t.occ1 & ~t.occ2, h3 = t.occ2;
     // grass :369-385
@@ -315,6 +343,7 @@ __device__ __forceinline__ void score_board(const NbrLut* lut, const Board& b, i
             int edges = __popc(comp & we) + __popc(comp & ws) + __popc(comp & wne);
             diameter = size == 3 ? 4 - edges : (edges == 3 && __popc(comp & deg1) == 2) ? 3 : 2;
         } else {
+            if (water_push(wq, comp, owner)) continue;
             diameter = 0;
             uint32_t src = comp;
             while (src) {
@@ -328,6 +357,18 @@ __device__ __forceinline__ void score_board(const NbrLut* lut, const Board& b, i
         sc += water_points(diameter + 1);
     }
     terms[4] = sc;
+}
+// all threads of the block, between two __syncthreads(): q->extra[owner] += points of each queued component
+template <int CAP, int OWNERS>
+__device__ __forceinline__ void resolve_water(const NbrLut* lut, WaterQueue<CAP, OWNERS>* q) {
+    int n = min(q->count, CAP), lane = threadIdx.x & 31;
+    for (int e = threadIdx.x >> 5; e < n; e += blockDim.x >> 5) {
+        uint32_t comp = q->comp[e], f = (1u << lane) & comp, nf;
+        int d = 0;
+        if (f) while ((nf = (f | nbr(lut, f)) & comp) != f) { f = nf; d++; }
+        d = __reduce_max_sync(0xFFFFFFFFu, d);
+        if (lane == 0) atomicAdd(&q->extra[q->owner[e]], water_points(d + 1));
+    }
 }
 __device__ __forceinline__ int score_player(const NbrLut* lut, const State& s, int p) {
     int t[5];

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(TPB) k_apply(void* states, int64_t n, const in
 __global__ void __launch_bounds__(TPB) k_score(const void* states, int64_t n, int16_t* scores,
                                                int16_t* terms) {
     __shared__ NbrLut lut;
+    __shared__ WaterQueue<2 * TPB, 2 * TPB> wq;
     int64_t g = (int64_t)blockIdx.x * TPB + threadIdx.x;
     // only the 18 board words are needed: 92 -> 80 B of traffic per position; the loads are
     // issued before the LUT copy so that the two overlap
@@ -65,20 +66,30 @@ __global__ void __launch_bounds__(TPB) k_score(const void* states, int64_t n, in
         }
     }
     build_nbr_lut(&lut);
+    water_queue_init(&wq);
+    __syncthreads();
+    int t[2][5];
+    if (g < n) {
+#pragma unroll
+        for (int pl = 0; pl < 2; pl++) {
+            Board b;
+#pragma unroll
+            for (int k = 0; k < 9; k++) b.p[k] = w[pl * 9 + k];
+            score_board(&lut, b, t[pl], &wq, (int)threadIdx.x * 2 + pl);
+        }
+    }
+    __syncthreads();
+    resolve_water(&lut, &wq);          // the rare large water components, one warp each
     __syncthreads();
     if (g >= n) return;
 #pragma unroll
     for (int pl = 0; pl < 2; pl++) {
-        Board b;
-#pragma unroll
-        for (int k = 0; k < 9; k++) b.p[k] = w[pl * 9 + k];
-        int t[5];
-        score_board(&lut, b, t);
+        t[pl][4] += wq.extra[threadIdx.x * 2 + pl];
         if (terms) {
 #pragma unroll
-            for (int k = 0; k < 5; k++) terms[(g * 2 + pl) * 5 + k] = (int16_t)t[k];
+            for (int k = 0; k < 5; k++) terms[(g * 2 + pl) * 5 + k] = (int16_t)t[pl][k];
         }
-        if (scores) scores[g * 2 + pl] = (int16_t)(t[0] + t[1] + t[2] + t[3] + t[4]);
+        if (scores) scores[g * 2 + pl] = (int16_t)(t[pl][0] + t[pl][1] + t[pl][2] + t[pl][3] + t[pl][4]);
     }
 }
 
