@@ -55,6 +55,13 @@ __device__ __forceinline__ const NbrLut* global_nbr_lut() { return reinterpret_c
 __device__ __forceinline__ uint32_t nbr(const NbrLut* lut, uint32_t m) {
     return lut->t[0][m & 255] | lut->t[1][(m >> 8) & 255] | lut->t[2][(m >> 16) & 127];
 }
+// The same expansion as ~20 shift/logic ops and no memory access.  With a full warp the three
+// random LUT reads cost ~6 shared-memory wavefronts (bank conflicts); scoring uses this form in
+// its straight-line part and the LUT inside the sparse, few-lane flood loops so that neither the
+// LSU pipe nor the ALU pipe is the only one loaded (profiles/README.md, k_score).
+__device__ __forceinline__ uint32_t nbr_alu(uint32_t m) {
+    return pull_E(m) | pull_W(m) | pull_S(m) | pull_N(m) | pull_NE(m) | pull_SW(m);
+}
 
 // ---- rng ---------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
@@ -284,8 +291,8 @@ __device__ __forceinline__ void score_board(const NbrLut* lut, const Board& b, i
     terms[0] = __popc(tp & h1) + 3 * __popc(tp & h2 & l0_wood) + 7 * __popc(tp & h3 & l0_wood & l1_wood);
     // One neighbour expansion per top type serves every term: n_X = hexes adjacent to an X-top.
     uint32_t tw = top_water(t), twd = top_wood(t), ts = top_stone(t), tbl = top_building(t), tf = top_field(t);
-    uint32_t n_w = nbr(lut, tw), n_p = nbr(lut, tp), n_wd = nbr(lut, twd), n_s = nbr(lut, ts);
-    uint32_t n_b = nbr(lut, tbl), n_f = nbr(lut, tf);
+    uint32_t n_w = nbr_alu(tw), n_p = nbr_alu(tp), n_wd = nbr_alu(twd), n_s = nbr_alu(ts);
+    uint32_t n_b = nbr_alu(tbl), n_f = nbr_alu(tf);
     // mountains :392-413
     uint32_t adj = ts & n_s;
     terms[1] = __popc(adj & h1) + 3 * __popc(adj & h2) + 7 * __popc(adj & h3);
