@@ -26,6 +26,7 @@ SIGNATURES = {
     "hz_random_actions": (_i, [_vp, _i64, _vp, _vp]),
     "hz_greedy_actions": (_i, [_vp, _i64, _vp, _vp]),
     "hz_playout": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
+    "hz_playout_keys": (_i, [_vp, _i64, _u64, _u64, _i, _vp, _vp, _vp]),
     "hz_tree_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "hz_tree_create": (_i, [C.POINTER(_vp), _vp, C.c_size_t, _i, _i, _i, _i, _i]),
     "hz_tree_destroy": (_i, [_vp]),
@@ -63,7 +64,7 @@ def load(path=None):
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype, fn.argtypes = res, args
-    if lib.hz_abi_version() != 2:
+    if lib.hz_abi_version() != 3:
         raise HarmoniesLibraryError("ABI version mismatch")
     if path is None:
         _lib = lib

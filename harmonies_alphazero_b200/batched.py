@@ -171,6 +171,34 @@ def playout(states, max_steps=1000, steps=None, total=None):
     return steps, total
 
 
+def playout_keys(keys, results=None, total=None, max_steps=1000, n=None, seed=0, first_id=0, device=None):
+    """Fresh games from their keys, played to the end in one launch (hz_playout_keys).
+    ``keys`` int64[n] on the device (or None: keys derived from (seed, first_id + i), then ``n``
+    and ``device`` are required).  Returns (results int32[n, 3], total int64[1]): per game the
+    meta word (phase, winner code), the final-score word and the number of actions played."""
+    lib = _lib.load()
+    if keys is not None:
+        if keys.dtype != torch.int64 or keys.dim() != 1 or not keys.is_cuda or not keys.is_contiguous():
+            raise TypeError("keys must be a contiguous int64[n] CUDA tensor")
+        n, device = keys.shape[0], keys.device
+    elif n is None or device is None:
+        raise ValueError("n and device are required when keys is None")
+    device = torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    results = torch.empty((n, 3), dtype=torch.int32, device=device) if results is None else results
+    if results.shape != (n, 3) or results.dtype != torch.int32 or not results.is_contiguous() or results.device != device:
+        raise TypeError("results must be a contiguous int32[n, 3] tensor on the keys' device")
+    total = torch.zeros(1, dtype=torch.int64, device=device) if total is None else total
+    with torch.cuda.device(device):
+        _lib.check(
+            lib.hz_playout_keys(_ptr(keys) if keys is not None else None, n, seed, first_id, max_steps, _ptr(results),
+                                _ptr(total), torch.cuda.current_stream(device).cuda_stream),
+            "hz_playout_keys",
+        )
+    return results, total
+
+
 class HostPlayout:
     """Playouts on HOST buffers: ``run(states_in, states_out)`` takes pinned int32[n,32] host
     tensors, plays every game to the end on the GPU and returns the final records in
@@ -216,18 +244,89 @@ class HostPlayout:
             raise ValueError("host buffers must be pinned")
         if keys_in.shape != (self.n,) or keys_in.dtype != torch.int64 or results_out.shape != (self.n, 3):
             raise TypeError("keys int64[n], results int32[n, 3]")
-        lib = _lib.load()
+        self._key_buffers(1)
         main = torch.cuda.current_stream(self.device)
-        if not hasattr(self, "dev_keys"):
-            self.dev_keys = torch.empty(self.n, dtype=torch.int64, device=self.device)
-            self.cols = torch.tensor([22, 23, 27], device=self.device)
-        self.dev_keys.copy_(keys_in, non_blocking=True)
-        with torch.cuda.device(self.device):
-            _lib.check(lib.hz_init_states(_ptr(self.dev_states), self.n, _ptr(self.dev_keys), 0, 0, main.cuda_stream), "hz_init_states")
-        playout(self.dev_states, self.max_steps, steps=self.steps, total=self.total)
-        results_out.copy_(self.dev_states.index_select(1, self.cols), non_blocking=True)
+        self.dev_keys[0].copy_(keys_in, non_blocking=True)
+        playout_keys(self.dev_keys[0], self.dev_res[0], self.total, self.max_steps)
+        results_out.copy_(self.dev_res[0], non_blocking=True)
         main.synchronize()
         return results_out
+
+    def _key_buffers(self, depth):
+        have = len(getattr(self, "dev_keys", []))
+        if have < depth:
+            self.dev_keys = getattr(self, "dev_keys", []) + [
+                torch.empty(self.n, dtype=torch.int64, device=self.device) for _ in range(depth - have)]
+            self.dev_res = getattr(self, "dev_res", []) + [
+                torch.empty((self.n, 3), dtype=torch.int32, device=self.device) for _ in range(depth - have)]
+
+    def run_keys_many(self, keys_batches, results_batches, depth=3):
+        """A stream of ``run_keys`` batches, pipelined: while the kernel of batch k runs on the
+        calling stream, the keys of batch k+1 travel host->device on a copy stream and the results
+        of batch k-1 travel device->host on another (PCIe is full duplex), through ``depth``
+        device buffer pairs.  Every batch is copied in and read back; the call returns when the
+        last result is on the host.  ``results_batches[k]`` may alias an earlier entry once the
+        caller has consumed it (at least ``depth`` batches later)."""
+        self._check_batches(keys_batches, results_batches, (self.n,), torch.int64, (self.n, 3))
+        depth = max(1, min(int(depth), len(keys_batches)))
+        self._key_buffers(depth)
+        return self._pipeline(
+            keys_batches, results_batches, depth, self.dev_keys, self.dev_res,
+            lambda slot: playout_keys(self.dev_keys[slot], self.dev_res[slot], self.total, self.max_steps))
+
+    def run_many(self, states_batches, out_batches, depth=3):
+        """``run`` for a stream of batches of 128-byte records, pipelined like ``run_keys_many``
+        (in place on ``depth`` device staging buffers; PCIe-bound: 128 B each way per game)."""
+        self._check_batches(states_batches, out_batches, (self.n, 32), torch.int32, (self.n, 32))
+        depth = max(1, min(int(depth), len(states_batches)))
+        if len(getattr(self, "dev_many", [])) < depth:
+            self.dev_many = [self.dev_states] + [torch.empty_like(self.dev_states) for _ in range(depth - 1)]
+        return self._pipeline(
+            states_batches, out_batches, depth, self.dev_many, self.dev_many,
+            lambda slot: playout(self.dev_many[slot], self.max_steps, steps=self.steps, total=self.total))
+
+    def _check_batches(self, ins, outs, in_shape, in_dtype, out_shape):
+        if len(ins) != len(outs):
+            raise ValueError("one output buffer per input buffer")
+        for a, b in zip(ins, outs):
+            if not (a.is_pinned() and b.is_pinned()):
+                raise ValueError("host buffers must be pinned")
+            if a.shape != in_shape or a.dtype != in_dtype or b.shape != out_shape or b.dtype != torch.int32:
+                raise TypeError(f"inputs {in_dtype}{list(in_shape)}, outputs int32{list(out_shape)}")
+
+    def _pipeline(self, ins, outs, depth, dev_in, dev_out, launch):
+        if not hasattr(self, "copy_in"):
+            self.copy_in, self.copy_out = torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        self.copy_in.wait_stream(main)
+        self.copy_out.wait_stream(main)
+        computed = [None] * depth      # event: the kernel that used slot's device buffers finished
+        drained = [None] * depth       # event: slot's output buffer has been copied to the host
+        for k, (a, b) in enumerate(zip(ins, outs)):
+            slot = k % depth
+            with torch.cuda.stream(self.copy_in):
+                if computed[slot] is not None:
+                    self.copy_in.wait_event(computed[slot])
+                if dev_in is dev_out and drained[slot] is not None:
+                    self.copy_in.wait_event(drained[slot])      # in-place buffers: wait for the read-back too
+                dev_in[slot].copy_(a, non_blocking=True)
+                arrived = torch.cuda.Event()
+                arrived.record(self.copy_in)
+            main.wait_event(arrived)
+            if drained[slot] is not None:
+                main.wait_event(drained[slot])
+            launch(slot)
+            computed[slot] = torch.cuda.Event()
+            computed[slot].record(main)
+            with torch.cuda.stream(self.copy_out):
+                self.copy_out.wait_event(computed[slot])
+                b.copy_(dev_out[slot], non_blocking=True)
+                drained[slot] = torch.cuda.Event()
+                drained[slot].record(self.copy_out)
+        main.wait_stream(self.copy_out)
+        main.wait_stream(self.copy_in)
+        main.synchronize()
+        return outs
 
 
 def launch_count():

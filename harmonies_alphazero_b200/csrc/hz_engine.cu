@@ -177,8 +177,12 @@ __global__ void __launch_bounds__(GWPB * 32) k_greedy(const void* states, int64_
 // the state per game.  Threads of a warp run different games and diverge only on the phase
 // (choose / place / end of turn); scoring runs once per game.
 constexpr int PTPB = 64;   // 65,536 games -> 1024 blocks: 6.9 per SM, <2 % tail imbalance over 148 SMs
+// FROM_KEYS: the game is created in registers from its 64-bit key (k_init fused in) and only
+// (meta word, score word, actions played) leave the chip: 8 B in, 12 B out per game.
+template <bool FROM_KEYS>
 __global__ void __launch_bounds__(PTPB) k_playout(void* states, int64_t n, int max_steps, uint32_t* steps,
-                                                  unsigned long long* total_steps) {
+                                                  unsigned long long* total_steps, const uint64_t* keys,
+                                                  uint64_t seed, uint64_t first_id, uint32_t* results) {
     __shared__ NbrLut lut;
     __shared__ uint64_t rtab[RTAB_N];
     build_nbr_lut(&lut);
@@ -188,7 +192,8 @@ __global__ void __launch_bounds__(PTPB) k_playout(void* states, int64_t n, int m
     uint32_t k = 0;
     if (g < n) {
         State s;
-        load_state(s, states, g);
+        if (FROM_KEYS) init_state(s, keys ? keys[g] : rand64(seed, first_id + (uint64_t)g));
+        else load_state(s, states, g);
         if (player_of(s)) swap_boards(s);   // mover-relative board order inside the loop (see REL)
         while ((int)k < max_steps && phase_of(s) != HZ_PHASE_OVER) {
             int a = random_action(s, legal_of<true>(s), rtab);
@@ -199,8 +204,14 @@ __global__ void __launch_bounds__(PTPB) k_playout(void* states, int64_t n, int m
         if (player_of(s)) swap_boards(s);   // back to absolute order
         // final scoring deferred to here: the lanes of the warp are converged again
         if (phase_of(s) == HZ_PHASE_OVER && winner_code(s) == 0) finalize_scores(s, &lut);
-        store_state(s, states, g);
-        if (steps) steps[g] = k;
+        if (FROM_KEYS) {
+            results[g * 3] = s.w[HZ_W_BAG1META];
+            results[g * 3 + 1] = s.w[HZ_W_SCORES];
+            results[g * 3 + 2] = s.w[HZ_W_MOVES];
+        } else {
+            store_state(s, states, g);
+            if (steps) steps[g] = k;
+        }
     }
     if (total_steps) {
         uint32_t sum = k;
@@ -605,7 +616,17 @@ int hz_playout(void* states, int64_t n, int max_steps, uint32_t* steps, unsigned
     if (n == 0) return HZ_OK;   // empty batch: nothing to do, pointers may be null
     if (!states || n < 0 || max_steps < 0) return HZ_ERR_ARG;
     if (n == 0) return HZ_OK;
-    k_playout<<<blocks_for(n, PTPB), PTPB, 0, (cudaStream_t)stream>>>(states, n, max_steps, steps, total_steps);
+    k_playout<false><<<blocks_for(n, PTPB), PTPB, 0, (cudaStream_t)stream>>>(states, n, max_steps, steps, total_steps,
+                                                                             nullptr, 0, 0, nullptr);
+    return hz_launched(1);
+}
+
+int hz_playout_keys(const uint64_t* keys, int64_t n, uint64_t seed, uint64_t first_id, int max_steps,
+                    uint32_t* results, unsigned long long* total_steps, void* stream) {
+    if (n == 0) return HZ_OK;   // empty batch: nothing to do, pointers may be null
+    if (!results || n < 0 || max_steps < 0) return HZ_ERR_ARG;
+    k_playout<true><<<blocks_for(n, PTPB), PTPB, 0, (cudaStream_t)stream>>>(nullptr, n, max_steps, nullptr, total_steps,
+                                                                            keys, seed, first_id, results);
     return hz_launched(1);
 }
 

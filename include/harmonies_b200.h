@@ -69,7 +69,7 @@
 extern "C" {
 #endif
 
-#define HZ_ABI_VERSION      2
+#define HZ_ABI_VERSION      3
 #define HZ_STATE_WORDS      32
 #define HZ_STATE_BYTES      128
 #define HZ_NUM_HEXES        23
@@ -201,6 +201,16 @@ int hz_greedy_actions(const void *states, int64_t n, int16_t *actions, void *str
  * total_steps (nullable): device uint64 to which the launch adds its step total. */
 int hz_playout(void *states, int64_t n, int max_steps, uint32_t *steps,
                unsigned long long *total_steps, void *stream);
+
+/* hz_init_states + hz_playout + result extraction in one launch, for callers that only want
+ * the outcome of fresh games (the reference's `HarmoniesGameState()` followed by a random
+ * playout loop, evaluation.py / tests): games are created on-chip from keys[i] (or from
+ * rand(seed, first_id + i) when keys is NULL), played to the end, and only
+ * results[i*3 + {0,1,2}] = {word HZ_W_BAG1META (phase, winner code), word HZ_W_SCORES,
+ * word HZ_W_MOVES (actions played)} is written: 8 bytes in, 12 bytes out per game. */
+int hz_playout_keys(const uint64_t *keys, int64_t n, uint64_t seed, uint64_t first_id,
+                    int max_steps, uint32_t *results, unsigned long long *total_steps,
+                    void *stream);
 
 /* ---- search tree (MCTS.py) ---------------------------------------------------------- */
 

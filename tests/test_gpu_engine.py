@@ -255,6 +255,34 @@ def test_host_buffer_api_equals_device_path(hb):
     hb.playout(ref)
     w = host(ref)
     assert np.array_equal(res[:, 0], w[:, 22]) and np.array_equal(res[:, 1], w[:, 23]) and np.array_equal(res[:, 2], w[:, 27])
+    # keys derived on the device from (seed, first_id): same games as hz_init_states(seed)
+    r2, t2 = hb.playout_keys(None, n=n, seed=321, first_id=0, device="cuda", max_steps=1000)
+    w2 = host(st)
+    assert np.array_equal(r2.cpu().numpy().view(np.uint32), w2[:, [22, 23, 27]]) and int(t2.item()) == int(total.item())
+    # the pipelined stream of batches returns what the one-batch call returns, batch by batch
+    batches = [torch.from_numpy(rng.integers(-2**63, 2**63 - 1, size=n, dtype=np.int64)).pin_memory() for _ in range(7)]
+    outs = [torch.empty((n, 3), dtype=torch.int32).pin_memory() for _ in range(7)]
+    before = int(api.total.item())
+    api.run_keys_many(batches, outs, depth=3)
+    many_steps = int(api.total.item()) - before
+    one = torch.empty((n, 3), dtype=torch.int32).pin_memory()
+    acc = 0
+    for kb, ob in zip(batches, outs):
+        api.run_keys(kb, one)
+        assert torch.equal(one, ob)
+        acc += int(one[:, 2].sum())
+    assert acc == many_steps
+    with pytest.raises(ValueError):
+        api.run_keys_many(batches, outs[:3])
+    # full-record stream
+    recs = [hb.init_states(n, seed=500 + k).cpu().pin_memory() for k in range(5)]
+    routs = [torch.empty((n, 32), dtype=torch.int32).pin_memory() for _ in range(5)]
+    api.run_many(recs, routs, depth=2)
+    for k in (0, 3, 4):
+        ref = hb.init_states(n, seed=500 + k)
+        hb.playout(ref)
+        assert torch.equal(routs[k], ref.cpu())
+    assert hb.playout_keys(torch.empty(0, dtype=torch.int64, device="cuda"))[0].shape == (0, 3)
 
 
 def test_score_encode_hash_vs_oracle_on_random_positions(hb, oracle):
