@@ -14,6 +14,7 @@
 // the 1x1 convs, then thread = output unit for the FC layers with the 7 positions held as 7
 // accumulators, so each weight is read once per 7 positions (weights stay in L1/L2).
 #include <math.h>
+#include <stdlib.h>
 
 #include "hz_common.cuh"
 
@@ -184,6 +185,194 @@ __global__ void __launch_bounds__(HTPB) k_heads(const __nv_bfloat16* __restrict_
     }
 }
 
+// ---- the default network's shape (C = 128, H = 256): persistent variant ----------------------
+// One 512-thread block per SM keeps BOTH FC weight matrices in shared memory (143 KB fp32, read
+// from L2 once per block instead of once per 7 positions) and walks groups of 14 positions:
+//   phase 1  the 1x1 convs as [cells x 128] x [128 x 3] on the tensor cores: a warp takes 16 board
+//            cells per mma.sync m16n8k16 tile; A fragments are the bf16 activations loaded straight
+//            from global memory with 16-byte requests (the K order is permuted so that a lane's
+//            uint4 IS its fragment), B = the conv weights split into bf16 hi + lo parts held in
+//            registers (two MMAs per k-step: fp32-weight accuracy, 2^-17 relative)
+//   phase 2  thread = 2 output units x 7 positions (14 accumulators): per 4 inputs 8 weight
+//            words + 7 broadcast LDS.128 feed 56 FMAs
+constexpr int FG = 14;
+constexpr int FTPB = 512;
+constexpr int FC = 128, FH = 256;
+constexpr int WPN = PIN * NPOL + 16;     // policy weights, flat copy of w_pol_t (+ slack: unit "143" reads are discarded)
+constexpr size_t FSMEM = sizeof(float) * (size_t)(WPN + 77 * FH + FG * PIN + FG * 80 + FG * 4);
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_16816(float c[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 lo, __nv_bfloat16 hi) {
+    return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+}
+
+__global__ void __launch_bounds__(FTPB, 1) k_heads_p(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ glob,
+                                                     int64_t n, HeadParams P, float* __restrict__ logits,
+                                                     float* __restrict__ value) {
+    extern __shared__ __align__(16) float smem[];
+    float* s_wp = smem;                      // [112][143] (+ slack)
+    float* s_wv = s_wp + WPN;                // [77][256]
+    float* s_pin = s_wv + 77 * FH;           // [FG][112]
+    float* s_vin = s_pin + FG * PIN;         // [FG][80]
+    float* s_red = s_vin + FG * 80;          // [FG][4]
+    const int t = threadIdx.x, warp = t >> 5, g8 = (t & 31) >> 2, q4 = t & 3;
+    // FC weights -> shared memory, asynchronously: phase 1 of the first group does not need them
+    for (int i = t; i < PIN * NPOL / 4; i += FTPB) cp_async16(s_wp + 4 * i, P.w_pol_t + 4 * i);
+    for (int i = t; i < 77 * FH / 4; i += FTPB) cp_async16(s_wv + 4 * i, P.w_v1_t + 4 * i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (t < 16) s_wp[PIN * NPOL + t] = 0.0f;
+    // B fragments of the conv weights: output n = g8 (0,1 policy, 2 value, others zero); the lane's
+    // k rows of k-step ks = (kk, s) are channels 32 kk + 8 q4 + 4 s + {0,1} and + {2,3}
+    uint32_t bh[16], bl[16];
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {
+#pragma unroll
+        for (int w = 0; w < 2; w++) {
+            int ch = 32 * (ks >> 1) + 8 * q4 + 4 * (ks & 1) + 2 * w;
+            float w0 = g8 < 3 ? P.w_conv[g8 * FC + ch] : 0.0f, w1 = g8 < 3 ? P.w_conv[g8 * FC + ch + 1] : 0.0f;
+            __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
+            bh[ks * 2 + w] = pack_bf16(h0, h1);
+            bl[ks * 2 + w] = pack_bf16(__float2bfloat16_rn(w0 - __bfloat162float(h0)), __float2bfloat16_rn(w1 - __bfloat162float(h1)));
+        }
+    }
+    const float bc0 = P.b_conv[0], bc1 = P.b_conv[1], bc2 = P.b_conv[2];
+    int64_t n_groups = (n + FG - 1) / FG;
+    bool weights_pending = true;
+    for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        int64_t base = grp * FG;
+        int cnt = (int)min((int64_t)FG, n - base), ncell = cnt * CELLS;
+        __syncthreads();
+        // ---- phase 1: 1x1 convs + ReLU (model.py:340-343,349-351)
+        const uint4* rows = reinterpret_cast<const uint4*>(x + base * CELLS * (int64_t)FC);
+        for (int tile = warp; tile * 16 < ncell; tile += FTPB / 32) {
+            int r0 = tile * 16 + g8, r1 = r0 + 8;
+            uint4 qa[4], qb[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                qa[kk] = r0 < ncell ? rows[r0 * (FC / 8) + kk * 4 + q4] : make_uint4(0, 0, 0, 0);
+                qb[kk] = r1 < ncell ? rows[r1 * (FC / 8) + kk * 4 + q4] : make_uint4(0, 0, 0, 0);
+            }
+            float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                mma_bf16_16816(c, qa[kk].x, qb[kk].x, qa[kk].y, qb[kk].y, bh[kk * 4], bh[kk * 4 + 1]);
+                mma_bf16_16816(c, qa[kk].x, qb[kk].x, qa[kk].y, qb[kk].y, bl[kk * 4], bl[kk * 4 + 1]);
+                mma_bf16_16816(c, qa[kk].z, qb[kk].z, qa[kk].w, qb[kk].w, bh[kk * 4 + 2], bh[kk * 4 + 3]);
+                mma_bf16_16816(c, qa[kk].z, qb[kk].z, qa[kk].w, qb[kk].w, bl[kk * 4 + 2], bl[kk * 4 + 3]);
+            }
+            // c[0], c[1] = row r0, outputs 2 q4, 2 q4 + 1;  c[2], c[3] = row r1
+            if (q4 < 2) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    int r = h ? r1 : r0;
+                    if (r < ncell) {
+                        int p = r / CELLS, cell = r - CELLS * p;
+                        if (q4 == 0) {
+                            s_pin[p * PIN + cell] = fmaxf(c[2 * h] + bc0, 0.0f);          // channel-major flatten (model.py:343)
+                            s_pin[p * PIN + CELLS + cell] = fmaxf(c[2 * h + 1] + bc1, 0.0f);
+                        } else {
+                            s_vin[p * 80 + cell] = fmaxf(c[2 * h] + bc2, 0.0f);
+                        }
+                    }
+                }
+            }
+        }
+        for (int i = t; i < cnt * NGLOB; i += FTPB) {   // ++ global features (:344-346,352)
+            int p = i / NGLOB, g = i - NGLOB * p;
+            float gv = __bfloat162float(glob[(base + p) * NGLOB + g]);
+            s_pin[p * PIN + 2 * CELLS + g] = gv;
+            s_vin[p * 80 + CELLS + g] = gv;
+        }
+        if (weights_pending) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            weights_pending = false;
+        }
+        __syncthreads();
+        // ---- phase 2: warps 0-5 policy FC (two halves of 7 positions), warps 6-13 value FCs
+        if (t < 192) {
+            int half = t / 96, u0 = t - 96 * half;
+            if (u0 < 72) {
+                int u1 = u0 + 72, p0 = half * 7;            // u1 == 143 (thread 71) reads a neighbour's weights; never stored
+                float acc0[7], acc1[7];
+                float b0 = P.b_pol[u0], b1 = u1 < NPOL ? P.b_pol[u1] : 0.0f;
+#pragma unroll
+                for (int p = 0; p < 7; p++) { acc0[p] = b0; acc1[p] = b1; }
+#pragma unroll 2
+                for (int j = 0; j < PIN; j += 4) {
+                    float wa[4], wb[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { wa[k] = s_wp[(j + k) * NPOL + u0]; wb[k] = s_wp[(j + k) * NPOL + u1]; }
+#pragma unroll
+                    for (int p = 0; p < 7; p++) {
+                        float4 in = *reinterpret_cast<const float4*>(s_pin + (p0 + p) * PIN + j);
+                        acc0[p] = fmaf(wa[0], in.x, acc0[p]); acc0[p] = fmaf(wa[1], in.y, acc0[p]);
+                        acc0[p] = fmaf(wa[2], in.z, acc0[p]); acc0[p] = fmaf(wa[3], in.w, acc0[p]);
+                        acc1[p] = fmaf(wb[0], in.x, acc1[p]); acc1[p] = fmaf(wb[1], in.y, acc1[p]);
+                        acc1[p] = fmaf(wb[2], in.z, acc1[p]); acc1[p] = fmaf(wb[3], in.w, acc1[p]);
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < 7; p++) {
+                    if (p0 + p < cnt) {
+                        logits[(base + p0 + p) * NPOL + u0] = acc0[p];
+                        if (u1 < NPOL) logits[(base + p0 + p) * NPOL + u1] = acc1[p];
+                    }
+                }
+            }
+        } else if (t < 448) {
+            int v = t - 192, half = v >> 7, u0 = v & 127, u1 = u0 + 128, p0 = half * 7;
+            float acc0[7], acc1[7];
+            float b0 = P.b_v1[u0], b1 = P.b_v1[u1];
+#pragma unroll
+            for (int p = 0; p < 7; p++) { acc0[p] = b0; acc1[p] = b1; }
+#pragma unroll 2
+            for (int j = 0; j < 76; j += 4) {
+                float wa[4], wb[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { wa[k] = s_wv[(j + k) * FH + u0]; wb[k] = s_wv[(j + k) * FH + u1]; }
+#pragma unroll
+                for (int p = 0; p < 7; p++) {
+                    float4 in = *reinterpret_cast<const float4*>(s_vin + (p0 + p) * 80 + j);
+                    acc0[p] = fmaf(wa[0], in.x, acc0[p]); acc0[p] = fmaf(wa[1], in.y, acc0[p]);
+                    acc0[p] = fmaf(wa[2], in.z, acc0[p]); acc0[p] = fmaf(wa[3], in.w, acc0[p]);
+                    acc1[p] = fmaf(wb[0], in.x, acc1[p]); acc1[p] = fmaf(wb[1], in.y, acc1[p]);
+                    acc1[p] = fmaf(wb[2], in.z, acc1[p]); acc1[p] = fmaf(wb[3], in.w, acc1[p]);
+                }
+            }
+            {   // j = 76 (VIN = 77)
+                float wa = s_wv[76 * FH + u0], wb = s_wv[76 * FH + u1];
+#pragma unroll
+                for (int p = 0; p < 7; p++) {
+                    float in = s_vin[(p0 + p) * 80 + 76];
+                    acc0[p] = fmaf(wa, in, acc0[p]); acc1[p] = fmaf(wb, in, acc1[p]);
+                }
+            }
+            float w2a = P.w_v2[u0], w2b = P.w_v2[u1];
+#pragma unroll
+            for (int p = 0; p < 7; p++) {
+                float part = fmaf(fmaxf(acc1[p], 0.0f), w2b, fmaxf(acc0[p], 0.0f) * w2a);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+                if ((t & 31) == 0) s_red[(p0 + p) * 4 + (u0 >> 5)] = part;
+            }
+        }
+        __syncthreads();
+        if (t < cnt) {
+            float sum = P.b_v2 + s_red[t * 4] + s_red[t * 4 + 1] + s_red[t * 4 + 2] + s_red[t * 4 + 3];
+            value[base + t] = tanhf(sum);                           // model.py:355
+        }
+    }
+}
+
 }  // namespace hz
 
 extern "C" int hz_net_heads(const void* x, const void* glob, int64_t n, int C, int H, const float* w_conv,
@@ -195,6 +384,22 @@ extern "C" int hz_net_heads(const void* x, const void* glob, int64_t n, int C, i
         return HZ_ERR_ARG;
     if (n < 0 || C <= 0 || (C % 8) != 0 || H <= 0 || (H % 2) != 0 || ((uintptr_t)x & 15)) return HZ_ERR_ARG;
     hz::HeadParams P{w_conv, b_conv, w_pol_t, b_pol, w_v1_t, b_v1, w_v2, b_v2, C, H};
+    static const bool force_generic = getenv("HZ_HEADS_GENERIC") != nullptr;   // A/B switch for profiling
+    if (!force_generic && C == hz::FC && H == hz::FH && (((uintptr_t)w_v1_t | (uintptr_t)w_pol_t) & 15) == 0) {
+        static bool attr_set[64] = {};   // the opt-in shared-memory size is per function and per device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(hz::k_heads_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hz::FSMEM);
+            if (e != cudaSuccess) return hz_record_launch(0, e);
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
+        int64_t fgroups = (n + hz::FG - 1) / hz::FG;
+        int fgrid = (int)(fgroups < 148 ? fgroups : 148);
+        hz::k_heads_p<<<fgrid, hz::FTPB, hz::FSMEM, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)glob,
+                                                                            n, P, logits, value);
+        return hz_launched(1);
+    }
     size_t smem = sizeof(float) * (size_t)(3 * C + hz::HP * hz::PIN + hz::HP * 80 + hz::HP * 8);
     int64_t groups = (n + hz::HP - 1) / hz::HP;
     int grid = (int)(groups < 148 * 4 ? groups : 148 * 4);

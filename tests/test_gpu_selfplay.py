@@ -63,7 +63,7 @@ def test_fused_heads_kernel_matches_torch_heads(mods, cfg_name):
     inf = net.InferenceNet(m, device="cuda", dtype=torch.bfloat16)
     assert inf.heads is not None
     C = inf.heads["C"]
-    for B in (1, 6, 7, 8, 300):
+    for B in (1, 6, 7, 8, 13, 14, 15, 300, 2077):
         x = (torch.randn((B, C, 5, 7), device="cuda") * 0.7).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         glob = torch.rand((B, 42), device="cuda").to(torch.bfloat16)
         logits, value = inf._fused_heads(x, glob, None)
