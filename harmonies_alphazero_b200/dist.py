@@ -32,20 +32,32 @@ def _flat_tensors(model):
 def broadcast_weights(model, src=0, group=None, dtype=None):
     """Broadcast every parameter and floating-point buffer of ``model`` from ``src`` in one
     flat message.  ``dtype`` (e.g. torch.bfloat16) halves the bytes when the receivers only
-    run bf16 inference.  Returns the number of bytes sent per rank."""
+    run bf16 inference.  Returns the number of bytes sent per rank.
+
+    The flat wire buffer and its per-tensor views are built once per (model, dtype) and reused:
+    a call is one fused pack (``torch._foreach_copy_``), one collective and one fused unpack,
+    not two small kernels per tensor."""
     tensors = _flat_tensors(model)
     if not tensors:
         return 0
     dev = tensors[0].device
     wire = dtype or torch.float32
-    flat = torch.cat([t.reshape(-1).to(wire) for t in tensors]).to(dev)
+    cache = model.__dict__.setdefault("_hz_wire_cache", {})
+    key = (wire, dev, tuple(t.numel() for t in tensors))
+    if key not in cache:
+        flat = torch.empty(sum(t.numel() for t in tensors), dtype=wire, device=dev)
+        views, off = [], 0
+        for t in tensors:
+            views.append(flat[off:off + t.numel()].view_as(t))
+            off += t.numel()
+        cache.clear()
+        cache[key] = (flat, views)
+    flat, views = cache[key]
+    if dist.get_rank(group) == src:
+        torch._foreach_copy_(views, tensors)
     dist.broadcast(flat, src=src, group=group)
     if dist.get_rank(group) != src:
-        off = 0
-        for t in tensors:
-            n = t.numel()
-            t.copy_(flat[off:off + n].view_as(t).to(t.dtype))
-            off += n
+        torch._foreach_copy_(tensors, views)
     return flat.numel() * flat.element_size()
 
 
