@@ -10,6 +10,7 @@ import pytest
 import torch
 
 from tests.conftest import load_golden
+from harmonies_alphazero_b200 import constants as K
 from harmonies_alphazero_b200 import packed as pk
 
 pytestmark = pytest.mark.gpu
@@ -373,6 +374,70 @@ def test_one_million_synthetic_positions(hb, oracle):
     sc2 = hb.score(dev(swapped)).cpu().numpy()
     assert np.array_equal(sc2, sc[:, ::-1])
     assert sc.max() < 200 and sc.min() >= 0
+
+
+def test_scoring_component_stress(hb, oracle):
+    """The loop-free scoring paths against the oracle's plain BFS on boards built to hit them:
+    water- and field-heavy tops (components of every size, field rings with enclosed holes), a
+    block of identical boards with several large water components (more queued components than
+    the per-block water queue holds -> in-lane fallback), and height-1 boards of a single type."""
+    rng = np.random.default_rng(77)
+    n = 60_000
+    shifts = np.arange(23, dtype=np.uint32)
+    words = np.zeros((n, 32), dtype=np.uint32)
+    # tile codes: water 1, plant 2, wood 3, stone 4, building 5, field 6
+    mixes = [np.array([.70, .06, .06, .06, .06, .06]), np.array([.06, .06, .06, .06, .06, .70]),
+             np.array([.45, .02, .02, .03, .03, .45]), np.array([.88, .02, .02, .03, .03, .02]),
+             np.array([.02, .02, .02, .03, .03, .88])]
+    for p in range(2):
+        mix = rng.integers(0, len(mixes), n)
+        top = np.zeros((n, 23), dtype=np.uint32)
+        for m, pr in enumerate(mixes):
+            sel = mix == m
+            top[sel] = rng.choice(np.arange(1, 7, dtype=np.uint32), size=(int(sel.sum()), 23), p=pr / pr.sum())
+        h = rng.choice(np.array([0, 1, 1, 1, 2, 3], dtype=np.uint8), size=(n, 23))     # some empty hexes too
+        for lvl in range(3):
+            below = rng.integers(1, 7, size=(n, 23), dtype=np.uint32)
+            code = np.where(h == lvl + 1, top, np.where(h > lvl + 1, below, 0)).astype(np.uint32)
+            for b in range(3):
+                words[:, p * 9 + lvl * 3 + b] = (((code >> b) & 1) << shifts).sum(axis=1, dtype=np.uint32)
+    # rows 20,000..24,095: one board with as many >= 5-hex water components as a search finds, repeated
+    best, best_cnt = 0, -1
+    for _ in range(4000):
+        m = int(rng.integers(0, 1 << 23))
+        rem, cnt = m, 0
+        while rem:
+            f = rem & -rem
+            while True:
+                nf = f
+                for i in range(23):
+                    if (f >> i) & 1:
+                        nf |= K.NEIGHBOR_MASKS[i]
+                nf &= m
+                if nf == f:
+                    break
+                f = nf
+            rem &= ~f
+            cnt += bin(f).count("1") >= 5
+        if cnt > best_cnt:
+            best, best_cnt = m, cnt
+    assert best_cnt >= 2
+    words[20_000:24_096, 0:18] = 0
+    words[20_000:24_096, 0] = best          # height-1 water (code 1) on the chosen hexes, both players
+    words[20_000:24_096, 9] = best
+    # rows 30,000..30,005: single-type full boards
+    for k in range(6):
+        words[30_000 + k, 0:18] = 0
+        for b in range(3):
+            if ((k + 1) >> b) & 1:
+                words[30_000 + k, b] = words[30_000 + k, 9 + b] = 0x7FFFFF
+    words[:, 21] = 0x05050505
+    words[:, 22] = 0x0505 | (1 << 25)
+    sc, tm = hb.score(dev(words), with_terms=True)
+    osc, otm = oracle.score(words)
+    assert np.array_equal(tm.cpu().numpy(), otm)
+    assert np.array_equal(sc.cpu().numpy(), osc)
+    assert otm[:, :, 2].max() >= 10 and otm[:, :, 4].max() >= 15      # several field components / long rivers occur
 
 
 def test_edge_cases(hb, oracle):
