@@ -194,7 +194,7 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------
-def mcts_measure(args, dev, world, rank, dist):
+def mcts_measure(args, dev, world, rank, dist, with_collectives=True):
     """configs[3]: MCTS self-play with the model.py net (random-init, bf16), 100 sims/move,
     4,096 concurrent games per GPU.  One step = one move of every game = 4,096 x 100
     simulations (select -> network forward -> expand+backup, CUDA-graph replayed)."""
@@ -245,7 +245,7 @@ def mcts_measure(args, dev, world, rank, dist):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     collectives = None
-    if dist is not None:
+    if dist is not None and with_collectives:
         # configs[4]: NCCL weight broadcast + packed trajectory gather, once per training step
         from harmonies_alphazero_b200 import dist as hzdist
 
@@ -557,6 +557,16 @@ def run_b200(args):
     if not args.no_mcts:
         # second half of BASELINE.json's metric: MCTS sims/s (configs[3]), reported alongside
         out["mcts"] = mcts_measure(args, dev, world, rank, dist if world > 1 else None)
+        if args.mcts_leaves == 1:
+            # the same leg with 4 simulations in flight per tree (virtual loss, north_star's tree mode;
+            # not visit-for-visit identical to the reference's sequential search, hence reported aside)
+            import copy
+
+            vl_args = copy.copy(args)
+            vl_args.mcts_leaves = 4
+            vl = mcts_measure(vl_args, dev, world, rank, dist if world > 1 else None, with_collectives=False)
+            out["mcts"]["virtual_loss"] = {"leaves_per_step": 4, "value": vl["value"], "unit": vl["unit"],
+                                           "ms_per_move": vl["ms_per_move"], "roofline_frac": vl["roofline"]["frac"]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
         if "mcts" in out:
