@@ -31,7 +31,9 @@ struct hz_tree {
     float* edge_P;
     uint16_t* edge_am;      // action | mover << 8
     int32_t* edge_V;        // in-flight (virtual-loss) visits, non-zero only between select and backup
-    uint32_t* table;        // [n_trees * table_size]
+    uint32_t* edge_cinfo;   // cached (first edge | edge count << 24) of the child once it is known to be expanded, else 0
+    uint32_t* table;        // [n_trees * table_size]  node index + 1, 0 = empty
+    uint64_t* table_hash;   // [n_trees * table_size]  key of that node (valid where table != 0): a probe is ONE round trip
     uint32_t* path;         // [n_trees * leaves * (max_sims + 1)]
     int32_t* depth;         // [n_trees * leaves]
     int32_t* leaf;          // [n_trees * leaves]
@@ -52,7 +54,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 struct TreeView {                 // device copy of the handle with per-tree offsets applied
     uint4* node_state; uint64_t* node_hash; uint32_t* node_edge0; uint32_t* node_info;
     uint32_t* edge_child; int32_t* edge_N; double* edge_W; float* edge_P; uint16_t* edge_am; int32_t* edge_V;
-    uint32_t* table; uint32_t* path;   // path: [leaves][max_sims + 1]
+    uint32_t* edge_cinfo; uint32_t* table; uint64_t* table_hash; uint32_t* path;   // path: [leaves][max_sims + 1]
 };
 __device__ __forceinline__ TreeView view_of(const hz_tree& T, int t) {
     TreeView v;
@@ -61,7 +63,9 @@ __device__ __forceinline__ TreeView view_of(const hz_tree& T, int t) {
     v.node_edge0 = T.node_edge0 + nb; v.node_info = T.node_info + nb;
     v.edge_child = T.edge_child + eb; v.edge_N = T.edge_N + eb; v.edge_W = T.edge_W + eb;
     v.edge_P = T.edge_P + eb; v.edge_am = T.edge_am + eb; v.edge_V = T.edge_V + eb;
+    v.edge_cinfo = T.edge_cinfo + eb;
     v.table = T.table + (size_t)t * T.table_size;
+    v.table_hash = T.table_hash + (size_t)t * T.table_size;
     v.path = T.path + (size_t)t * T.leaves * (T.max_sims + 1);
     return v;
 }
@@ -89,6 +93,7 @@ __global__ void __launch_bounds__(TTPB) k_tree_reset(hz_tree T, const uint4* roo
     v.node_edge0[0] = 0;
     v.node_info[0] = (uint32_t)player_of(s) << 8;
     v.table[h & (uint64_t)(T.table_size - 1)] = 1;
+    v.table_hash[h & (uint64_t)(T.table_size - 1)] = h;
     for (int j = 0; j < T.leaves; j++) { T.depth[t * T.leaves + j] = 0; T.leaf[t * T.leaves + j] = 0; }
     T.sim[t] = 0; T.n_nodes[t] = 1; T.n_edges[t] = 0; T.status[t] = 0;
     // default key: a stream of its own per (game, move), independent of the game's draw stream
@@ -184,20 +189,23 @@ __global__ void __launch_bounds__(TTPB) k_tree_select(hz_tree T, float cpuct, ui
     for (int j = 0; j < K; j++) {
         uint32_t* path = v.path + (size_t)j * (T.max_sims + 1);
         int node = 0, depth = 0;
-        while (true) {
-            uint32_t info = v.node_info[node];
-            int ne = (int)(info & 0xFFu);
-            if (ne == 0) break;                                          // is_leaf, MCTS.py:18-20,76
-            uint32_t e0 = v.node_edge0[node];
-            int N[3]; double W[3]; float P[3];
+        // (first edge, edge count) of the current node: from the node arrays for the root, afterwards
+        // from the winning edge's cached copy, so that a level costs one memory round trip
+        uint32_t e0 = v.node_edge0[0];
+        int ne = (int)(v.node_info[0] & 0xFFu);
+        while (ne != 0) {                                                // is_leaf, MCTS.py:18-20,76
+            int N[3]; double W[3]; float P[3]; uint32_t C[3], CI[3];
             int ns = 0;
 #pragma unroll
             for (int r = 0; r < 3; r++) {
                 int k = lane + 32 * r;
                 bool on = k < ne;
+                if (32 * r >= ne) { N[r] = 0; W[r] = 0.0; P[r] = 0.0f; C[r] = 0u; CI[r] = 0u; continue; }   // warp-uniform
                 N[r] = on ? v.edge_N[e0 + k] : 0;
                 W[r] = on ? v.edge_W[e0 + k] : 0.0;
                 P[r] = on ? v.edge_P[e0 + k] : 0.0f;
+                C[r] = on ? v.edge_child[e0 + k] : 0u;
+                CI[r] = on ? v.edge_cinfo[e0 + k] : 0u;
                 if (K > 1 && on) {
                     int vl = v.edge_V[e0 + k];
                     N[r] += vl;
@@ -213,6 +221,7 @@ __global__ void __launch_bounds__(TTPB) k_tree_select(hz_tree T, float cpuct, ui
 #pragma unroll
             for (int r = 0; r < 3; r++) {
                 int k = lane + 32 * r;
+                if (32 * r >= ne) break;                                 // warp-uniform: most nodes have <= 32 edges
                 if (k < ne) {
                     float cp = cpuct * P[r];                             // np.float32 product, :107-109
                     double u = (double)cp * sqrt_ns / (double)(1 + N[r]);                      // :110-111
@@ -236,7 +245,20 @@ __global__ void __launch_bounds__(TTPB) k_tree_select(hz_tree T, float cpuct, ui
                 if (K > 1) v.edge_V[e] += 1;
             }
             depth++;
-            node = (int)v.edge_child[e];                                 // :145-146
+            int br = best_k >> 5;                                        // warp-uniform
+            uint32_t wc = br == 0 ? C[0] : br == 1 ? C[1] : C[2], wi = br == 0 ? CI[0] : br == 1 ? CI[1] : CI[2];
+            node = (int)__shfl_sync(FULL, wc, best_k & 31);              // :145-146
+            uint32_t ci = __shfl_sync(FULL, wi, best_k & 31);
+            if (ci == 0) {                                               // not known to be expanded: ask the node
+                ne = (int)(v.node_info[node] & 0xFFu);
+                if (ne != 0) {
+                    e0 = v.node_edge0[node];
+                    if (lane == 0) v.edge_cinfo[e] = e0 | ((uint32_t)ne << 24);
+                }
+            } else {
+                e0 = ci & 0xFFFFFFu;
+                ne = (int)(ci >> 24);
+            }
         }
         if (lane == 0) { T.leaf[t * K + j] = node; T.depth[t * K + j] = depth; }
         size_t row = (size_t)t * K + j;
@@ -266,9 +288,10 @@ __device__ __forceinline__ int table_find(const hz_tree& T, const TreeView& v, u
     uint32_t slot = (uint32_t)h & mask;
     while (true) {
         uint32_t e = v.table[slot];
+        uint64_t eh = v.table_hash[slot];     // independent of e: both loads are in flight together
         if (e == 0) return -1;
         int idx = (int)e - 1;
-        if (v.node_hash[idx] == h) {
+        if (eh == h) {
             if (!HZ_TREE_FULL_COMPARE) return idx;
             State o;
             load_state(o, v.node_state, idx);
@@ -286,10 +309,14 @@ __device__ __forceinline__ void table_insert(const hz_tree& T, const TreeView& v
     uint32_t mask = (uint32_t)T.table_size - 1u;
     uint32_t slot = (uint32_t)h & mask;
     while (atomicCAS(&v.table[slot], 0u, (uint32_t)idx + 1u) != 0u) slot = (slot + 1) & mask;
+    v.table_hash[slot] = h;     // read by later rounds only (after the __syncwarp that ends this one)
 }
 
 // ---- expand_leaf + terminal value + back_fill (MCTS.py:151-264, 297-352) -------------------------
-__global__ void __launch_bounds__(TTPB, 4) k_tree_expand_backup(hz_tree T, const float* policy, const float* value,
+#ifndef HZ_EXPAND_MIN_BLOCKS
+#define HZ_EXPAND_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(TTPB, HZ_EXPAND_MIN_BLOCKS) k_tree_expand_backup(hz_tree T, const float* policy, const float* value,
                                                              int is_logits, const float* noise, double eps) {
     __shared__ uint32_t sm_words[WPB][32];
     // scoring happens only for children that end the game: read the neighbour LUT in place
@@ -304,24 +331,42 @@ __global__ void __launch_bounds__(TTPB, 4) k_tree_expand_backup(hz_tree T, const
     for (int j = 0; j < K; j++) {
     const size_t row = (size_t)t * K + j;
     int leaf = T.leaf[row], sim = sim0 + j;
+    // Everything that depends only on (tree, row, leaf) is requested up front, so that the logits,
+    // the tree counters and the statistics of the path edges (back_fill does not depend on the
+    // expansion) travel while the leaf state does: the kernel is a chain of dependent round trips.
+    const int depth = T.depth[row];
+    const uint32_t* path = v.path + (size_t)j * (T.max_sims + 1);
+    const float* prow = policy + row * HZ_ACTION_SIZE;
+    float pl[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) pl[i] = lane + 32 * i < HZ_ACTION_SIZE ? prow[lane + 32 * i] : -INFINITY;
+    const float val_f = value[row];
+    const uint32_t pe = lane < depth ? path[lane] : 0u;
+    const uint32_t leaf_info = v.node_info[leaf];
+    const uint64_t leaf_hash = v.node_hash[leaf];
+    const uint64_t skey = T.search_key[t];
+    int n_nodes = T.n_nodes[t];
+    const int e0 = T.n_edges[t];
     warp_load_words(sm_words[warp], v.node_state, leaf, lane);
+    int p_am = 0, p_N = 0;
+    double p_W = 0.0;
+    if (lane < depth) { p_am = v.edge_am[pe]; p_N = v.edge_N[pe]; p_W = v.edge_W[pe]; }
     State ls;
     state_from_words(ls, sm_words[warp]);
     int leaf_player = player_of(ls);
     double val;
     if (!is_over(ls)) {                                              // MCTS.py:297
-        val = (double)value[row];                                    // :302-304
-        const float* prow = policy + row * HZ_ACTION_SIZE;
+        val = (double)val_f;                                         // :302-304
         // K > 1: a leaf reached twice in one step is expanded by its first simulation only
-        bool expand = (v.node_info[leaf] & 0xFFu) == 0;
+        bool expand = (leaf_info & 0xFFu) == 0;
         float mx = 0.0f, inv_sum = 1.0f;
         if (is_logits) {                                             // fused softmax (model.py:104)
-            float m = -INFINITY;
-            for (int a = lane; a < HZ_ACTION_SIZE; a += 32) m = fmaxf(m, prow[a]);
+            float m = fmaxf(fmaxf(fmaxf(pl[0], pl[1]), fmaxf(pl[2], pl[3])), pl[4]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
             float sum = 0.0f;
-            for (int a = lane; a < HZ_ACTION_SIZE; a += 32) sum += expf(prow[a] - m);
+#pragma unroll
+            for (int i = 0; i < 5; i++) if (lane + 32 * i < HZ_ACTION_SIZE) sum += expf(pl[i] - m);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
             mx = m; inv_sum = 1.0f / sum;
@@ -338,9 +383,7 @@ __global__ void __launch_bounds__(TTPB, 4) k_tree_expand_backup(hz_tree T, const
                 if ((lw[a >> 5] >> (a & 31)) & 1u) noise_sum += (double)nrow[a];
         }
         float one_minus = (float)(1.0 - eps);
-        uint64_t skey = T.search_key[t];
-        uint64_t leaf_hash = v.node_hash[leaf];
-        int n_nodes = T.n_nodes[t], e0 = T.n_edges[t], n_new_edges = 0;
+        int n_new_edges = 0;
         bool overflow = false;
         for (int base = 0; base < n && !overflow; base += 32) {      // expand_leaf, MCTS.py:171-215
             int k = base + lane;
@@ -409,6 +452,7 @@ __global__ void __launch_bounds__(TTPB, 4) k_tree_expand_backup(hz_tree T, const
                 v.edge_child[e] = (uint32_t)id;
                 v.edge_N[e] = 0;
                 v.edge_V[e] = 0;
+                v.edge_cinfo[e] = 0;
                 v.edge_W[e] = 0.0;
                 v.edge_P[e] = p;
                 v.edge_am[e] = (uint16_t)(a | (leaf_player << 8));
@@ -426,16 +470,21 @@ __global__ void __launch_bounds__(TTPB, 4) k_tree_expand_backup(hz_tree T, const
         int oc = outcome_of(ls);
         val = oc == 0 ? 0.0 : (leaf_player == 0 ? (double)oc : -(double)oc);
     }
-    // back_fill (MCTS.py:220-264): edges of one path are distinct, lanes update them in parallel
-    int depth = T.depth[row];
-    const uint32_t* path = v.path + (size_t)j * (T.max_sims + 1);
-    for (int d = lane; d < depth; d += 32) {
+    // back_fill (MCTS.py:220-264): edges of one path are distinct, lanes update them in parallel;
+    // the first 32 were fetched at the top
+    if (lane < depth) {
+        double dir = (p_am >> 8) == leaf_player ? 1.0 : -1.0;        // :242-247
+        v.edge_N[pe] = p_N + 1;                                      // :252
+        v.edge_W[pe] = p_W + val * dir;                              // :253
+        if (K > 1) v.edge_V[pe] -= 1;                                // the in-flight visit has landed
+    }
+    for (int d = lane + 32; d < depth; d += 32) {
         uint32_t e = path[d];
         int mover = v.edge_am[e] >> 8;
-        double dir = mover == leaf_player ? 1.0 : -1.0;              // :242-247
-        v.edge_N[e] += 1;                                            // :252
-        v.edge_W[e] += val * dir;                                    // :253
-        if (K > 1) v.edge_V[e] -= 1;                                 // the in-flight visit has landed
+        double dir = mover == leaf_player ? 1.0 : -1.0;
+        v.edge_N[e] += 1;
+        v.edge_W[e] += val * dir;
+        if (K > 1) v.edge_V[e] -= 1;
     }
     __syncwarp();                                                    // next leaf sees this one's nodes, edges and statistics
     }
@@ -551,7 +600,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Layout {
     int max_nodes, max_edges, table_size;
-    size_t off[19], total;
+    size_t off[21], total;
 };
 static Layout layout_for(int n_trees, int max_sims, int max_nodes, int leaves) {
     Layout L;
@@ -562,11 +611,11 @@ static Layout layout_for(int n_trees, int max_sims, int max_nodes, int leaves) {
     L.table_size = ts;
     size_t nt = (size_t)n_trees, nn = nt * L.max_nodes, ne = nt * L.max_edges;
     size_t K = (size_t)leaves;
-    size_t sizes[19] = {nn * 128, nn * 8, nn * 4, nn * 4, ne * 4, ne * 4, ne * 8, ne * 4, ne * 2,
+    size_t sizes[21] = {nn * 128, nn * 8, nn * 4, nn * 4, ne * 4, ne * 4, ne * 8, ne * 4, ne * 2,
                         nt * ts * 4, nt * K * (size_t)(max_sims + 1) * 4, nt * K * 4, nt * K * 4, nt * 4, nt * 4, nt * 4, nt, nt * 8,
-                        ne * 4};
+                        ne * 4, nt * ts * 8, ne * 4};
     size_t o = 0;
-    for (int i = 0; i < 19; i++) { L.off[i] = o; o += align256(sizes[i]); }
+    for (int i = 0; i < 21; i++) { L.off[i] = o; o += align256(sizes[i]); }
     L.total = o;
     return L;
 }
@@ -585,6 +634,7 @@ int hz_tree_create(hz_tree** out, void* workspace, size_t workspace_bytes, int n
     if (!out || !workspace || n_trees <= 0 || max_sims <= 0 || leaves <= 0 || leaves > 64) return HZ_ERR_ARG;
     if (key_mode != HZ_KEY_EXACT && key_mode != HZ_KEY_REFERENCE) return HZ_ERR_ARG;
     Layout L = layout_for(n_trees, max_sims, max_nodes, leaves);
+    if (L.max_edges >= (1 << 24)) return HZ_ERR_ARG;     // edge_cinfo packs the first-edge index into 24 bits
     if (workspace_bytes < L.total || ((uintptr_t)workspace & 255)) return HZ_ERR_WORKSPACE;
     hz_tree* t = new hz_tree;
     char* b = (char*)workspace;
@@ -599,6 +649,7 @@ int hz_tree_create(hz_tree** out, void* workspace, size_t workspace_bytes, int n
     t->n_nodes = (int32_t*)(b + L.off[14]); t->n_edges = (int32_t*)(b + L.off[15]);
     t->status = (uint8_t*)(b + L.off[16]); t->search_key = (uint64_t*)(b + L.off[17]);
     t->edge_V = (int32_t*)(b + L.off[18]);
+    t->table_hash = (uint64_t*)(b + L.off[19]); t->edge_cinfo = (uint32_t*)(b + L.off[20]);
     t->table_bytes = (size_t)n_trees * L.table_size * 4;
     *out = t;
     return HZ_OK;

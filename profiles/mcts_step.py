@@ -50,6 +50,7 @@ def timed(fn, reps=20):
     ms = []
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(400_000)     # keep the GPU busy while the host enqueues: device time, not launch latency
         e0.record(); fn(); e1.record()
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1) * 1e3)
