@@ -45,19 +45,20 @@ def play_match(candidate_net, best_net, num_games, mcts_config_eval, device="cud
         states = hb.init_states(n, device=dev, seed=seed, first_id=0 if g == 0 else num_games)   # distinct games per group
         if sims % leaves:
             raise ValueError("num_simulations must be a multiple of leaves")
-        tree = BatchedMCTS(n, sims, device=dev, key_mode=key_mode, leaves=leaves)
-        rows = n * leaves
         anynet = candidate_net if candidate_net is not GREEDY else best_net
         if anynet is GREEDY:
             anynet = None
-        dt = anynet.dtype if anynet is not None else torch.float32
-        C = 40 if anynet is not None and hasattr(anynet, "stem40") else 38
-        bufs = (
-            torch.empty((rows, C, 5, 7), dtype=dt, device=dev, memory_format=torch.channels_last).zero_(),
-            torch.zeros((rows, 42), dtype=dt, device=dev),
-            torch.zeros((rows, 143), dtype=torch.float32, device=dev),
-            torch.zeros(rows, dtype=torch.float32, device=dev),
-        )
+        tree = bufs = None
+        if anynet is not None:                                       # greedy vs greedy needs no search arena
+            tree = BatchedMCTS(n, sims, device=dev, key_mode=key_mode, leaves=leaves)
+            rows = n * leaves
+            C = 40 if hasattr(anynet, "stem40") else 38
+            bufs = (
+                torch.empty((rows, C, 5, 7), dtype=anynet.dtype, device=dev, memory_format=torch.channels_last).zero_(),
+                torch.zeros((rows, 42), dtype=anynet.dtype, device=dev),
+                torch.zeros((rows, 143), dtype=torch.float32, device=dev),
+                torch.zeros(rows, dtype=torch.float32, device=dev),
+            )
         for _ in range(200):
             over, oc = hb.outcome(states)
             if bool(over.all()):
@@ -73,7 +74,8 @@ def play_match(candidate_net, best_net, num_games, mcts_config_eval, device="cud
                 actions = tree.choose()                              # first max N: testing=True
             actions = torch.where(live, actions, torch.full_like(actions, -1))
             hb.apply(states, actions)
-        tree.check_status()
+        if tree is not None:
+            tree.check_status()
         over, oc = hb.outcome(states)
         if not bool(over.all()):
             raise RuntimeError("arena game did not finish")
