@@ -20,10 +20,14 @@ def _inference_net(model, device, dtype):
     return InferenceNet(model, device=device, dtype=dtype)
 
 
-def execute_self_play_phase(self, data_generating_manager, n_slots=4096, dtype=torch.bfloat16, device="cuda"):
+def execute_self_play_phase(self, data_generating_manager, n_slots=4096, dtype=torch.bfloat16, device="cuda",
+                            leaves_per_step=1):
     """Bound as a method of the reference ``Trainer``.  Same contract as trainer.py:62-134:
     plays ``num_games_per_iter`` games with the data-generating (best) model and extends
-    ``self.replay_buffer`` with (board, global, pi, z) CPU tensors of every completed game."""
+    ``self.replay_buffer`` with (board, global, pi, z) CPU tensors of every completed game.
+    ``leaves_per_step`` > 1 (a divisor of num_simulations) keeps that many simulations in flight
+    per tree with virtual loss: not the reference's sequential search any more, but with few
+    games per iteration (the reference's default is 25) it is what fills the network batch."""
     num_games = int(self.self_play_config["num_games_per_iter"])
     print(f"\n--- Starting Self-Play Phase ({num_games} games, batched on {device}) ---")
     t0 = time.time()
@@ -31,7 +35,8 @@ def execute_self_play_phase(self, data_generating_manager, n_slots=4096, dtype=t
     was_training = model.training
     model.eval()
     net = _inference_net(model, device, dtype)
-    cfg = SelfPlayConfig.from_mcts_config(self.mcts_config, n_slots=max(1, min(n_slots, num_games)))
+    cfg = SelfPlayConfig.from_mcts_config(self.mcts_config, n_slots=max(1, min(n_slots, num_games)),
+                                          leaves_per_step=int(leaves_per_step))
     traj = BatchedSelfPlay(net, cfg, device=device).play(num_games)
     examples = traj.to_reference_examples()
     self.replay_buffer.extend(examples)                      # trainer.py:127
