@@ -17,15 +17,17 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--games", type=int, default=8192)
 ap.add_argument("--sims", type=int, default=100)
 ap.add_argument("--profile", action="store_true")
+ap.add_argument("--slots", type=int, default=4096)
+ap.add_argument("--leaves", type=int, default=1)
 a = ap.parse_args()
 torch.backends.cudnn.benchmark = True
 torch.manual_seed(0)
 dev = torch.device("cuda", 0)
 model = hznet.AlphaZeroNet.from_config(hznet.DEFAULT_MODEL_CONFIG).eval()
 inf = hznet.InferenceNet(model, device=dev, dtype=torch.bfloat16)
-cfg = sp.SelfPlayConfig(n_slots=4096, num_simulations=a.sims, seed=1)
+cfg = sp.SelfPlayConfig(n_slots=a.slots, num_simulations=a.sims, seed=1, leaves_per_step=a.leaves)
 drv = sp.BatchedSelfPlay(inf, cfg, device=dev)
-drv.play(64)
+drv.play(min(64, a.slots))
 evs = []
 orig = drv.search
 
@@ -52,4 +54,4 @@ print(json.dumps({"gap_ms_mean": sum(gaps) / max(1, len(gaps)), "gap_ms_sorted_t
 st = traj.stats
 print(json.dumps({"steps": len(ms), "loop_s": st["seconds"], "search_s": sum(ms) / 1e3,
                   "outside_search_ms_per_step": (st["seconds"] - sum(ms) / 1e3) / len(ms) * 1e3,
-                  "search_ms_per_step": sum(ms) / len(ms), "slot_utilisation": st["examples"] / (len(ms) * 4096), "stats": st}))
+                  "search_ms_per_step": sum(ms) / len(ms), "slot_utilisation": st["examples"] / (len(ms) * a.slots), "stats": st}))
