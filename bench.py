@@ -540,15 +540,17 @@ def run_b200(args):
                      "frac": achieved / pk["hbm_gbs"],
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch at 65,536 games, ncu --set full
                      # (profiles/r01_playout_ncu.txt): the initial records only; results stay in L2
-                     "traffic": 8410880 if n == 65536 else None, "peak_source": pk_src + " (burst copy)",
+                     "traffic": 8424448 if n == 65536 else None, "peak_source": pk_src + " (burst copy)",
                      "kernel": "hz::k_playout", "note": "algorithmic 258 B/step x steps per launch / CUDA-event launch time "
                      "(SURVEY.md 8d). frac > 1 is expected here and does NOT mean skipped work: the fused kernel keeps each "
                      "game's state in registers for its ~62 steps, so DRAM sees 128 B per GAME (traffic) instead of 258 B per "
                      "STEP; every final record is bit-identical to the CPU oracle's (tests/test_gpu_engine.py). The kernel is "
                      "bound by integer-ALU issue: see issue_slots below (SURVEY.md H7) and 'unfused' for the per-step path.",
                      # ncu --set full of this kernel at 65,536 games (profiles/r01_playout_ncu.txt)
-                     "issue_slots": {"issue_active_pct": 57.9, "alu_pipe_pct": 50.6, "ipc_active": 2.12,
-                                     "active_threads_per_warp": 25.76, "achieved_occupancy_pct": 18.6, "source": "ncu r01c"}},
+                     "issue_slots": {"issue_active_pct": 57.7, "alu_pipe_pct": 51.2, "ipc_active": 2.11,
+                                     "active_threads_per_warp": 26.4, "achieved_occupancy_pct": 18.4,
+                                     "latency_floor_us": 62.4, "source": "ncu r01d (profiles/r01_playout_ncu.txt); latency_floor = "
+                                     "duration of a quarter-size wave: one game is a chain of ~70 dependent steps"}},
         "wall_s": wall,
         "unfused": {"value": unfused_steps / (unfused_ms * 1e-3), "unit": UNIT, "launches": 76 * 3, "ms": unfused_ms,
                     "achieved_GBps": unfused_steps * ALGO_BYTES_PER_STEP / (unfused_ms * 1e-3) / 1e9,
