@@ -458,11 +458,24 @@ __device__ __forceinline__ void set_meta(State& s, uint32_t m) {
 // DEFER_SCORE: at the end of the game only mark phase game_over (winner still None) and let
 // the caller run finalize_scores() later — the fused playout does that once per warp after
 // all of its games have ended, so the scoring loops run with all lanes converged.
-__device__ __forceinline__ void finalize_scores(State& s, const NbrLut* lut) {
-    int s0 = score_player(lut, s, 0), s1 = score_player(lut, s, 1);       // :344-346
+__device__ __forceinline__ void store_final_scores(State& s, int s0, int s1) {
     s.w[HZ_W_SCORES] = ((uint32_t)s0 & 0xFFFFu) | (((uint32_t)s1 & 0xFFFFu) << 16);
     uint32_t wc = s0 > s1 ? 1u : s1 > s0 ? 2u : 3u;                       // :348-354
     s.w[HZ_W_BAG1META] = (s.w[HZ_W_BAG1META] & ~(3u << 29)) | (wc << 29);
+}
+__device__ __forceinline__ void finalize_scores(State& s, const NbrLut* lut) {
+    int s0 = score_player(lut, s, 0), s1 = score_player(lut, s, 1);       // :344-346
+    store_final_scores(s, s0, s1);
+}
+// both players' scores with large water components pushed to the block's queue (owner slots
+// 2*threadIdx.x + player); the caller adds q->extra[...] after resolve_water()
+template <int CAP, int OWNERS>
+__device__ __forceinline__ void partial_scores(const State& s, const NbrLut* lut, WaterQueue<CAP, OWNERS>* q, int& s0, int& s1) {
+    int t[5];
+    score_board(lut, board_of(s, 0), t, q, (int)threadIdx.x * 2);
+    s0 = t[0] + t[1] + t[2] + t[3] + t[4];
+    score_board(lut, board_of(s, 1), t, q, (int)threadIdx.x * 2 + 1);
+    s1 = t[0] + t[1] + t[2] + t[3] + t[4];
 }
 template <bool DEFER_SCORE = false, bool REL = false>
 __device__ __forceinline__ int apply_move(State& s, int a, uint32_t explicit_code, uint64_t dkey,

@@ -185,13 +185,17 @@ __global__ void __launch_bounds__(PTPB) k_playout(void* states, int64_t n, int m
                                                   uint64_t seed, uint64_t first_id, uint32_t* results) {
     __shared__ NbrLut lut;
     __shared__ uint64_t rtab[RTAB_N];
+    __shared__ WaterQueue<2 * PTPB, 2 * PTPB> wq;
     build_nbr_lut(&lut);
     build_rand_table(rtab);
+    water_queue_init(&wq);
     __syncthreads();
     int64_t g = (int64_t)blockIdx.x * PTPB + threadIdx.x;
     uint32_t k = 0;
+    State s;
+    bool fin = false;
+    int s0 = 0, s1 = 0;
     if (g < n) {
-        State s;
         if (FROM_KEYS) init_state(s, keys ? keys[g] : rand64(seed, first_id + (uint64_t)g));
         else load_state(s, states, g);
         if (player_of(s)) swap_boards(s);   // mover-relative board order inside the loop (see REL)
@@ -202,8 +206,16 @@ __global__ void __launch_bounds__(PTPB) k_playout(void* states, int64_t n, int m
             k++;
         }
         if (player_of(s)) swap_boards(s);   // back to absolute order
-        // final scoring deferred to here: the lanes of the warp are converged again
-        if (phase_of(s) == HZ_PHASE_OVER && winner_code(s) == 0) finalize_scores(s, &lut);
+        // final scoring deferred to here: the lanes of the warp are converged again; rivers of >= 5
+        // hexes go to the block's queue and get a whole warp each (resolve_water)
+        fin = phase_of(s) == HZ_PHASE_OVER && winner_code(s) == 0;
+        if (fin) partial_scores(s, &lut, &wq, s0, s1);
+    }
+    __syncthreads();
+    resolve_water(&lut, &wq);
+    __syncthreads();
+    if (g < n) {
+        if (fin) store_final_scores(s, s0 + wq.extra[threadIdx.x * 2], s1 + wq.extra[threadIdx.x * 2 + 1]);
         if (FROM_KEYS) {
             results[g * 3] = s.w[HZ_W_BAG1META];
             results[g * 3 + 1] = s.w[HZ_W_SCORES];
