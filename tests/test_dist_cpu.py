@@ -47,6 +47,14 @@ def _worker(rank, world, port, out):
         torch.manual_seed(0)
         ref = AlphaZeroNet.from_config(TEST_MODEL_CONFIG)
         ok_w = all(torch.equal(a, b) for a, b in zip(m.parameters(), ref.parameters())) if rank else True
+        # a second broadcast after a training step on rank 0 carries the NEW values (the cached
+        # wire buffer is refilled on every call)
+        if rank == 0:
+            with torch.no_grad():
+                for p_ in m.parameters():
+                    p_.add_(1.0)
+        broadcast_weights(m, src=0)
+        ok_w = ok_w and all(torch.equal(a, b + 1.0) for a, b in zip(m.parameters(), ref.parameters()))
         # bf16 wire format halves the bytes
         nbytes16 = broadcast_weights(m, src=0, dtype=torch.bfloat16)
         # trajectories: ragged counts (rank 1 has more, one rank may have none)
