@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--mcts-streams", type=int, default=1, help="slot groups on separate CUDA streams")
     ap.add_argument("--mcts-leaves", type=int, default=1, help="simulations in flight per tree and step (1 = reference-exact; >1 = virtual loss)")
     ap.add_argument("--mcts-steps", type=int, default=5, help="timed moves (each = games x sims simulations)")
+    ap.add_argument("--mcts-no-graph", action="store_true", help="launch the simulation steps eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -210,7 +211,8 @@ def mcts_measure(args, dev, world, rank, dist, with_collectives=True):
     inf = hznet.InferenceNet(model, device=dev, dtype=torch.bfloat16)
     B, S = args.mcts_games, args.mcts_sims
     cfg = sp.SelfPlayConfig(n_slots=B, num_simulations=S, cpuct=2.0, dirichlet_alpha=0.4, dirichlet_epsilon=0.25,
-                            turns_until_tau0=15, seed=77, first_game_id=rank * B, n_streams=args.mcts_streams, leaves_per_step=args.mcts_leaves)
+                            turns_until_tau0=15, seed=77, first_game_id=rank * B, n_streams=args.mcts_streams, leaves_per_step=args.mcts_leaves,
+                            use_cuda_graph=not args.mcts_no_graph)
     drv = sp.BatchedSelfPlay(inf, cfg, device=dev)
     states = hb.init_states(B, device=dev, seed=77, first_id=rank * B)
     hb.playout(states, max_steps=8)                 # a few moves in: realistic branching
