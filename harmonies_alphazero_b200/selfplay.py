@@ -87,7 +87,8 @@ class Trajectories:
             return []
         board, glob = self.encode()
         board, glob, pi, z = board.cpu(), glob.cpu(), self.pi().cpu(), self.z.cpu().view(-1, 1)
-        return [(board[i], glob[i], pi[i], z[i]) for i in range(len(self))]
+        # unbind creates the per-example views in C: ~1.5x faster than indexing in a Python loop
+        return list(zip(board.unbind(0), glob.unbind(0), pi.unbind(0), z.unbind(0)))
 
     def to(self, device):
         return Trajectories(self.states.to(device), self.visits.to(device), self.z.to(device),
