@@ -78,8 +78,9 @@ class ReplayRing:
         out = deque(maxlen=self.capacity)
         order = self._ordered_index()
         for i in range(0, order.numel(), 8192):
-            b, g, p, z = (t.cpu() for t in self._batch(order[i:i + 8192]))
-            out.extend((b[k], g[k], p[k], z[k]) for k in range(b.shape[0]))
+            fields = [t.cpu().numpy() for t in self._batch(order[i:i + 8192])]
+            # every tensor owns its storage (a view would pull its whole batch into the pickle)
+            out.extend(tuple(torch.from_numpy(f[k].copy()) for f in fields) for k in range(fields[0].shape[0]))
         return out
 
     def state_dict(self):

@@ -80,15 +80,21 @@ class Trajectories:
         """(board [M,38,5,7], glob [M,42]) via hz_encode — needs the tensors on a CUDA device."""
         return hb.encode(self.states.contiguous(), dtype=dtype)
 
-    def to_reference_examples(self):
+    def to_reference_examples(self, last=None):
         """list[(board, global, pi, z)] of CPU tensors, exactly what self_play_worker returns
-        and ReplayBuffer.extend consumes (trainer.py:127,531-538; buffer.py:55-67)."""
-        if len(self) == 0:
+        and ReplayBuffer.extend consumes (trainer.py:127,531-538; buffer.py:55-67).  Every tensor
+        owns its storage, like the reference's: buffer.save_buffer pickles the deque, and a VIEW
+        into one big batch tensor would drag the whole batch into the pickle once per example.
+        ``last`` = only the final ``last`` examples (what a deque(maxlen=last) keeps of an extend)."""
+        n = len(self)
+        if n == 0:
             return []
-        board, glob = self.encode()
-        board, glob, pi, z = board.cpu(), glob.cpu(), self.pi().cpu(), self.z.cpu().view(-1, 1)
-        # unbind creates the per-example views in C: ~1.5x faster than indexing in a Python loop
-        return list(zip(board.unbind(0), glob.unbind(0), pi.unbind(0), z.unbind(0)))
+        lo = 0 if last is None else max(0, n - int(last))
+        sub = self if lo == 0 else Trajectories(self.states[lo:], self.visits[lo:], self.z[lo:], self.game_id[lo:], self.move_no[lo:])
+        board, glob = sub.encode()
+        fields = [t.cpu().numpy() for t in (board, glob, sub.pi(), sub.z.view(-1, 1))]
+        fn = torch.from_numpy
+        return [tuple(fn(f[i].copy()) for f in fields) for i in range(n - lo)]
 
     def to(self, device):
         return Trajectories(self.states.to(device), self.visits.to(device), self.z.to(device),

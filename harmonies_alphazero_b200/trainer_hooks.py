@@ -38,7 +38,8 @@ def execute_self_play_phase(self, data_generating_manager, n_slots=4096, dtype=t
     cfg = SelfPlayConfig.from_mcts_config(self.mcts_config, n_slots=max(1, min(n_slots, num_games)),
                                           leaves_per_step=int(leaves_per_step))
     traj = BatchedSelfPlay(net, cfg, device=device).play(num_games)
-    examples = traj.to_reference_examples()
+    # a deque(maxlen) keeps only the tail of an extend: build just those examples
+    examples = traj.to_reference_examples(last=getattr(self.replay_buffer, "maxlen", None))
     self.replay_buffer.extend(examples)                      # trainer.py:127
     if was_training:
         model.train()

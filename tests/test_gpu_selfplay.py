@@ -169,6 +169,13 @@ def test_selfplay_games_and_example_contract(mods, oracle):
     assert b.dtype == gl.dtype == p.dtype == zz.dtype == torch.float32 and not b.is_cuda
     ob, og = oracle.encode(S[:1])
     assert np.array_equal(b.numpy(), ob[0]) and np.array_equal(gl.numpy(), og[0])
+    # buffer.save_buffer pickles the deque of examples: each tensor must own its storage
+    import pickle
+
+    assert len(pickle.dumps(ex[:20], pickle.HIGHEST_PROTOCOL)) < 20 * 8000
+    assert b.untyped_storage().nbytes() == 38 * 5 * 7 * 4
+    tail = traj.to_reference_examples(last=7)
+    assert len(tail) == 7 and all(torch.equal(x, y) for x, y in zip(tail[-1], ex[-1])) and torch.equal(tail[0][2], ex[-7][2])
 
 
 def test_replay_ring_matches_reference_deque_semantics(mods, oracle):
@@ -188,6 +195,9 @@ def test_replay_ring_matches_reference_deque_semantics(mods, oracle):
     assert len(ring) == len(ref) == 500
     got = ring.to_reference_buffer()
     assert got.maxlen == 500 and len(got) == 500
+    import pickle
+
+    assert len(pickle.dumps(got, pickle.HIGHEST_PROTOCOL)) < 500 * 8000      # buffer.save_buffer stays ~6 KB per example
     for k in (0, 1, 250, 499):
         for a, b in zip(got[k], ref[k]):
             assert torch.equal(a, b)
