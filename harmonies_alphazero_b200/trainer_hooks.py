@@ -68,8 +68,55 @@ def self_play_worker(args):
         return []
 
 
-def install(trainer_module):
-    """Monkey-patch the reference ``trainer`` module in place."""
+def evaluate_model(self, dtype=torch.bfloat16, device="cuda", eval_config=None):
+    """Bound as a method of the reference ``Trainer``: the candidate-vs-best match of
+    trainer.py:293-431 with all ``eval_episodes`` games played concurrently (arena.play_match:
+    candidate is player 0 in even games, every move a fresh search by the side to move's
+    network under mcts_config_eval), followed by the reference's promotion rule: win rate over
+    decided games (0.5 if none, :328-331) above ``eval_win_rate_threshold`` saves the candidate
+    as the best model and reloads ``best_model_manager`` (:345-361).  Returns the match dict."""
+    import sys
+
+    from . import arena
+
+    cfg = self.self_play_config
+    n_games, threshold = int(cfg["eval_episodes"]), float(cfg["eval_win_rate_threshold"])
+    if eval_config is None:                                  # trainer.py:392-394
+        tm = sys.modules.get(type(self).__module__)
+        name = "test_mcts_config_eval" if self.mcts_config.get("testing") else "mcts_config_eval"
+        eval_config = getattr(tm, name)
+    print(f"\n--- Starting Evaluation Phase ({n_games} games, batched on {device}) ---")
+    t0 = time.time()
+    nets = []
+    for mgr in (self.model_manager, self.best_model_manager):
+        was_training = mgr.model.training
+        mgr.model.eval()
+        nets.append(_inference_net(mgr.model, device, dtype))
+        if was_training:
+            mgr.model.train()
+    res = arena.play_match(nets[0], nets[1], n_games, eval_config, device=device)
+    decided = res["candidate_wins"] + res["best_wins"]
+    win_rate = res["candidate_wins"] / decided if decided else 0.5
+    res["win_rate"] = win_rate
+    print(f"  Results: Candidate={res['candidate_wins']}, Best={res['best_wins']}, Draws/Errors={res['draws']}")
+    print(f"  Candidate Win Rate (vs Best, excluding draws): {win_rate:.3f}")
+    res["promoted"] = win_rate > threshold
+    if res["promoted"]:
+        print(f"  Candidate model passed threshold ({threshold:.2f}); updating '{self.best_model_filename}'.")
+        self.model_manager.save_checkpoint(folder=cfg["checkpoint_folder"], filename=self.best_model_filename,
+                                           iteration=cfg["num_iterations"])
+        self.best_model_manager.load_checkpoint(folder=cfg["checkpoint_folder"], filename=self.best_model_filename)
+    else:
+        print(f"  Candidate model did not pass threshold ({threshold:.2f}). Best model remains unchanged.")
+    print(f"  Time taken: {time.time() - t0:.2f} seconds")
+    return res
+
+
+def install(trainer_module, evaluation=True):
+    """Monkey-patch the reference ``trainer`` module in place: self-play always, the arena
+    evaluation (Trainer.evaluate_model) unless ``evaluation=False``."""
     trainer_module.Trainer.execute_self_play_phase = execute_self_play_phase
     trainer_module.self_play_worker = self_play_worker
+    if evaluation:
+        trainer_module.Trainer.evaluate_model = evaluate_model
     return trainer_module

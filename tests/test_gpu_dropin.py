@@ -205,3 +205,31 @@ def test_trainer_hook_fills_replay_buffer(eng):
     assert abs(float(p.sum()) - 1.0) < 1e-5
     one = trainer_hooks.self_play_worker((Manager.model.state_dict(), net.TEST_MODEL_CONFIG, {}, FakeTrainer.mcts_config, "cpu"))
     assert len(one) >= 56 and one[0][0].shape == (38, 5, 7)
+
+    # arena hook (trainer.py:293-431): match + the reference's promotion rule
+    calls = []
+
+    class EvalManager:
+        def __init__(self, seed):
+            torch.manual_seed(seed)
+            self.model = net.AlphaZeroNet.from_config(net.TEST_MODEL_CONFIG)
+
+        def save_checkpoint(self, folder, filename, iteration):
+            calls.append(("save", folder, filename, iteration))
+
+        def load_checkpoint(self, folder, filename):
+            calls.append(("load", folder, filename))
+
+    class EvalTrainer(FakeTrainer):
+        self_play_config = {"eval_episodes": 6, "eval_win_rate_threshold": -1.0, "checkpoint_folder": "ckpt", "num_iterations": 9}
+        best_model_filename = "best.pth"
+
+    et = EvalTrainer()
+    et.model_manager, et.best_model_manager = EvalManager(1), EvalManager(2)
+    cfg_eval = {"num_simulations": 6, "cpuct": 1.0, "testing": True}
+    res = trainer_hooks.evaluate_model(et, eval_config=cfg_eval)
+    assert res["candidate_wins"] + res["best_wins"] + res["draws"] == 6 and res["promoted"]
+    assert calls == [("save", "ckpt", "best.pth", 9), ("load", "ckpt", "best.pth")]
+    et.self_play_config = dict(et.self_play_config, eval_win_rate_threshold=2.0)
+    calls.clear()
+    assert not trainer_hooks.evaluate_model(et, eval_config=cfg_eval)["promoted"] and calls == []
