@@ -469,8 +469,56 @@ def gen_greedy(n_trace=700, n_weird=300):
     print(f"greedy: {len(sel)} states, {sum(a < 0 for a in acts)} without a legal move")
 
 
+def gen_net(n=16):
+    """a17: the reference's own AlphaZeroModel (model.py:277-357) with the test-size
+    configuration (config.py:103-113), randomised BatchNorm statistics, eval mode: its
+    state_dict, ``n`` inputs encoded by the reference from real positions, and its outputs
+    (logits, tanh value, and ModelManager.predict's unmasked softmax, model.py:81-110)."""
+    import importlib
+
+    import torch
+
+    rh.load_reference()
+    if rh.REF_ROOT not in sys.path:
+        sys.path.insert(0, rh.REF_ROOT)
+    model_mod, cfgm = importlib.import_module("model"), importlib.import_module("config")
+    pgs = importlib.import_module("process_game_state")
+    mc = dict(cfgm.test_model_config) if hasattr(cfgm, "test_model_config") else dict(cfgm.model_config_default)
+    torch.manual_seed(1234)
+    ref = model_mod.AlphaZeroModel(
+        input_channels=mc["input_channels"], cnn_filters=mc["cnn_filters"], board_size=mc["board_size"],
+        action_size=mc["action_size"], global_feature_size=mc["global_feature_size"],
+        value_hidden_dim=mc["value_head_hidden_dim"], num_res_blocks=mc["num_res_blocks"])
+    for m in ref.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.3); m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.2)
+    ref.eval()
+    boards, globs = [], []
+    for g in range(n):
+        st = rh.new_game_stream(1000 + g)
+        for _ in range(3 + 4 * g):
+            if st.is_game_over():
+                break
+            moves = sorted(st.get_legal_moves(), key=pgs.get_action_index)
+            st = st.apply_move(moves[(7 * g + 3) % len(moves)])
+        b, gl = pgs.create_state_tensors(st)
+        boards.append(b); globs.append(gl)
+    B, G = torch.stack(boards), torch.stack(globs)
+    with torch.no_grad():
+        logits, value = ref(B, G)
+    out = {"cfg_" + k: np.array(v) for k, v in mc.items() if isinstance(v, (int, float))}
+    out.update({"sd_" + k: v.numpy() for k, v in ref.state_dict().items()})
+    out.update(board=B.numpy(), glob=G.numpy(), logits=logits.numpy(), value=value.numpy().reshape(-1),
+               probs=torch.softmax(logits, dim=1).numpy())
+    np.savez_compressed(os.path.join(OUT, "net.npz"), **out)
+    print(f"net: {sum(v.numel() for v in ref.state_dict().values())} values in the state_dict, {n} positions")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "net" in (sys.argv[1:] or ["net"]):
+        gen_net()
     if "greedy" in (sys.argv[1:] or ["greedy"]):
         gen_greedy()
     which = sys.argv[1:] or ["engine", "scoring", "encode", "equiv", "mcts", "weird"]

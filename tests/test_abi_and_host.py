@@ -123,3 +123,36 @@ def test_draw_source_is_uniform_without_replacement():
     bag = [0, 0, 1, 0, 1, 0]
     assert sorted(pk.draw_pile(bag, pk.rand(1, 1))) == [2, 4] and bag == [0] * 6
     assert pk.draw_pile([0] * 6, 99) == []
+
+
+def _golden_net():
+    import torch
+
+    from harmonies_alphazero_b200 import net
+
+    g = load_golden("net")
+    cfg = dict(net.DEFAULT_MODEL_CONFIG, **{k[4:]: int(g[k]) for k in g.files if k.startswith("cfg_")})
+    m = net.AlphaZeroNet.from_config(cfg)
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd_")}
+    m.load_state_dict(sd, strict=True)          # same parameter AND buffer names as model.py:277-323
+    return g, m.eval()
+
+
+def test_network_is_the_reference_model():
+    """a17: tests/golden/net.npz holds the state_dict, inputs and outputs of the reference's own
+    AlphaZeroModel (model.py:277-357, eval mode).  Our module loads that state_dict strictly
+    and reproduces logits / value; the BatchNorm-folded inference copy agrees to fp32 noise.
+    Tolerance: 1e-5 absolute (fp32 conv summation order)."""
+    import torch
+
+    from harmonies_alphazero_b200 import net
+
+    g, m = _golden_net()
+    b, gl = torch.from_numpy(g["board"]), torch.from_numpy(g["glob"])
+    with torch.no_grad():
+        logits, value = m(b, gl)
+    assert np.abs(logits.numpy() - g["logits"]).max() < 1e-5 and np.abs(value.numpy().reshape(-1) - g["value"]).max() < 1e-5
+    inf = net.InferenceNet(m, device="cpu", dtype=torch.float32)
+    l2, v2 = inf(b, gl)
+    assert np.abs(l2.numpy() - g["logits"]).max() < 1e-4 and np.abs(v2.numpy() - g["value"]).max() < 1e-5
+    assert np.abs(torch.softmax(l2, 1).numpy() - g["probs"]).max() < 1e-5      # ModelManager.predict: unmasked softmax

@@ -48,6 +48,23 @@ def test_inference_net_matches_module(mods):
     assert (v16 - v_ref.view(-1)).abs().max() < 0.1
 
 
+def test_inference_net_matches_reference_model_golden(mods):
+    """the reference's own model (state_dict + outputs in tests/golden/net.npz) through the CUDA
+    inference path: fp32 within 1e-4 of the reference's logits, bf16 at bf16 precision"""
+    from tests.test_abi_and_host import _golden_net
+
+    _, net, _, _ = mods
+    g, m = _golden_net()
+    b, gl = torch.from_numpy(g["board"]).cuda(), torch.from_numpy(g["glob"]).cuda()
+    inf = net.InferenceNet(m, device="cuda", dtype=torch.float32)
+    l, v = inf(b.contiguous(memory_format=torch.channels_last), gl)
+    assert np.abs(l.cpu().numpy() - g["logits"]).max() < 1e-4 and np.abs(v.cpu().numpy() - g["value"]).max() < 1e-4
+    inf16 = net.InferenceNet(m, device="cuda", dtype=torch.bfloat16)
+    l16, v16 = inf16(b.to(torch.bfloat16).contiguous(memory_format=torch.channels_last), gl.to(torch.bfloat16))
+    assert np.abs(torch.softmax(l16, 1).cpu().numpy() - g["probs"]).max() < 0.03
+    assert np.abs(v16.cpu().numpy() - g["value"]).max() < 0.08
+
+
 @pytest.mark.parametrize("cfg_name", ["TEST_MODEL_CONFIG", "DEFAULT_MODEL_CONFIG"])
 def test_fused_heads_kernel_matches_torch_heads(mods, cfg_name):
     """hz_net_heads (model.py:340-355 in one kernel) vs the same tail computed by torch in
