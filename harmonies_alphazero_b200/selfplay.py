@@ -101,6 +101,22 @@ class Trajectories:
                             self.game_id.to(device), self.move_no.to(device), dict(self.stats))
 
 
+class SyntheticEvaluator:
+    """Stands in for the network where the leaf evaluation has to be an exact, device-independent
+    function of the position (parity tests against the reference's own self-play worker,
+    tree-only measurements): priors and value come from hz_tree_fake_eval, the same function of
+    the leaf's canonical hash as oracle/ref_harness.FakeModelManager.  Pass it as ``net``."""
+
+    dtype = torch.float32
+    tree_eval = True
+
+    def __init__(self, device="cuda"):
+        self.device = torch.device(device)
+
+    def __call__(self, board, glob, out=None):
+        raise RuntimeError("SyntheticEvaluator is evaluated on the tree (hz_tree_fake_eval), not on tensors")
+
+
 class _Group:
     """A contiguous range of slots with its own trees, static network buffers, CUDA graph and
     stream.  Two groups on two streams let one group's tree kernels (HBM/latency-bound) run
@@ -130,13 +146,16 @@ class _Group:
         """one simulation for every tree of the group: select -> network -> expand+backup"""
         o, t = self.o, self.tree
         t.select(o.cfg.cpuct, self.board, self.glob, dtype=o.net.dtype, channels_last=o.channels_last, pad40=o.pad40)
-        if o._net_takes_out:          # InferenceNet writes straight into the static buffers
+        if getattr(o.net, "tree_eval", False):
+            t.fake_eval(self.logits, self.value)       # priors, not logits
+        elif o._net_takes_out:        # InferenceNet writes straight into the static buffers
             o.net(self.board, self.glob, out=(self.logits, self.value))
         else:
             logits, value = o.net(self.board, self.glob)
             self.logits.copy_(logits)
             self.value.copy_(value)
-        t.expand_backup(self.logits, self.value, is_logits=True, noise=self.noise, eps=o.cfg.dirichlet_epsilon)
+        t.expand_backup(self.logits, self.value, is_logits=not getattr(o.net, "tree_eval", False), noise=self.noise,
+                        eps=o.cfg.dirichlet_epsilon)
 
     def capture(self):
         """Warm up (cuDNN algorithm selection must happen outside capture) and capture one

@@ -515,10 +515,75 @@ def gen_net(n=16):
     print(f"net: {sum(v.numel() for v in ref.state_dict().values())} values in the state_dict, {n} positions")
 
 
+def gen_selfplay(n_games=3, sims=12, seed=4242):
+    """f1: the reference's own ``self_play_worker`` (trainer.py:434-541), unmodified, run for
+    ``n_games`` whole games.  Only its collaborators are pinned down: ModelManager is the fake
+    evaluator (priors/value = exact function of the leaf hash), HarmoniesGameState() draws from
+    the library's stream of game key rand(seed, game), and every search draws in-tree with the
+    library's default search key rand(key ^ SEARCH_SALT, move number).  testing=True (no root
+    noise, greedy move), as config.py:136-150.  Stored per example: the packed state before the
+    search, pi (float32, as the worker stores it) and z."""
+    import importlib
+
+    ref = rh.load_reference()
+    if rh.REF_ROOT not in sys.path:
+        sys.path.insert(0, rh.REF_ROOT)
+    tr = importlib.import_module("trainer")
+    cfg = {"num_simulations": sims, "cpuct": 2, "dirichlet_alpha": 0.4, "dirichlet_epsilon": 0.25,
+           "fpu_value": 0.25, "turns_until_tau0": 15, "action_size": 143, "testing": True}
+
+    class FakeManager(rh.FakeModelManager):
+        class _M:
+            def load_state_dict(self, sd):
+                pass
+
+            def eval(self):
+                pass
+
+        def __init__(self, *a, **k):
+            self.model = self._M()
+
+    recorded = []
+    real_search = tr.get_best_action_and_pi
+    game_key = [0]
+
+    def search(state, manager, mcts_config, move_number):
+        recorded.append(pk.pack_state(state, rng_key=game_key[0], rng_event=rh.ctx.event, moves=move_number))
+        saved = (rh.ctx.mode, rh.ctx.key, rh.ctx.event, rh.ctx.k)
+        rh.ctx.mode, rh.ctx.key, rh.ctx.sim = "tree", pk.rand(game_key[0] ^ pk.SEARCH_SALT, move_number), -1
+        try:
+            return real_search(state, manager, mcts_config, move_number)
+        finally:
+            rh.ctx.mode, rh.ctx.key, rh.ctx.event, rh.ctx.k = saved
+
+    tr.ModelManager, tr.get_best_action_and_pi = FakeManager, search
+    states, pis, zs, gids, boards, globs = [], [], [], [], [], []
+    t0 = time.time()
+    try:
+        for g in range(n_games):
+            game_key[0] = pk.rand(seed, g)
+            rh.ctx.mode, rh.ctx.key, rh.ctx.event, rh.ctx.k = "stream", game_key[0], 0, 0
+            recorded.clear()
+            data = tr.self_play_worker(({}, {}, {"device": "cpu"}, cfg, "cpu"))
+            assert data and len(data) == len(recorded)
+            for w, (b, gl, pi, z) in zip(recorded, data):
+                states.append(w); pis.append(pi.numpy()); zs.append(float(z.item())); gids.append(g)
+                boards.append(b.numpy()); globs.append(gl.numpy())
+    finally:
+        tr.get_best_action_and_pi = real_search
+    np.savez_compressed(
+        os.path.join(OUT, "selfplay.npz"), states=np.array(states, dtype=np.uint32), pi=np.array(pis, dtype=np.float32),
+        z=np.array(zs, dtype=np.float32), game=np.array(gids, dtype=np.int32), seed=np.uint64(seed), sims=np.int32(sims),
+        cpuct=np.float32(cfg["cpuct"]), board0=np.array(boards[:4], dtype=np.float32), glob0=np.array(globs[:4], dtype=np.float32))
+    print(f"selfplay: {n_games} games, {len(states)} examples, {time.time() - t0:.1f}s")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if "net" in (sys.argv[1:] or ["net"]):
         gen_net()
+    if "selfplay" in (sys.argv[1:] or ["selfplay"]):
+        gen_selfplay()
     if "greedy" in (sys.argv[1:] or ["greedy"]):
         gen_greedy()
     which = sys.argv[1:] or ["engine", "scoring", "encode", "equiv", "mcts", "weird"]

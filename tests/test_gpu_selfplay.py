@@ -195,6 +195,34 @@ def test_selfplay_games_and_example_contract(mods, oracle):
     assert len(tail) == 7 and all(torch.equal(x, y) for x, y in zip(tail[-1], ex[-1])) and torch.equal(tail[0][2], ex[-7][2])
 
 
+def test_selfplay_reproduces_the_reference_worker(mods):
+    """f1: tests/golden/selfplay.npz was written by the reference's own self_play_worker
+    (trainer.py:434-541) playing whole games with the fake evaluator and the library's draw
+    streams.  BatchedSelfPlay.play with the same evaluator must produce the same examples:
+    identical states before every search (bit-exact), pi within 1e-6, identical z."""
+    from tests.conftest import load_golden
+
+    hb, net, sp, _ = mods
+    g = load_golden("selfplay")
+    n_games = int(g["game"].max()) + 1
+    cfg = sp.SelfPlayConfig(n_slots=n_games, num_simulations=int(g["sims"]), cpuct=float(g["cpuct"]), testing=True,
+                            seed=int(g["seed"]), use_cuda_graph=False)
+    traj = sp.BatchedSelfPlay(sp.SyntheticEvaluator(), cfg).play(n_games)
+    assert len(traj) == len(g["z"])
+    S, P, Z = traj.states.cpu().numpy().view(np.uint32), traj.pi().cpu().numpy(), traj.z.cpu().numpy()
+    G, M = traj.game_id.cpu().numpy(), traj.move_no.cpu().numpy()
+    for game in range(n_games):
+        idx = np.nonzero(G == game)[0]
+        idx = idx[np.argsort(M[idx], kind="stable")]
+        ref = np.nonzero(g["game"] == game)[0]
+        assert len(idx) == len(ref)
+        assert np.array_equal(S[idx][:, :28], g["states"][ref][:, :28])
+        assert np.abs(P[idx] - g["pi"][ref]).max() <= 1e-6
+        assert np.array_equal(Z[idx], g["z"][ref])
+    board, glob = hb.encode(torch.from_numpy(g["states"][:4].view(np.int32)).cuda())     # the worker's state tensors
+    assert np.array_equal(board.cpu().numpy(), g["board0"]) and np.array_equal(glob.cpu().numpy(), g["glob0"])
+
+
 def test_replay_ring_matches_reference_deque_semantics(mods, oracle):
     """f2: packed GPU ring == deque(maxlen) of the reference tuples (buffer.py, trainer.py:127)"""
     hb, net, sp, _ = mods

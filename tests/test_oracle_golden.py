@@ -171,3 +171,30 @@ def test_mcts_python_callback(oracle):
     r = oracle.search(*args, eval_fn=lambda w: pk.fake_eval(pk.canon_hash(w)))
     r2 = oracle.search(*args)
     assert np.array_equal(r["N"], r2["N"]) and np.array_equal(r["W"], r2["W"])
+
+
+def test_selfplay_worker_golden(oracle):
+    """the reference worker's games (tests/golden/selfplay.npz): the oracle's search from each
+    recorded state, with the library's default search key, gives the recorded pi; applying the
+    first-max-N move leads to the next recorded state; z follows the final outcome"""
+    g = load_golden("selfplay")
+    S, PI, Z, G = g["states"], g["pi"], g["z"], g["game"]
+    sims, cpuct = int(g["sims"]), float(g["cpuct"])
+    for game in range(int(G.max()) + 1):
+        idx = np.nonzero(G == game)[0]
+        for j, i in enumerate(idx):
+            w = S[i]
+            key = int(w[24]) | (int(w[25]) << 32)
+            r = oracle.search(w, pk.rand(key ^ pk.SEARCH_SALT, int(w[27])), sims, cpuct)
+            N = r["N"].astype(np.float64)
+            assert np.abs(N / N.sum() - PI[i]).max() <= 1e-6
+            nxt, st = oracle.apply(w[None], np.array([int(np.argmax(r["N"]))], dtype=np.int16))
+            assert st[0] == 0
+            if j + 1 < len(idx):
+                assert np.array_equal(nxt[0][:28], S[idx[j + 1]][:28])
+            else:
+                over, oc = oracle.outcome(nxt)
+                assert over[0]
+                mover = (S[idx] [:, 22] >> 24) & 1
+                want = np.where(mover == 0, float(oc[0]), -float(oc[0])) if oc[0] != 0 else np.zeros(len(idx))
+                assert np.array_equal(Z[idx], want.astype(np.float32))
