@@ -79,7 +79,7 @@ def _worker(rank, world, port, out):
 
 def test_two_rank_gloo_broadcast_and_gather():
     world, port = 2, _free_port()
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()      # never fork a process that already runs torch threads
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     for r in range(world):
