@@ -89,10 +89,19 @@ def _fold(conv, bn):
 class InferenceNet:
     """Folded, channels-last inference copy of an AlphaZeroNet on one device."""
 
-    def __init__(self, model, device="cuda", dtype=torch.bfloat16, fused=True, fused_heads=True):
+    def __init__(self, model, device="cuda", dtype=torch.bfloat16, fused=True, fused_heads=True, tower="cudnn"):
+        """tower: "cudnn" (library convolutions) or "hand" (csrc/hz_tower.cu, the hand-written
+        sm_100a tcgen05 tower; bf16 on CUDA with 128 filters only — it raises otherwise, there is
+        no silent fallback between the two)."""
         self.device, self.dtype = torch.device(device), dtype
         self.fused = fused and self.device.type == "cuda"
         self.use_fused_heads = fused_heads
+        if tower not in ("cudnn", "hand"):
+            raise ValueError("tower must be 'cudnn' or 'hand'")
+        if tower == "hand" and not (self.device.type == "cuda" and dtype == torch.bfloat16):
+            raise ValueError("the hand-written tower is bf16 on CUDA only")
+        self.tower = tower
+        self.hand = None
         self.load(model)
 
     def load(self, model):
@@ -116,6 +125,10 @@ class InferenceNet:
         lin = lambda l: (l.weight.detach().to(dev, dt).contiguous(), l.bias.detach().to(dev, dt))  # noqa: E731
         self.policy_fc, self.value_fc1, self.value_fc2 = lin(model.policy_fc), lin(model.value_fc1), lin(model.value_fc2)
         self._build_fused_heads(model)
+        if self.tower == "hand":
+            from .tower import HandTower
+
+            self.hand = HandTower(model, dev)
         if self.fused:
             # the fused cuDNN entry points do not cover every dtype/arch combination: probe once
             # and use conv2d + relu (still cuDNN) if they refuse
@@ -186,10 +199,7 @@ class InferenceNet:
     def forward(self, board, glob, out=None):
         """board [B,38,5,7] (channels-last preferred), glob [B,42], both ``dtype``.
         Returns (logits fp32 [B,143], value fp32 [B]); ``out`` = preallocated pair to fill."""
-        x = self._conv_relu(board, self.stem40 if board.shape[1] == 40 else self.stem, 1)
-        for c1, c2 in self.blocks:
-            y = self._conv_relu(x, c1, 1)
-            x = self._conv_relu(y, c2, 1, residual=x)
+        x = self.tower_out(board)
         B = x.shape[0]
         if self.heads is not None and self.use_fused_heads:
             return self._fused_heads(x, glob, out)
@@ -199,6 +209,23 @@ class InferenceNet:
             out[1].copy_(value)
             return out
         return self._torch_heads(x, glob, B)
+
+    @torch.no_grad()
+    def tower_out(self, board):
+        """Output of the stem + residual blocks, [B,C,5,7] (channels-last on CUDA)."""
+        if self.hand is not None:
+            if board.shape[1] % 8:      # 38 planes: pad to the 40-plane leaf layout
+                b40 = torch.zeros((board.shape[0], 40, 5, 7), dtype=self.dtype, device=self.device).contiguous(memory_format=torch.channels_last)
+                b40[:, : board.shape[1]] = board
+                board = b40
+            elif not board.is_contiguous(memory_format=torch.channels_last):
+                board = board.contiguous(memory_format=torch.channels_last)
+            return self.hand.forward(board)
+        x = self._conv_relu(board, self.stem40 if board.shape[1] == 40 else self.stem, 1)
+        for c1, c2 in self.blocks:
+            y = self._conv_relu(x, c1, 1)
+            x = self._conv_relu(y, c2, 1, residual=x)
+        return x
 
     def _torch_heads(self, x, glob, B):
         p = self._conv_relu(x, self.phead, 0).contiguous(memory_format=torch.contiguous_format).view(B, -1)

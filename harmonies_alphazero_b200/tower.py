@@ -1,0 +1,119 @@
+"""Hand-written sm_100a residual tower (csrc/hz_tower.cu) behind a small Python handle.
+
+Replaces the 17 cuDNN convolutions of the reference network's body (model.py:325-339: stem
+conv+bn+relu, then ``num_res_blocks`` x ResidualBlock.forward, model.py:380-392) for the
+default width (128 filters).  BatchNorm is folded in fp32 exactly as ``net._fold`` does for the
+cuDNN path, weights are rounded to bf16 once, accumulation is fp32 in tensor memory.
+
+There is no fallback: without the CUDA library every call raises.  ``InferenceNet(tower="cudnn")``
+is the A/B switch for measurements.
+"""
+
+import torch
+
+from . import _lib
+
+G = 16            # boards per tile
+KH_BYTES = 71680  # 560 rows x 128 bytes: one 64-channel half of a tile
+
+
+def pack_conv_weight(w):
+    """[128, Cin, 3, 3] fp32 (BatchNorm folded) -> uint8 [9, nkh, 128, 128]: per tap (ky*3+kx) and
+    64-channel half a K-major SWIZZLE_128B tile of bf16 (16-byte group g stored at g ^ (out & 7))."""
+    O, I = w.shape[0], w.shape[1]
+    if O != 128 or w.shape[2:] != (3, 3):
+        raise ValueError("hand-written tower needs 128 output channels and 3x3 kernels")
+    nkh = (I + 63) // 64
+    wp = torch.zeros((O, nkh * 64, 3, 3), dtype=torch.float32)
+    wp[:, :I] = w.detach().float().cpu()
+    t = wp.permute(2, 3, 0, 1).reshape(9, O, nkh, 8, 8).to(torch.bfloat16)       # [tap][o][kh][g][8]
+    t = t.permute(0, 2, 1, 3, 4).contiguous()                                     # [tap][kh][o][g][8]
+    o = torch.arange(O).view(O, 1)
+    j = torch.arange(8).view(1, 8)
+    src_group = (j ^ (o & 7)).view(1, 1, O, 8, 1).expand(9, nkh, O, 8, 8)        # position j holds group j ^ (o & 7)
+    img = torch.gather(t, 3, src_group).contiguous()
+    return img.view(torch.uint8).reshape(9, nkh, O, 128), nkh
+
+
+class HandTower:
+    """Folded stem + residual blocks of an AlphaZeroNet on one CUDA device."""
+
+    def __init__(self, model, device="cuda"):
+        from .net import _fold
+
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.HarmoniesLibraryError("the hand-written tower runs on a CUDA device only (no CPU fallback)")
+        self.lib = _lib.load()
+        if model.conv.out_channels != 128 or model.conv.in_channels > 64:
+            raise ValueError("hand-written tower supports cnn_filters == 128 and <= 64 input planes")
+        self.in_channels = model.conv.in_channels
+        dev = self.device
+
+        def conv(c, bn):
+            w, b = _fold(c, bn)
+            img, nkh = pack_conv_weight(w)
+            return img.to(dev), b.detach().float().contiguous().to(dev), nkh
+
+        self.stem = conv(model.conv, model.bn)
+        self.blocks = [(conv(b.conv1, b.bn1), conv(b.conv2, b.bn2)) for b in model.residual_blocks]
+        self._bufs = {}
+        self.fault = None     # optional host-mapped fault word (tests)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _buffers(self, n_pad):
+        b = self._bufs.get(n_pad)
+        if b is None:
+            tiles = n_pad // G
+            mk = lambda halves: torch.zeros(tiles * halves * KH_BYTES, dtype=torch.uint8, device=self.device)  # noqa: E731
+            b = self._bufs[n_pad] = dict(x0=mk(1), a=mk(2), b=mk(2), c=mk(2),
+                                         out=torch.zeros((n_pad, 35, 128), dtype=torch.bfloat16, device=self.device))
+        return b
+
+    def to_tiles(self, src_nhwc, channels, halves, dst):
+        n = src_nhwc.shape[0]
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.hz_tower_to_tiles(src_nhwc.data_ptr(), dst.data_ptr(), n, channels, halves, self._stream()), "hz_tower_to_tiles")
+
+    def from_tiles(self, src, n):
+        out = torch.empty((n, 35, 128), dtype=torch.bfloat16, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.hz_tower_from_tiles(src.data_ptr(), out.data_ptr(), n, self._stream()), "hz_tower_from_tiles")
+        return out
+
+    def conv(self, x, halves, wb, res, y, n_pad, relu=True, out_nhwc=False):
+        img, bias, nkh = wb
+        assert nkh == halves
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.hz_tower_conv3x3(
+                x.data_ptr(), halves, img.data_ptr(), bias.data_ptr(), None if res is None else res.data_ptr(), y.data_ptr(),
+                n_pad, 1 if relu else 0, 1 if out_nhwc else 0, self.fault, self._stream()), "hz_tower_conv3x3")
+
+    @torch.no_grad()
+    def forward(self, board, out=None):
+        """board: bf16 [B, C, 5, 7] in channels-last memory (NHWC, C = 38 or 40 with zero planes
+        behind the 38), B arbitrary.  Returns the tower output as a channels-last [B,128,5,7]
+        view of an NHWC buffer (what hz_net_heads reads)."""
+        if board.dtype != torch.bfloat16 or not board.is_contiguous(memory_format=torch.channels_last):
+            raise ValueError("HandTower.forward wants a channels-last bf16 board tensor")
+        B, C = board.shape[0], board.shape[1]
+        if C % 8:
+            raise ValueError("channel count of the board tensor must be a multiple of 8 (use the 40-plane leaf layout)")
+        n_pad = (B + G - 1) // G * G
+        buf = self._buffers(n_pad)
+        self.to_tiles(board, C, 1, buf["x0"])
+        x, y, z = buf["a"], buf["b"], buf["c"]
+        if out is None:
+            out = buf["out"]       # static: the same addresses every call (CUDA graphs)
+        if not self.blocks:
+            self.conv(buf["x0"], 1, self.stem, None, out, n_pad, out_nhwc=True)
+        else:
+            self.conv(buf["x0"], 1, self.stem, None, x, n_pad)
+            for i, (c1, c2) in enumerate(self.blocks):
+                last = i == len(self.blocks) - 1
+                self.conv(x, 2, c1, None, y, n_pad)
+                self.conv(y, 2, c2, x, out if last else z, n_pad, out_nhwc=last)
+                x, z = z, x
+        return out[:B].view(B, 5, 7, 128).permute(0, 3, 1, 2)

@@ -69,7 +69,7 @@
 extern "C" {
 #endif
 
-#define HZ_ABI_VERSION      3
+#define HZ_ABI_VERSION      4
 #define HZ_STATE_WORDS      32
 #define HZ_STATE_BYTES      128
 #define HZ_NUM_HEXES        23
@@ -290,6 +290,38 @@ int hz_net_heads(const void *x, const void *glob, int64_t n, int C, int H, const
                  const float *b_conv, const float *w_pol_t, const float *b_pol,
                  const float *w_v1_t, const float *b_v1, const float *w_v2, float b_v2,
                  float *logits, float *value, void *stream);
+
+/* ---- residual tower (model.py:325-339, ResidualBlock.forward model.py:380-392) -----------
+ * Hand-written sm_100a 3x3 convolution (tcgen05.mma, accumulators in tensor memory, operands
+ * brought in by the bulk copy engine), BatchNorm folded, bf16 in / fp32 accumulate / bf16 out.
+ *
+ * "T16" activation layout: boards in tiles of 16; per tile and per 64-channel half 560 rows of
+ * 128 bytes, row = cell*16 + board (cell = y*7 + x of the 5x7 plane), and inside a row the
+ * 16-byte group g (channels 8g..8g+7 of the half) is stored at position g ^ (row & 7): the
+ * shared-memory image of a K-major SWIZZLE_128B tensor-core operand, so a tile is loaded with
+ * plain bulk copies.  Tile stride = channel_halves * 71,680 bytes.
+ * Weight layout: [tap = ky*3+kx][channel half][out channel 0..127] rows of 128 bytes with the
+ * same swizzle (group g at g ^ (out & 7)): 16 KB per (tap, half). */
+size_t hz_tower_tile_bytes(int64_t n_boards, int channel_halves);
+/* Upper bound on the persistent grid of hz_tower_conv3x3 (0 = one CTA per SM, the default).
+ * Process-wide; meant for tests that push many tiles through few CTAs. */
+int hz_tower_set_max_ctas(int max_ctas);
+
+/* NHWC bf16 [n,35,channels] -> T16 tiles (channels % 8 == 0, <= 64*channel_halves; missing
+ * channels and the boards that pad n up to a multiple of 16 are written as zero). */
+int hz_tower_to_tiles(const void *src_nhwc, void *dst_tiles, int64_t n_boards, int channels,
+                      int channel_halves, void *stream);
+/* T16 tiles (2 halves) -> NHWC bf16 [n,35,128] */
+int hz_tower_from_tiles(const void *src_tiles, void *dst_nhwc, int64_t n_boards, void *stream);
+
+/* y = [relu]( conv3x3(x, w) + bias [+ residual] ) for n_boards (multiple of 16) boards.
+ * x: T16 tiles with in_channel_halves (1 for the stem: 38 input planes zero-padded to 64; 2 for
+ * the residual convolutions); residual (nullable): T16 tiles, 2 halves; y: T16 tiles (2 halves),
+ * or NHWC [n,35,128] when out_nhwc != 0 (the layout hz_net_heads reads).  fault (nullable): a
+ * host-mapped word that receives the id of a barrier wait that timed out before the kernel traps. */
+int hz_tower_conv3x3(const void *x_tiles, int in_channel_halves, const void *w_tiles,
+                     const float *bias, const void *residual_tiles, void *y, int64_t n_boards,
+                     int relu, int out_nhwc, unsigned int *fault, void *stream);
 
 #define HZ_PLAYOUT_SALT 0xA5A5F00DC0FFEE11ull
 #define HZ_SEARCH_SALT  0x5EA2C47EE5A17B00ull

@@ -1,0 +1,12 @@
+#!/bin/bash
+# round-2 GPU call A: tcgen05 primitive probe, tower parity tests, tower timing vs cuDNN
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv | tee gpurun_out/a_smi.txt
+( cd profiles
+  for v in "16 0 0 0 1" "112 0 0 0 1" "112 0 0 1 1" "96 16 16 1 1" "112 112 128 1 1" "224 0 0 1 1" "256 16 256 1 2" "96 8 48 1 2" "112 24 384 0 2"; do
+    timeout 60 ./umma_probe $v
+  done ) 2>&1 | tee gpurun_out/a_probe.log
+for k in test_tile_layout_roundtrip test_conv_bit_exact_on_integers test_conv_many_tiles test_conv_random_values test_whole_tower; do
+  timeout 300 python -m pytest tests/test_gpu_tower.py -x -q -k $k 2>&1 | tail -15
+done 2>&1 | tee gpurun_out/a_tests.log
+timeout 600 python profiles/tower_bench.py --json gpurun_out/a_tower_bench.json 2>&1 | tail -60 | tee gpurun_out/a_bench.log

@@ -1,0 +1,113 @@
+"""Times the hand-written tower (csrc/hz_tower.cu) against the cuDNN tower on the same box:
+per 3x3 residual convolution and for the whole stem + 8-block tower, at the self-play batch
+(4,096 boards) and a 4x batch.  CUDA events on the launching stream, warm-up, L2 flushed between
+timed iterations for the single-layer numbers (the whole tower's working set exceeds nothing: its
+activations live in L2 in both implementations, which is the regime self-play runs in).
+
+usage: python profiles/tower_bench.py [--boards 4096] [--iters 20] [--json out.json]
+"""
+
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from harmonies_alphazero_b200 import net as hnet  # noqa: E402
+
+
+def timeit(fn, iters, flush=None):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e3)
+    ts.sort()
+    return {"us_min": ts[0], "us_med": ts[len(ts) // 2]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--boards", type=int, default=4096)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--json", default=None)
+    a = ap.parse_args()
+    torch.manual_seed(0)
+    model = hnet.AlphaZeroNet.from_config(hnet.DEFAULT_MODEL_CONFIG).eval()
+    hand = hnet.InferenceNet(model, tower="hand")
+    lib = hnet.InferenceNet(model, tower="cudnn")
+    B = a.boards
+    board = torch.zeros((B, 40, 5, 7), dtype=torch.bfloat16, device="cuda").contiguous(memory_format=torch.channels_last)
+    board[:, :38] = (torch.rand((B, 38, 5, 7), device="cuda") < 0.15).to(torch.bfloat16)
+    glob = torch.rand((B, 42), device="cuda").to(torch.bfloat16)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    out = {"boards": B, "gpu": torch.cuda.get_device_name(0)}
+    dense_flop = 2.0 * B * 35 * 9 * 128 * 128
+    # one residual convolution (128 -> 128, residual + ReLU)
+    ht = hand.hand
+    n_pad = (B + 15) // 16 * 16
+    buf = ht._buffers(n_pad)
+    hand.tower_out(board)      # fills the tile buffers with real activations
+    c1, c2 = ht.blocks[0]
+    r = timeit(lambda: ht.conv(buf["a"], 2, c2, buf["b"], buf["c"], n_pad), a.iters, flush)
+    r["dense_equiv_tflops"] = dense_flop / r["us_min"] / 1e6
+    r["executed_tflops"] = dense_flop * 247 / 315 / r["us_min"] / 1e6
+    out["hand_conv_l2_flushed"] = r
+    r = timeit(lambda: ht.conv(buf["a"], 2, c2, buf["b"], buf["c"], n_pad), a.iters)
+    r["dense_equiv_tflops"] = dense_flop / r["us_min"] / 1e6
+    out["hand_conv_warm"] = r
+    x = lib.tower_out(board)
+    r = timeit(lambda: lib._conv_relu(x, lib.blocks[0][1], 1, residual=x), a.iters, flush)
+    r["dense_equiv_tflops"] = dense_flop / r["us_min"] / 1e6
+    out["cudnn_conv_l2_flushed"] = r
+    r = timeit(lambda: lib._conv_relu(x, lib.blocks[0][1], 1, residual=x), a.iters)
+    r["dense_equiv_tflops"] = dense_flop / r["us_min"] / 1e6
+    out["cudnn_conv_warm"] = r
+    # whole tower and whole forward (tower + heads), CUDA graph replay like self-play
+    for name, net in (("hand", hand), ("cudnn", lib)):
+        logits = torch.zeros((B, 143), dtype=torch.float32, device="cuda")
+        value = torch.zeros(B, dtype=torch.float32, device="cuda")
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                net(board, glob, out=(logits, value))
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            net(board, glob, out=(logits, value))
+        r = timeit(g.replay, a.iters)
+        r["net_tflops"] = hnet.flops_per_position() * B / r["us_min"] / 1e6
+        out[name + "_forward_graph"] = r
+        gt = torch.cuda.CUDAGraph()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            net.tower_out(board)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(gt):
+            net.tower_out(board)
+        out[name + "_tower_graph"] = timeit(gt.replay, a.iters)
+    lh, vh = hand(board, glob)
+    ll, vl = lib(board, glob)
+    out["max_logit_diff_hand_vs_cudnn"] = float((lh - ll).abs().max())
+    out["max_value_diff_hand_vs_cudnn"] = float((vh - vl).abs().max())
+    print(json.dumps(out, indent=1))
+    if a.json:
+        with open(a.json, "w") as f:
+            json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,191 @@
+"""GPU tests of the hand-written sm_100a residual tower (csrc/hz_tower.cu)
+through the C ABI.
+
+* exact: with small-integer activations / weights every fp32 partial sum is an integer below
+  2^24, so tcgen05 accumulation order cannot matter and the bf16 outputs must equal
+  RNE(conv2d) BIT FOR BIT — for the stem shape (one 64-channel half), the residual shape (two
+  halves), with and without residual / ReLU, in both output layouts, and with many tiles pushed
+  through few CTAs (ring, tile-buffer and TMEM-unit phase wrap-around).
+* model: the whole tower against the cuDNN path of InferenceNet (same folded bf16 weights) and the
+  fp32 reference architecture (model.py:325-357), at bf16 tolerance (stated in the test).
+"""
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tw():
+    from harmonies_alphazero_b200 import _lib, tower
+
+    _lib.load()
+    return tower
+
+
+class _Raw:
+    """HandTower plumbing without a model: buffers + ctypes calls."""
+
+    def __init__(self, tower):
+        self.t = tower.HandTower.__new__(tower.HandTower)
+        self.t.device = torch.device("cuda")
+        from harmonies_alphazero_b200 import _lib
+
+        self.t.lib = _lib.load()
+        self.t._bufs = {}
+        self.t.fault = None
+        self.tower = tower
+
+    def tiles(self, x_nchw):
+        """bf16 [B,C,5,7] -> T16 tiles (C <= 64: one half, else two)"""
+        B, C = x_nchw.shape[:2]
+        halves = 1 if C <= 64 else 2
+        n_pad = (B + 15) // 16 * 16
+        nhwc = x_nchw.permute(0, 2, 3, 1).contiguous()
+        dst = torch.zeros(n_pad // 16 * halves * self.tower.KH_BYTES, dtype=torch.uint8, device="cuda")
+        self.t.to_tiles(nhwc, C, halves, dst)
+        return dst, halves, n_pad
+
+    def conv(self, x_nchw, w, bias, res_nchw=None, relu=True, out_nhwc=False):
+        B = x_nchw.shape[0]
+        xt, halves, n_pad = self.tiles(x_nchw)
+        img, nkh = self.tower.pack_conv_weight(w)
+        assert nkh == halves
+        rt = None if res_nchw is None else self.tiles(res_nchw)[0]
+        if out_nhwc:
+            y = torch.zeros((n_pad, 35, 128), dtype=torch.bfloat16, device="cuda")
+        else:
+            y = torch.zeros(n_pad // 16 * 2 * self.tower.KH_BYTES, dtype=torch.uint8, device="cuda")
+        self.t.conv(xt, halves, (img.cuda(), bias.float().cuda(), nkh), rt, y, n_pad, relu=relu, out_nhwc=out_nhwc)
+        torch.cuda.synchronize()
+        out = y if out_nhwc else self.t.from_tiles(y, n_pad)
+        return out[:B].view(B, 5, 7, 128).permute(0, 3, 1, 2)
+
+
+def _ref(x, w, bias, res, relu):
+    y = F.conv2d(x.double().cpu(), w.double().cpu(), bias.double().cpu(), padding=1)
+    if res is not None:
+        y = y + res.double().cpu()
+    if relu:
+        y = torch.relu(y)
+    return y.float().to(torch.bfloat16)
+
+
+def _ints(shape, lo, hi, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(lo, hi + 1, shape, generator=g).float()
+
+
+def test_tile_layout_roundtrip(tw):
+    raw = _Raw(tw)
+    x = _ints((37, 128, 5, 7), -3, 3, 1).to(torch.bfloat16).cuda()
+    xt, halves, n_pad = raw.tiles(x)
+    back = raw.t.from_tiles(xt, 37).view(37, 5, 7, 128).permute(0, 3, 1, 2)
+    assert torch.equal(back, x)
+    # the documented address of an element: row = cell*16 + board, group g at g ^ (row & 7)
+    img = xt.cpu().numpy()
+    xs = x.cpu()
+    for (b, c, y, xx) in [(0, 0, 0, 0), (5, 77, 3, 4), (36, 127, 4, 6), (17, 64, 2, 1)]:
+        tile, bb, cell = b // 16, b % 16, y * 7 + xx
+        rr = cell * 16 + bb
+        off = (tile * 2 + c // 64) * tw.KH_BYTES + rr * 128 + ((((c % 64) // 8) ^ (rr & 7)) << 4) + (c % 8) * 2
+        got = torch.from_numpy(img[off:off + 2].copy()).view(torch.bfloat16)[0]
+        assert got == xs[b, c, y, xx]
+
+
+@pytest.mark.parametrize("cin,boards,res,relu,nhwc", [
+    (128, 16, False, True, False),
+    (128, 16, True, True, False),
+    (128, 48, True, False, True),
+    (40, 16, False, True, False),
+    (40, 33, False, True, True),
+    (128, 16 * 9 + 5, True, True, False),
+])
+def test_conv_bit_exact_on_integers(tw, cin, boards, res, relu, nhwc):
+    raw = _Raw(tw)
+    x = _ints((boards, cin, 5, 7), -2, 2, 10 + boards).to(torch.bfloat16).cuda()
+    w = _ints((128, cin, 3, 3), -1, 1, 20 + cin)
+    bias = _ints((128,), -4, 4, 30)
+    r = _ints((boards, 128, 5, 7), -8, 8, 40).to(torch.bfloat16).cuda() if res else None
+    got = raw.conv(x, w, bias, r, relu=relu, out_nhwc=nhwc)
+    want = _ref(x, w, bias, r, relu)
+    assert torch.equal(got.cpu(), want), f"max abs diff {(got.cpu().float() - want.float()).abs().max()}"
+
+
+def test_conv_many_tiles_through_few_ctas(tw):
+    """23 tiles through 3 CTAs: every ring / buffer / TMEM-unit barrier wraps its phase several times."""
+    raw = _Raw(tw)
+    raw.t.lib.hz_tower_set_max_ctas(3)
+    try:
+        boards = 16 * 23
+        x = _ints((boards, 128, 5, 7), -2, 2, 5).to(torch.bfloat16).cuda()
+        w = _ints((128, 128, 3, 3), -1, 1, 6)
+        bias = _ints((128,), -4, 4, 7)
+        r = _ints((boards, 128, 5, 7), -8, 8, 8).to(torch.bfloat16).cuda()
+        got = raw.conv(x, w, bias, r)
+        assert torch.equal(got.cpu(), _ref(x, w, bias, r, True))
+    finally:
+        raw.t.lib.hz_tower_set_max_ctas(0)
+
+
+def test_conv_random_values_bf16_tolerance(tw):
+    """Real-valued data: fp32 accumulation order differs from the reference's, so the bound is one
+    bf16 rounding of the output (2^-8 relative) plus fp32 accumulation noise."""
+    raw = _Raw(tw)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((64, 128, 5, 7), generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn((128, 128, 3, 3), generator=g) * 0.03).to(torch.bfloat16).float()
+    bias = torch.randn((128,), generator=g)
+    r = torch.randn((64, 128, 5, 7), generator=g).to(torch.bfloat16).cuda()
+    got = raw.conv(x, w, bias, r).float().cpu()
+    y = F.conv2d(x.double().cpu(), w.double(), bias.double(), padding=1) + r.double().cpu()
+    want = torch.relu(y).float()
+    err = (got - want).abs()
+    assert float((err - want.abs() * 2.0 ** -8).max()) <= 1e-3
+
+
+def test_whole_tower_against_cudnn_and_fp32(tw):
+    from harmonies_alphazero_b200 import net as hnet
+
+    torch.manual_seed(0)
+    model = hnet.AlphaZeroNet.from_config(hnet.DEFAULT_MODEL_CONFIG).eval()
+    # non-trivial BatchNorm statistics so that folding is exercised
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.1)
+    B = 100
+    g = torch.Generator().manual_seed(1)
+    board = (torch.rand((B, 38, 5, 7), generator=g) < 0.15).float()
+    glob = torch.rand((B, 42), generator=g)
+    with torch.no_grad():
+        ref_logits, ref_value = model(board, glob)
+    hand = hnet.InferenceNet(model, device="cuda", tower="hand")
+    lib = hnet.InferenceNet(model, device="cuda", tower="cudnn")
+    b40 = torch.zeros((B, 40, 5, 7), dtype=torch.bfloat16, device="cuda").contiguous(memory_format=torch.channels_last)
+    b40[:, :38] = board.cuda().to(torch.bfloat16)
+    gl = glob.cuda().to(torch.bfloat16)
+    lh, vh = hand(b40, gl)
+    ll, vl = lib(b40, gl)
+    torch.cuda.synchronize()
+    # both bf16 paths differ from the fp32 reference by bf16 rounding of 17 layers of activations;
+    # they must agree with each other at least as well as cuDNN agrees with fp32
+    e_lib = float((ll.cpu() - ref_logits).abs().max())
+    e_hand = float((lh.cpu() - ref_logits).abs().max())
+    scale = float(ref_logits.abs().max())
+    assert e_hand <= max(2.0 * e_lib, 0.02 * scale), (e_hand, e_lib, scale)
+    assert float((vh.cpu() - ref_value.view(-1)).abs().max()) <= max(2.0 * float((vl.cpu() - ref_value.view(-1)).abs().max()), 0.02)
+    # tower outputs themselves
+    xh = hand.tower_out(b40).float().cpu()
+    xl = lib.tower_out(b40).float().cpu()
+    with torch.no_grad():
+        x = F.relu(model.bn(model.conv(board)))
+        for blk in model.residual_blocks:
+            x = blk(x)
+    tol = 0.03 * float(x.abs().max())
+    assert float((xh - x).abs().max()) <= tol and float((xl - x).abs().max()) <= tol
