@@ -64,8 +64,12 @@ def play_match(candidate_net, best_net, num_games, mcts_config_eval, device="cud
             if bool(over.all()):
                 break
             live = ~over.bool()
-            # all live games of a group are in lockstep: same player to move
-            mover = int(((states[live][:, 22] >> 24) & 1)[0].item())
+            # all live games of a group are in lockstep (fresh standard games: every game has
+            # taken the same number of actions): same player to move
+            movers = (states[live][:, 22] >> 24) & 1
+            mover = int(movers[0].item())
+            if not bool((movers == mover).all()):
+                raise RuntimeError("arena games of one group are out of lockstep (different players to move)")
             net = candidate_net if mover == g else best_net
             if net is GREEDY:                                        # evaluation.py:137-196, one kernel
                 actions = hb.greedy_actions(states)
@@ -75,7 +79,7 @@ def play_match(candidate_net, best_net, num_games, mcts_config_eval, device="cud
             actions = torch.where(live, actions, torch.full_like(actions, -1))
             hb.apply(states, actions)
         if tree is not None:
-            tree.check_status()
+            tree.check_status()          # status is sticky across resets: covers every search of the match
         over, oc = hb.outcome(states)
         if not bool(over.all()):
             raise RuntimeError("arena game did not finish")

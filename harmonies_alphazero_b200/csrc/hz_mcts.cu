@@ -95,7 +95,10 @@ __global__ void __launch_bounds__(TTPB) k_tree_reset(hz_tree T, const uint4* roo
     v.table[h & (uint64_t)(T.table_size - 1)] = 1;
     v.table_hash[h & (uint64_t)(T.table_size - 1)] = h;
     for (int j = 0; j < T.leaves; j++) { T.depth[t * T.leaves + j] = 0; T.leaf[t * T.leaves + j] = 0; }
-    T.sim[t] = 0; T.n_nodes[t] = 1; T.n_edges[t] = 0; T.status[t] = 0;
+    T.sim[t] = 0; T.n_nodes[t] = 1; T.n_edges[t] = 0;
+    // a reset starts a new search but must not erase the record of a truncated one: the flags of
+    // the search that ends here move to the sticky high nibble (cleared only by hz_tree_create)
+    { uint8_t s8 = T.status[t]; T.status[t] = (uint8_t)((s8 & 0xF0u) | ((s8 & 0x0Fu) << 4)); }
     // default key: a stream of its own per (game, move), independent of the game's draw stream
     T.search_key[t] = keys ? keys[t] : rand64(key_of(s) ^ HZ_SEARCH_SALT, (uint64_t)s.w[HZ_W_MOVES]);
 }

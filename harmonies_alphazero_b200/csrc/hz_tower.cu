@@ -6,11 +6,19 @@
 //   * tcgen05.mma, M = 128 output channels (A = one tap's weight tile, K-major SWIZZLE_128B),
 //     N = board positions (B = a window of the activation tile, K-major SWIZZLE_128B), accumulators
 //     in TMEM: lane = output channel, column = position.
-//   * activations live in HBM as 16-board tiles, cell-major: row (cell*16 + board) of 128 bytes per
-//     64-channel half ("T16" layout, already in the shared-memory swizzle so that one bulk copy
-//     (TMA, cp.async.bulk) brings a tile in).  With cells outermost a tap is a shift by whole
-//     cells: the B operand of tap (dy,dx) for output board-row r is the SAME resident tile read
-//     through a descriptor whose start address moved by ((r+dy)*7 + max(dx,0)) cells.
+//   * activations live in HBM as 16-board tiles in exactly the byte image the tensor core reads
+//     from shared memory, so one bulk copy (TMA, cp.async.bulk) brings a tile half in.  Positions
+//     are cell-major: p = cell*16 + board.  Two images exist:
+//       T16  (every layer's output, the residual convolutions' input): MN-major, no swizzle —
+//            8-channel group kg at kg*8960 bytes, inside it 8-position group pg at pg*128, inside
+//            that a core matrix [8 channels][8 positions] with positions contiguous.  An epilogue
+//            thread owns one output channel and therefore writes 16 boards of a cell as two
+//            16-byte vectors (and reads the residual the same way).
+//       T16K (the stem's input, written by the leaf encoder 8 channels = 16 bytes at a time):
+//            K-major SWIZZLE_128B, row p of 128 bytes = 64 channels, group g at g ^ (p & 7).
+//     With cells outermost a tap is a shift by whole cells: the B operand of tap (dy,dx) for
+//     output board-row r is the SAME resident tile read through a descriptor whose start address
+//     moved by ((r+dy)*7 + max(dx,0)) cells.
 //   * taps that fall off the 5x7 board are never multiplied: rows with r+dy outside 0..4 skip the
 //     tap, and a dx = -1 / +1 tap covers only the six cells x = 1..6 / 0..5 (N = 96 instead of 112,
 //     accumulator window moved by 16 columns).  Executed MACs = 247/315 of a zero-padded conv.
@@ -35,7 +43,8 @@ using namespace hz::sm100;
 constexpr int G = 16;                          // boards per tile
 constexpr int CELLS = 35, BROWS = 5, BCOLS = 7;
 constexpr int TILE_ROWS = CELLS * G;           // 560 rows of 128 bytes per channel half
-constexpr int KH_BYTES = TILE_ROWS * 128;      // 71,680
+constexpr int KH_BYTES = TILE_ROWS * 128;      // 71,680: one 64-channel half of a tile (either image)
+constexpr int KG_BYTES = (TILE_ROWS / 8) * 128; // 8,960: one 8-channel group of a T16 tile (70 position groups)
 constexpr int ROW_BYTES = BCOLS * G * 128;     // 14,336: one board row of one channel half
 constexpr int W_BYTES = 128 * 128;             // 16,384: [128 out][64 in] bf16
 constexpr int NSTAGE = 5;
@@ -55,26 +64,121 @@ constexpr int B_WFULL = 0, B_WEMPTY = NSTAGE, B_AFULL = 2 * NSTAGE, B_AEMPTY = 2
 // pass 0 (rows 0,1,2): dy = +1, 0, -1  -> row 0 (no dy = -1) completes after two thirds of the pass
 // pass 1 (rows 3,4)  : dy = -1, 0, +1  -> row 4 (no dy = +1) completes after two thirds of the pass
 __constant__ int8_t TAP_ORDER[2][9] = {{7, 6, 8, 4, 3, 5, 1, 0, 2}, {1, 0, 2, 4, 3, 5, 7, 6, 8}};
-__constant__ int8_t LAST_TAP[5] = {5, 2, 2, 8, 5};   // last tap (in its pass's order) that touches row r
 __constant__ int8_t EPI_ORDER[5] = {0, 1, 2, 4, 3};  // order in which the row accumulators complete
 // accumulator unit of board row r and how many times the unit has been used before (tile iteration it)
 __device__ __forceinline__ int unit_of(int r) { return r == 4 ? 0 : r; }
 __device__ __forceinline__ int use_of(int r, int it) { return r == 0 ? 2 * it : r == 4 ? 2 * it + 1 : it; }
 
 struct Params {
-    const uint8_t* x;      // input tiles  [n_tiles][nkh][560][128 B]
+    const uint8_t* x;      // input tiles: T16 [n_tiles][nkh*8 groups][8960 B] or T16K [n_tiles][nkh][560][128 B]
     const uint8_t* w;      // weight tiles [9][nkh][128][128 B]
     const float* bias;     // [128]
-    const uint8_t* res;    // residual tiles [n_tiles][2][560][128 B] or null
-    uint8_t* y;            // output: T16 tiles (2 halves) or NHWC [n_boards][35][128]
-    int n_tiles, nkh, relu, out_nhwc;
+    const uint8_t* res;    // residual, T16 tiles (2 halves), or null
+    uint8_t* y;            // output, T16 tiles (2 halves)
+    int n_tiles, nkh, relu, in_kmajor;
+    int dbg;               // profiling only (hz_tower_set_debug): 1 skip MMAs, 2 skip epilogue memory traffic, 4 skip weight copies, 8 skip activation copies
     unsigned int* fault;
 };
 
-__device__ __forceinline__ uint32_t t16_offset(int rr, int c) {   // byte offset of (row rr, channel c) inside a tile (2 halves)
-    return (uint32_t)(c >> 6) * KH_BYTES + (uint32_t)rr * 128u + ((uint32_t)(((c & 63) >> 3) ^ (rr & 7)) << 4) + (uint32_t)(c & 7) * 2u;
+// B operand, MN-major without swizzle: core matrices of [8 channels][8 positions]; LBO = stride
+// between 8-channel groups (K direction), SBO = stride between 8-position groups (N direction)
+__device__ __forceinline__ uint64_t smem_desc_t16(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((KG_BYTES >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((128 >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
 }
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---- MMA issue, fully unrolled -------------------------------------------------------------------
+// One thread issues ~312 MMAs of ~50 tensor-core cycles each per tile, so the issue path has to be
+// a handful of instructions per MMA: the whole warp runs the (warp-uniform) control flow, taps /
+// rows / k-steps are compile-time, descriptors are a 32-bit add on a precomputed low word, and only
+// the tcgen05 instructions themselves sit behind elect.sync.
+__host__ __device__ constexpr int tap_at(int pass, int ti) {
+    constexpr int O[2][9] = {{7, 6, 8, 4, 3, 5, 1, 0, 2}, {1, 0, 2, 4, 3, 5, 7, 6, 8}};
+    return O[pass][ti];
+}
+__host__ __device__ constexpr int last_tap_of(int r) {
+    constexpr int L[5] = {5, 2, 2, 8, 5};
+    return L[r];
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// descriptor words: hi is constant per operand kind, lo = encoded start address (+ LBO field)
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024, version 1, SWIZZLE_128B
+constexpr uint32_t DESC_LO_SW128 = 1u << 16;                                  // LBO field (unused) = 1
+constexpr uint32_t DESC_HI_T16 = (128u >> 4) | (1u << 14);                    // SBO 128, version 1, no swizzle
+constexpr uint32_t DESC_LO_T16 = (uint32_t)(KG_BYTES >> 4) << 16;             // LBO = 8-channel group stride
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+// the MMAs of one weight stage (tap, channel half): 4 k-steps x the rows of the pass the tap touches
+template <bool KMAJOR, int PASS, int TI>
+__device__ __forceinline__ void issue_stage(uint32_t a_lo, uint32_t b_lo, uint32_t tbase, uint32_t acc_first) {
+    constexpr int tap = tap_at(PASS, TI), dy = tap / 3 - 1, dx = tap % 3 - 1;
+    constexpr int r0 = PASS ? 3 : 0, r1 = PASS ? 5 : 3;
+    constexpr uint32_t idesc = idesc_bf16_f32(128, dx ? 96 : 112) | (KMAJOR ? 0u : (1u << 16));
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int r = r0; r < r1; r++) {
+            const int sr = r + dy;
+            if (sr < 0 || sr >= BROWS) continue;
+            const int cell0 = sr * BCOLS + (dx > 0 ? 1 : 0);
+            const uint32_t boff = KMAJOR ? (uint32_t)((cell0 * (G * 128) + k * 32) >> 4) : (uint32_t)((k * 2 * KG_BYTES + cell0 * (G * 16)) >> 4);
+            const uint32_t d = tbase + (uint32_t)(unit_of(r) * UNIT_COLS + (dx < 0 ? G : 0));
+            umma_bf16(d, desc64(a_lo + (uint32_t)(k * 2), DESC_HI_SW128), desc64(b_lo + boff, KMAJOR ? DESC_HI_SW128 : DESC_HI_T16), idesc,
+                      (TI == 0 && k == 0) ? acc_first : 1u);
+        }
+    }
+}
+
+template <bool KMAJOR, int PASS, int TI>
+struct StageLoop {
+    // runs stages TI..8 of a pass for one channel half
+    template <class Ctx>
+    static __device__ __forceinline__ void run(Ctx& c, int kh, int it, bool last_kh) {
+        constexpr int tap = tap_at(PASS, TI);
+        constexpr int r0 = PASS ? 3 : 0, r1 = PASS ? 5 : 3;
+        mbar_wait(c.bar0 + 8u * (B_WFULL + c.stage), c.ph, c.fault, 0x400 + c.stage);
+        if (TI == 0 && kh == 0) {       // first touch of the pass's accumulators for this tile: previous tenants must be drained
+#pragma unroll
+            for (int r = r0; r < r1; r++) mbar_wait(c.bar0 + 8u * (B_TEMPTY + unit_of(r)), (use_of(r, it) & 1) ^ 1, c.fault, 0x500 + r);
+        }
+        tc_fence_after();
+        if (elect_one()) {
+            const uint32_t a_lo = DESC_LO_SW128 | ((c.sW + c.stage * W_BYTES) >> 4);
+            const uint32_t b_lo = (KMAJOR ? DESC_LO_SW128 : DESC_LO_T16) | ((c.sX + (uint32_t)kh * KH_BYTES) >> 4);
+            if (!(c.dbg & 1)) issue_stage<KMAJOR, PASS, TI>(a_lo, b_lo, c.tbase, kh == 0 ? 0u : 1u);
+            umma_commit(c.bar0 + 8u * (B_WEMPTY + c.stage));      // frees the weight stage when these MMAs have read it
+            if (last_kh) {
+#pragma unroll
+                for (int r = r0; r < r1; r++)
+                    if (tap == last_tap_of(r)) umma_commit(c.bar0 + 8u * (B_TFULL + unit_of(r)));
+            }
+        }
+        __syncwarp();
+        if (++c.stage == NSTAGE) { c.stage = 0; c.ph ^= 1; }
+        if constexpr (TI < 8) StageLoop<KMAJOR, PASS, TI + 1>::run(c, kh, it, last_kh);
+    }
+};
+
+struct IssueCtx {
+    uint32_t bar0, sW, sX, tbase, stage, ph;
+    unsigned int* fault;
+    int dbg;
+};
+
+template <bool KMAJOR>
 __global__ void __launch_bounds__(NTHREADS, 1) k_conv3x3(Params P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -106,8 +210,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv3x3(Params P) {
                     for (int ti = 0; ti < 9; ti++) {
                         int tap = TAP_ORDER[pass][ti];
                         mbar_wait(bar(B_WEMPTY + stage), ph ^ 1, P.fault, 0x100 + stage);
-                        mbar_expect_tx(bar(B_WFULL + stage), W_BYTES);
-                        bulk_g2s(sW + stage * W_BYTES, P.w + (size_t)(tap * nkh + kh) * W_BYTES, W_BYTES, bar(B_WFULL + stage));
+                        if (P.dbg & 4) mbar_arrive(bar(B_WFULL + stage));
+                        else {
+                            mbar_expect_tx(bar(B_WFULL + stage), W_BYTES);
+                            bulk_g2s(sW + stage * W_BYTES, P.w + (size_t)(tap * nkh + kh) * W_BYTES, W_BYTES, bar(B_WFULL + stage));
+                        }
                         if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
                     }
     } else if (warp == 2 && lane == 0) {
@@ -116,87 +223,78 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv3x3(Params P) {
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, it++)
             for (int kh = 0; kh < nkh; kh++) {
                 mbar_wait(bar(B_AEMPTY + kh), (it & 1) ^ 1, P.fault, 0x200 + kh);
+                if (P.dbg & 8) { mbar_arrive(bar(B_AFULL + kh)); continue; }
                 mbar_expect_tx(bar(B_AFULL + kh), KH_BYTES);
                 const uint8_t* src = P.x + ((size_t)tile * nkh + kh) * KH_BYTES;
                 for (int r = 0; r < BROWS; r++)
                     bulk_g2s(sX + kh * KH_BYTES + r * ROW_BYTES, src + (size_t)r * ROW_BYTES, ROW_BYTES, bar(B_AFULL + kh));
             }
-    } else if (warp == 1 && lane == 0) {
-        // ---- MMA issuer ----
-        const uint32_t idesc112 = idesc_bf16_f32(128, 112), idesc96 = idesc_bf16_f32(128, 96);
-        uint32_t stage = 0, ph = 0;
+    } else if (warp == 1) {
+        // ---- MMA issuer: the whole warp runs the loop, one elected lane issues ----
+        IssueCtx c{sBar, sW, sX, tbase, 0u, 0u, P.fault, P.dbg};
         int it = 0;
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, it++) {
-            uint32_t started = 0;                                  // rows whose accumulator holds this tile's sums
-            for (int pass = 0; pass < 2; pass++) {
-                const int r0 = pass ? 3 : 0, r1 = pass ? 5 : 3;
-                for (int kh = 0; kh < nkh; kh++) {
-                    if (pass == 0) mbar_wait(bar(B_AFULL + kh), it & 1, P.fault, 0x300 + kh);
-                    for (int ti = 0; ti < 9; ti++) {
-                        const int tap = TAP_ORDER[pass][ti];
-                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                        mbar_wait(bar(B_WFULL + stage), ph, P.fault, 0x400 + stage);
-                        tc_fence_after();
-                        const uint32_t wa = sW + stage * W_BYTES;
-                        const uint32_t idesc = dx ? idesc96 : idesc112;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const uint64_t da = smem_desc_sw128(wa + k * 32);
-                            for (int r = r0; r < r1; r++) {
-                                const int sr = r + dy;
-                                if (sr < 0 || sr >= BROWS) continue;
-                                const int unit = unit_of(r);
-                                if (!((started >> r) & 1u)) {       // first use of the unit for this row: the previous tenant must be drained
-                                    mbar_wait(bar(B_TEMPTY + unit), (use_of(r, it) & 1) ^ 1, P.fault, 0x500 + unit);
-                                    tc_fence_after();
-                                }
-                                const uint32_t cell0 = (uint32_t)(sr * BCOLS + (dx > 0 ? 1 : 0));
-                                const uint64_t db = smem_desc_sw128(sX + kh * KH_BYTES + cell0 * (G * 128) + k * 32);
-                                const uint32_t d = tbase + unit * UNIT_COLS + (dx < 0 ? G : 0);
-                                umma_bf16(d, da, db, idesc, (started >> r) & 1u);
-                                started |= 1u << r;
-                            }
-                        }
-                        umma_commit(bar(B_WEMPTY + stage));        // frees the weight stage when these MMAs have read it
-                        if (kh == nkh - 1)
-                            for (int r = r0; r < r1; r++)
-                                if (tap == LAST_TAP[r]) umma_commit(bar(B_TFULL + unit_of(r)));
-                        if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
-                    }
-                    if (pass == 1) umma_commit(bar(B_AEMPTY + kh));   // the tile's channel half is no longer read
-                }
+            for (int kh = 0; kh < nkh; kh++) {
+                mbar_wait(bar(B_AFULL + kh), it & 1, P.fault, 0x300 + kh);
+                StageLoop<KMAJOR, 0, 0>::run(c, kh, it, kh == nkh - 1);
+            }
+            for (int kh = 0; kh < nkh; kh++) {
+                StageLoop<KMAJOR, 1, 0>::run(c, kh, it, kh == nkh - 1);
+                if (elect_one()) umma_commit(bar(B_AEMPTY + kh));   // the tile's channel half is no longer read
+                __syncwarp();
             }
         }
-        umma_commit(bar(B_DONE));
+        if (elect_one()) umma_commit(bar(B_DONE));
+        __syncwarp();
         mbar_wait(bar(B_DONE), 0, P.fault, 0x600);
     } else if (warp >= 4) {
-        // ---- epilogue: thread = output channel; 16 boards of one cell per TMEM load ----
+        // ---- epilogue: thread = output channel c; one TMEM load = the 16 boards of a cell, which are
+        // 2 x 16 contiguous bytes of channel c's row in the T16 image (vector stores, vector residual loads)
         const int q = warp & 3, c = q * 32 + lane;
         const float bias = P.bias[c];
+        const uint32_t chan_off = (uint32_t)(c >> 3) * KG_BYTES + (uint32_t)(c & 7) * 16u;
         int it = 0;
         for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, it++) {
-            const size_t tile_off = (size_t)tile * 2 * KH_BYTES;
+            const size_t tile_off = (size_t)tile * 2 * KH_BYTES + chan_off;
             for (int ri = 0; ri < BROWS; ri++) {
                 const int r = EPI_ORDER[ri], unit = unit_of(r);
+                // the residual of the whole board row is requested before the accumulator is waited for
+                uint4 rv[2 * BCOLS];
+                const bool mem = !(P.dbg & 2);
+                if (P.res && mem) {
+#pragma unroll
+                    for (int x = 0; x < BCOLS; x++) {
+                        const uint8_t* rp = P.res + tile_off + (size_t)(r * BCOLS + x) * (G * 16);
+                        rv[2 * x] = *reinterpret_cast<const uint4*>(rp);
+                        rv[2 * x + 1] = *reinterpret_cast<const uint4*>(rp + 128);
+                    }
+                }
                 mbar_wait(bar(B_TFULL + unit), use_of(r, it) & 1, P.fault, 0x700 + unit);
                 tc_fence_after();
+#pragma unroll
                 for (int x = 0; x < BCOLS; x++) {
                     uint32_t v[16];
                     tmem_ld16(tbase + ((uint32_t)(q * 32) << 16) + unit * UNIT_COLS + x * G, v);
                     tmem_ld_wait();
-                    const int cell = r * BCOLS + x;
+                    float o[16];
 #pragma unroll
-                    for (int b = 0; b < G; b++) {
-                        const int rr = cell * G + b;
-                        const uint32_t off = t16_offset(rr, c);
-                        float o = __uint_as_float(v[b]) + bias;
-                        if (P.res) o += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(P.res + tile_off + off));
-                        if (P.relu) o = fmaxf(o, 0.0f);
-                        if (P.out_nhwc)
-                            reinterpret_cast<__nv_bfloat16*>(P.y)[((size_t)(tile * G + b) * CELLS + cell) * 128 + c] = __float2bfloat16_rn(o);
-                        else
-                            *reinterpret_cast<__nv_bfloat16*>(P.y + tile_off + off) = __float2bfloat16_rn(o);
+                    for (int b = 0; b < G; b++) o[b] = __uint_as_float(v[b]) + bias;
+                    if (P.res && mem) {
+                        const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rv[2 * x]);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            o[2 * j] += __uint_as_float(rw[j] << 16);
+                            o[2 * j + 1] += __uint_as_float(rw[j] & 0xFFFF0000u);
+                        }
                     }
+                    if (P.relu) {
+#pragma unroll
+                        for (int b = 0; b < G; b++) o[b] = fmaxf(o[b], 0.0f);
+                    }
+                    uint8_t* yp = P.y + tile_off + (size_t)(r * BCOLS + x) * (G * 16);
+                    if (!mem) { if (o[0] + o[5] + o[10] + o[15] == 12345.678f) *reinterpret_cast<float*>(yp) = o[3]; continue; }
+                    *reinterpret_cast<uint4*>(yp) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+                    *reinterpret_cast<uint4*>(yp + 128) = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -209,40 +307,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv3x3(Params P) {
     if (warp == 3) tmem_dealloc(tbase, 512);
 }
 
-// ---- layout conversion (interop with NHWC tensors: tests, the leaf encoder's output) ------------
-// src [n][35][C] bf16 (C % 8 == 0, C <= 64*nkh) -> tiles [n_pad/16][nkh][560][128 B]; pad boards/channels = 0
-__global__ void k_to_tiles(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t n, int C, int nkh, int64_t n_chunks) {
+// ---- layout conversion (interop with NHWC tensors: tests, the heads kernel) -----------------------
+// src [n][35][C] bf16 (C % 8 == 0, C <= 64) -> T16K tiles [n_pad/16][560][128 B]; pad boards/channels = 0
+__global__ void k_to_tiles_k(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t n, int C, int64_t n_chunks) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_chunks; i += (int64_t)gridDim.x * blockDim.x) {
         int j = (int)(i & 7);                       // chunk position inside the 128-byte row (swizzled)
-        int64_t row = i >> 3;                       // global row: ((tile*nkh + kh)*560 + rr)
-        int rr = (int)(row % TILE_ROWS);
-        int64_t tk = row / TILE_ROWS;
-        int kh = (int)(tk % nkh);
-        int64_t tile = tk / nkh;
-        int cell = rr / G, b = rr % G;
-        int chunk = j ^ (rr & 7);                   // logical 8-channel group stored at position j
-        int ch = kh * 64 + chunk * 8;
+        int64_t row = i >> 3;                       // tile*560 + p
+        int p = (int)(row % TILE_ROWS);
+        int64_t tile = row / TILE_ROWS;
+        int cell = p / G, b = p % G;
+        int ch = (j ^ (p & 7)) * 8;                 // logical 8-channel group stored at position j
         int64_t board = tile * G + b;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (board < n && ch < C) v = src[((board * CELLS + cell) * C + ch) >> 3];
         dst[i] = v;
     }
 }
-// tiles (2 halves) -> dst [n][35][128] bf16
-__global__ void k_from_tiles(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t n, int64_t n_chunks) {
+// src [n][35][128] bf16 -> T16 tiles (2 halves); one thread = 8 positions of one channel (a 16-byte chunk)
+__global__ void k_to_tiles(const __nv_bfloat16* __restrict__ src, uint4* __restrict__ dst, int64_t n, int64_t n_chunks) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_chunks; i += (int64_t)gridDim.x * blockDim.x) {
-        int g = (int)(i & 15);                      // 8-channel group of the NHWC row
-        int64_t pos = i >> 4;                       // board*35 + cell
+        int k8 = (int)(i & 7);
+        int64_t g = i >> 3;                         // (tile*16 + kg)*70 + pg
+        int pg = (int)(g % (TILE_ROWS / 8));
+        int64_t tk = g / (TILE_ROWS / 8);
+        int kg = (int)(tk & 15);
+        int64_t tile = tk >> 4;
+        int c = kg * 8 + k8;
+        uint32_t w[4];
+#pragma unroll
+        for (int h = 0; h < 4; h++) {
+            uint32_t two = 0;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                int p = pg * 8 + 2 * h + e, cell = p / G;
+                int64_t board = tile * G + p % G;
+                uint32_t bits = board < n ? (uint32_t)__bfloat16_as_ushort(src[(board * CELLS + cell) * 128 + c]) : 0u;
+                two |= bits << (16 * e);
+            }
+            w[h] = two;
+        }
+        dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+// T16 tiles (2 halves) -> dst [n][35][128] bf16; one thread = one output element pair
+__global__ void k_from_tiles(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n_elems) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i & 127);
+        int64_t pos = i >> 7;                       // board*35 + cell
         int cell = (int)(pos % CELLS);
         int64_t board = pos / CELLS;
-        int64_t tile = board / G;
-        int rr = cell * G + (int)(board % G);
-        int kh = g >> 3, chunk = g & 7;
-        size_t off = ((size_t)(tile * 2 + kh) * TILE_ROWS + rr) * 128 + (size_t)((chunk ^ (rr & 7)) << 4);
-        dst[i] = src[off >> 4];
+        int p = cell * G + (int)(board % G);
+        size_t off = (size_t)(board / G) * 2 * KH_BYTES + (size_t)(c >> 3) * KG_BYTES + (size_t)(p >> 3) * 128 + (c & 7) * 16 + (p & 7) * 2;
+        dst[i] = src[off >> 1];
     }
 }
 
+static int g_debug = 0;
 static int g_max_ctas = 0;   // 0 = one CTA per SM; tests lower it to drive several tiles through one CTA
 
 static int ensure_attr() {
@@ -250,7 +370,8 @@ static int ensure_attr() {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_conv3x3, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_conv3x3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv3x3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return hz_record_launch(0, e);
         if (dev >= 0 && dev < 64) done[dev] = true;
     }
@@ -273,31 +394,38 @@ int hz_tower_set_max_ctas(int max_ctas) {
     return HZ_OK;
 }
 
-int hz_tower_to_tiles(const void* src_nhwc, void* dst_tiles, int64_t n_boards, int channels, int channel_halves, void* stream) {
-    if (!src_nhwc || !dst_tiles || n_boards <= 0 || channels <= 0 || (channels & 7) || channel_halves < 1 || channel_halves > 2 ||
-        channels > 64 * channel_halves || ((uintptr_t)src_nhwc & 15) || ((uintptr_t)dst_tiles & 15))
-        return HZ_ERR_ARG;
+int hz_tower_set_debug(int flags) {
+    hz::tower::g_debug = flags;
+    return HZ_OK;
+}
+
+int hz_tower_to_tiles(const void* src_nhwc, void* dst_tiles, int64_t n_boards, int channels, int kmajor, void* stream) {
+    if (!src_nhwc || !dst_tiles || n_boards <= 0 || ((uintptr_t)src_nhwc & 15) || ((uintptr_t)dst_tiles & 15)) return HZ_ERR_ARG;
+    if (kmajor ? (channels <= 0 || (channels & 7) || channels > 64) : channels != 128) return HZ_ERR_ARG;
     int64_t tiles = (n_boards + hz::tower::G - 1) / hz::tower::G;
-    int64_t n_chunks = tiles * channel_halves * hz::tower::TILE_ROWS * 8;
+    int64_t n_chunks = tiles * (kmajor ? 1 : 2) * hz::tower::TILE_ROWS * 8;
     int grid = (int)((n_chunks + 255) / 256 < 148 * 16 ? (n_chunks + 255) / 256 : 148 * 16);
-    hz::tower::k_to_tiles<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)src_nhwc, (uint4*)dst_tiles, n_boards, channels,
-                                                                   channel_halves, n_chunks);
+    if (kmajor)
+        hz::tower::k_to_tiles_k<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)src_nhwc, (uint4*)dst_tiles, n_boards, channels, n_chunks);
+    else
+        hz::tower::k_to_tiles<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src_nhwc, (uint4*)dst_tiles, n_boards, n_chunks);
     return hz_launched(1);
 }
 
 int hz_tower_from_tiles(const void* src_tiles, void* dst_nhwc, int64_t n_boards, void* stream) {
     if (!src_tiles || !dst_nhwc || n_boards <= 0 || ((uintptr_t)src_tiles & 15) || ((uintptr_t)dst_nhwc & 15)) return HZ_ERR_ARG;
-    int64_t n_chunks = n_boards * hz::tower::CELLS * 16;
-    int grid = (int)((n_chunks + 255) / 256 < 148 * 16 ? (n_chunks + 255) / 256 : 148 * 16);
-    hz::tower::k_from_tiles<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)src_tiles, (uint4*)dst_nhwc, n_boards, n_chunks);
+    int64_t n_elems = n_boards * hz::tower::CELLS * 128;
+    int grid = (int)((n_elems + 255) / 256 < 148 * 32 ? (n_elems + 255) / 256 : 148 * 32);
+    hz::tower::k_from_tiles<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src_tiles, (__nv_bfloat16*)dst_nhwc, n_elems);
     return hz_launched(1);
 }
 
-int hz_tower_conv3x3(const void* x_tiles, int in_channel_halves, const void* w_tiles, const float* bias, const void* residual_tiles,
-                     void* y, int64_t n_boards, int relu, int out_nhwc, unsigned int* fault, void* stream) {
+int hz_tower_conv3x3(const void* x_tiles, int in_channel_halves, int in_kmajor, const void* w_tiles, const float* bias,
+                     const void* residual_tiles, void* y, int64_t n_boards, int relu, unsigned int* fault, void* stream) {
     using namespace hz::tower;
     if (!x_tiles || !w_tiles || !bias || !y || n_boards <= 0 || (n_boards % G) || in_channel_halves < 1 || in_channel_halves > 2)
         return HZ_ERR_ARG;
+    if (in_kmajor && in_channel_halves != 1) return HZ_ERR_ARG;
     if (((uintptr_t)x_tiles | (uintptr_t)w_tiles | (uintptr_t)y | (uintptr_t)residual_tiles) & 15) return HZ_ERR_ARG;
     int st = ensure_attr();
     if (st != HZ_OK) return st;
@@ -310,14 +438,16 @@ int hz_tower_conv3x3(const void* x_tiles, int in_channel_halves, const void* w_t
     P.n_tiles = (int)(n_boards / G);
     P.nkh = in_channel_halves;
     P.relu = relu;
-    P.out_nhwc = out_nhwc;
+    P.in_kmajor = in_kmajor;
     P.fault = fault;
+    P.dbg = g_debug;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_max_ctas > 0 && g_max_ctas < sms) sms = g_max_ctas;
     int grid = P.n_tiles < sms ? P.n_tiles : sms;
-    k_conv3x3<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    if (in_kmajor) k_conv3x3<true><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    else k_conv3x3<false><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(P);
     return hz_launched(1);
 }
 

@@ -298,6 +298,11 @@ class BatchedSelfPlay:
                 expl = (move_no < cfg.turns_until_tau0).to(torch.uint8)   # MCTS.py:399-402
                 u01 = torch.rand(B, device=dev, dtype=torch.float32)
             actions = self.choose(u01, expl)
+            # a root without visits (num_simulations <= leaves_per_step, or a search that only ever
+            # reached the unexpanded root) has no move to offer: the reference then plays a random
+            # legal move and records the all-zero visit vector (MCTS.py:382-392,425-433 — its uniform
+            # fallback is written into an int array and truncates to 0)
+            actions = torch.where(actions < 0, hb.random_actions(states), actions)
             actions = torch.where(live, actions, torch.full_like(actions, -1))
             status = hb.apply(states, actions)                   # the real move re-draws independently (trainer.py:502)
             bad_status = torch.maximum(bad_status, torch.where(live, status, torch.zeros_like(status)).max())

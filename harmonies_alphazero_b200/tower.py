@@ -19,7 +19,8 @@ KH_BYTES = 71680  # 560 rows x 128 bytes: one 64-channel half of a tile
 
 def pack_conv_weight(w):
     """[128, Cin, 3, 3] fp32 (BatchNorm folded) -> uint8 [9, nkh, 128, 128]: per tap (ky*3+kx) and
-    64-channel half a K-major SWIZZLE_128B tile of bf16 (16-byte group g stored at g ^ (out & 7))."""
+    64-channel half a K-major SWIZZLE_128B tile of bf16 (16-byte group g stored at g ^ (out & 7)):
+    the A operand of the tower's tcgen05.mma."""
     O, I = w.shape[0], w.shape[1]
     if O != 128 or w.shape[2:] != (3, 3):
         raise ValueError("hand-written tower needs 128 output channels and 3x3 kernels")
@@ -72,10 +73,11 @@ class HandTower:
                                          out=torch.zeros((n_pad, 35, 128), dtype=torch.bfloat16, device=self.device))
         return b
 
-    def to_tiles(self, src_nhwc, channels, halves, dst):
+    def to_tiles(self, src_nhwc, channels, kmajor, dst):
+        """NHWC bf16 -> T16K (kmajor, <= 64 channels: the stem input) or T16 (128 channels) tiles"""
         n = src_nhwc.shape[0]
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.hz_tower_to_tiles(src_nhwc.data_ptr(), dst.data_ptr(), n, channels, halves, self._stream()), "hz_tower_to_tiles")
+            _lib.check(self.lib.hz_tower_to_tiles(src_nhwc.data_ptr(), dst.data_ptr(), n, channels, 1 if kmajor else 0, self._stream()), "hz_tower_to_tiles")
 
     def from_tiles(self, src, n):
         out = torch.empty((n, 35, 128), dtype=torch.bfloat16, device=self.device)
@@ -83,13 +85,13 @@ class HandTower:
             _lib.check(self.lib.hz_tower_from_tiles(src.data_ptr(), out.data_ptr(), n, self._stream()), "hz_tower_from_tiles")
         return out
 
-    def conv(self, x, halves, wb, res, y, n_pad, relu=True, out_nhwc=False):
+    def conv(self, x, halves, wb, res, y, n_pad, relu=True, kmajor=False):
         img, bias, nkh = wb
         assert nkh == halves
         with torch.cuda.device(self.device):
             _lib.check(self.lib.hz_tower_conv3x3(
-                x.data_ptr(), halves, img.data_ptr(), bias.data_ptr(), None if res is None else res.data_ptr(), y.data_ptr(),
-                n_pad, 1 if relu else 0, 1 if out_nhwc else 0, self.fault, self._stream()), "hz_tower_conv3x3")
+                x.data_ptr(), halves, 1 if kmajor else 0, img.data_ptr(), bias.data_ptr(), None if res is None else res.data_ptr(),
+                y.data_ptr(), n_pad, 1 if relu else 0, self.fault, self._stream()), "hz_tower_conv3x3")
 
     @torch.no_grad()
     def forward(self, board, out=None):
@@ -103,17 +105,15 @@ class HandTower:
             raise ValueError("channel count of the board tensor must be a multiple of 8 (use the 40-plane leaf layout)")
         n_pad = (B + G - 1) // G * G
         buf = self._buffers(n_pad)
-        self.to_tiles(board, C, 1, buf["x0"])
+        self.to_tiles(board, C, True, buf["x0"])
         x, y, z = buf["a"], buf["b"], buf["c"]
         if out is None:
             out = buf["out"]       # static: the same addresses every call (CUDA graphs)
-        if not self.blocks:
-            self.conv(buf["x0"], 1, self.stem, None, out, n_pad, out_nhwc=True)
-        else:
-            self.conv(buf["x0"], 1, self.stem, None, x, n_pad)
-            for i, (c1, c2) in enumerate(self.blocks):
-                last = i == len(self.blocks) - 1
-                self.conv(x, 2, c1, None, y, n_pad)
-                self.conv(y, 2, c2, x, out if last else z, n_pad, out_nhwc=last)
-                x, z = z, x
+        self.conv(buf["x0"], 1, self.stem, None, x, n_pad, kmajor=True)
+        for c1, c2 in self.blocks:
+            self.conv(x, 2, c1, None, y, n_pad)
+            self.conv(y, 2, c2, x, z, n_pad)
+            x, z = z, x
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.hz_tower_from_tiles(x.data_ptr(), out.data_ptr(), n_pad, self._stream()), "hz_tower_from_tiles")
         return out[:B].view(B, 5, 7, 128).permute(0, 3, 1, 2)

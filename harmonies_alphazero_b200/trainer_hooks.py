@@ -8,6 +8,7 @@ replay buffer exactly the tuples it expects.
     trainer_hooks.install(trainer)                  # Trainer now self-plays on the B200
 """
 
+import random
 import time
 
 import torch
@@ -20,8 +21,16 @@ def _inference_net(model, device, dtype):
     return InferenceNet(model, device=device, dtype=dtype)
 
 
+def _fresh_seed():
+    """The reference draws every game's tiles from the global ``random`` module
+    (harmonies_engine.py:126), so consecutive phases never replay the same deals.  The batched
+    engine derives a game's draw stream from (seed, game id): take the seed from the same global
+    generator — fresh games every call, reproducible after ``random.seed(k)``."""
+    return random.getrandbits(63)
+
+
 def execute_self_play_phase(self, data_generating_manager, n_slots=4096, dtype=torch.bfloat16, device="cuda",
-                            leaves_per_step=1):
+                            leaves_per_step=1, seed=None):
     """Bound as a method of the reference ``Trainer``.  Same contract as trainer.py:62-134:
     plays ``num_games_per_iter`` games with the data-generating (best) model and extends
     ``self.replay_buffer`` with (board, global, pi, z) CPU tensors of every completed game.
@@ -36,7 +45,8 @@ def execute_self_play_phase(self, data_generating_manager, n_slots=4096, dtype=t
     model.eval()
     net = _inference_net(model, device, dtype)
     cfg = SelfPlayConfig.from_mcts_config(self.mcts_config, n_slots=max(1, min(n_slots, num_games)),
-                                          leaves_per_step=int(leaves_per_step))
+                                          leaves_per_step=int(leaves_per_step),
+                                          seed=_fresh_seed() if seed is None else int(seed))
     traj = BatchedSelfPlay(net, cfg, device=device).play(num_games)
     # a deque(maxlen) keeps only the tail of an extend: build just those examples
     examples = traj.to_reference_examples(last=getattr(self.replay_buffer, "maxlen", None))
@@ -61,14 +71,14 @@ def self_play_worker(args):
         model.eval()
         dev = "cuda" if str(worker_device) in ("cpu", "mps") else worker_device   # the engine is GPU-only
         net = _inference_net(model, dev, torch.float32)
-        cfg = SelfPlayConfig.from_mcts_config(mcts_config, n_slots=1, use_cuda_graph=False)
+        cfg = SelfPlayConfig.from_mcts_config(mcts_config, n_slots=1, use_cuda_graph=False, seed=_fresh_seed())
         return BatchedSelfPlay(net, cfg, device=dev).play(1).to_reference_examples()
     except Exception as e:  # noqa: BLE001  (the reference worker also returns [] on any failure, trainer.py:459-514)
         print(f"WORKER ERROR: {e}")
         return []
 
 
-def evaluate_model(self, dtype=torch.bfloat16, device="cuda", eval_config=None):
+def evaluate_model(self, dtype=torch.bfloat16, device="cuda", eval_config=None, seed=None):
     """Bound as a method of the reference ``Trainer``: the candidate-vs-best match of
     trainer.py:293-431 with all ``eval_episodes`` games played concurrently (arena.play_match:
     candidate is player 0 in even games, every move a fresh search by the side to move's
@@ -94,7 +104,8 @@ def evaluate_model(self, dtype=torch.bfloat16, device="cuda", eval_config=None):
         nets.append(_inference_net(mgr.model, device, dtype))
         if was_training:
             mgr.model.train()
-    res = arena.play_match(nets[0], nets[1], n_games, eval_config, device=device)
+    res = arena.play_match(nets[0], nets[1], n_games, eval_config, device=device,
+                           seed=_fresh_seed() if seed is None else int(seed))   # fresh deals per evaluation, like the reference
     decided = res["candidate_wins"] + res["best_wins"]
     win_rate = res["candidate_wins"] / decided if decided else 0.5
     res["win_rate"] = win_rate

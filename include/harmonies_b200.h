@@ -270,7 +270,9 @@ int hz_tree_choose(hz_tree *t, const float *u01, const uint8_t *exploratory,
                    int16_t *actions, void *stream);
 
 /* Per-tree counters: n_nodes, n_edges (int32 each, nullable) and status bytes (nullable):
- * 0 ok, 1 node arena overflow, 2 edge arena overflow, 4 path overflow. */
+ * bits 0-3 = the current search: 1 node arena overflow, 2 edge arena overflow, 4 path overflow;
+ * bits 4-7 = the same flags raised by any EARLIER search of this handle (hz_tree_reset moves
+ * them up instead of clearing them, so a truncated search can never go unnoticed). */
 int hz_tree_stats(hz_tree *t, int32_t *n_nodes, int32_t *n_edges, uint8_t *status,
                   void *stream);
 
@@ -295,33 +297,40 @@ int hz_net_heads(const void *x, const void *glob, int64_t n, int C, int H, const
  * Hand-written sm_100a 3x3 convolution (tcgen05.mma, accumulators in tensor memory, operands
  * brought in by the bulk copy engine), BatchNorm folded, bf16 in / fp32 accumulate / bf16 out.
  *
- * "T16" activation layout: boards in tiles of 16; per tile and per 64-channel half 560 rows of
- * 128 bytes, row = cell*16 + board (cell = y*7 + x of the 5x7 plane), and inside a row the
- * 16-byte group g (channels 8g..8g+7 of the half) is stored at position g ^ (row & 7): the
- * shared-memory image of a K-major SWIZZLE_128B tensor-core operand, so a tile is loaded with
- * plain bulk copies.  Tile stride = channel_halves * 71,680 bytes.
- * Weight layout: [tap = ky*3+kx][channel half][out channel 0..127] rows of 128 bytes with the
- * same swizzle (group g at g ^ (out & 7)): 16 KB per (tap, half). */
+ * Activations are kept in 16-board tiles that are byte-for-byte the shared-memory image of the
+ * tensor-core operand (a tile half = 71,680 bytes = one bulk copy).  Position p = cell*16 + board
+ * (cell = y*7 + x of the 5x7 plane, board = index inside the tile).
+ *   "T16"  (outputs, residual-block inputs; 128 channels = 143,360 bytes per tile): MN-major, no
+ *          swizzle: element (p, c) at  (c/8)*8960 + (p/8)*128 + (c%8)*16 + (p%8)*2.
+ *   "T16K" (the stem's input; <= 64 channels, one half per tile): K-major SWIZZLE_128B: element
+ *          (p, c) at  p*128 + (((c/8) ^ (p%8)) * 16) + (c%8)*2.
+ * Weights: [tap = ky*3+kx][channel half][out channel 0..127] rows of 128 bytes, K-major
+ * SWIZZLE_128B (input-channel group g of the half at g ^ (out & 7)): 16 KB per (tap, half). */
 size_t hz_tower_tile_bytes(int64_t n_boards, int channel_halves);
 /* Upper bound on the persistent grid of hz_tower_conv3x3 (0 = one CTA per SM, the default).
  * Process-wide; meant for tests that push many tiles through few CTAs. */
 int hz_tower_set_max_ctas(int max_ctas);
+/* Profiling switches of hz_tower_conv3x3 (0 = normal operation; results are WRONG otherwise):
+ * 1 skip the MMAs, 2 skip the epilogue's memory traffic, 4 skip the weight copies, 8 skip the
+ * activation copies.  Used by profiles/tower_bench.py to attribute the kernel's time. */
+int hz_tower_set_debug(int flags);
 
-/* NHWC bf16 [n,35,channels] -> T16 tiles (channels % 8 == 0, <= 64*channel_halves; missing
- * channels and the boards that pad n up to a multiple of 16 are written as zero). */
+/* NHWC bf16 [n,35,channels] -> tiles.  kmajor != 0: T16K (channels % 8 == 0, <= 64; missing
+ * channels zero); kmajor == 0: T16 (channels must be 128).  Boards that pad n up to a multiple
+ * of 16 are written as zero. */
 int hz_tower_to_tiles(const void *src_nhwc, void *dst_tiles, int64_t n_boards, int channels,
-                      int channel_halves, void *stream);
-/* T16 tiles (2 halves) -> NHWC bf16 [n,35,128] */
+                      int kmajor, void *stream);
+/* T16 tiles -> NHWC bf16 [n,35,128] (the layout hz_net_heads reads) */
 int hz_tower_from_tiles(const void *src_tiles, void *dst_nhwc, int64_t n_boards, void *stream);
 
 /* y = [relu]( conv3x3(x, w) + bias [+ residual] ) for n_boards (multiple of 16) boards.
- * x: T16 tiles with in_channel_halves (1 for the stem: 38 input planes zero-padded to 64; 2 for
- * the residual convolutions); residual (nullable): T16 tiles, 2 halves; y: T16 tiles (2 halves),
- * or NHWC [n,35,128] when out_nhwc != 0 (the layout hz_net_heads reads).  fault (nullable): a
- * host-mapped word that receives the id of a barrier wait that timed out before the kernel traps. */
-int hz_tower_conv3x3(const void *x_tiles, int in_channel_halves, const void *w_tiles,
+ * x: in_kmajor != 0: T16K tiles, in_channel_halves must be 1 (the stem: 38 input planes
+ * zero-padded to 64); in_kmajor == 0: T16 tiles with in_channel_halves * 64 channels.
+ * residual (nullable) and y: T16 tiles, 128 channels.  fault (nullable): a host-mapped word that
+ * receives the id of a barrier wait that timed out before the kernel traps. */
+int hz_tower_conv3x3(const void *x_tiles, int in_channel_halves, int in_kmajor, const void *w_tiles,
                      const float *bias, const void *residual_tiles, void *y, int64_t n_boards,
-                     int relu, int out_nhwc, unsigned int *fault, void *stream);
+                     int relu, unsigned int *fault, void *stream);
 
 #define HZ_PLAYOUT_SALT 0xA5A5F00DC0FFEE11ull
 #define HZ_SEARCH_SALT  0x5EA2C47EE5A17B00ull

@@ -66,6 +66,15 @@ def main():
     r = timeit(lambda: ht.conv(buf["a"], 2, c2, buf["b"], buf["c"], n_pad), a.iters)
     r["dense_equiv_tflops"] = dense_flop / r["us_min"] / 1e6
     out["hand_conv_warm"] = r
+    # attribution: the same launch with parts switched off (results are garbage, timing only)
+    attr = {}
+    for flags, name in ((1, "no_mma"), (2, "no_epilogue_mem"), (4, "no_weight_copies"), (8, "no_act_copies"), (12, "no_copies"),
+                        (3, "no_mma_no_epi_mem"), (13, "copies_off_mma_off"), (15, "barriers_only")):
+        ht.lib.hz_tower_set_debug(flags)
+        attr[name] = timeit(lambda: ht.conv(buf["a"], 2, c2, buf["b"], buf["c"], n_pad), a.iters)["us_min"]
+    ht.lib.hz_tower_set_debug(0)
+    out["hand_conv_attribution_us"] = attr
+    hand.tower_out(board)
     x = lib.tower_out(board)
     r = timeit(lambda: lib._conv_relu(x, lib.blocks[0][1], 1, residual=x), a.iters, flush)
     r["dense_equiv_tflops"] = dense_flop / r["us_min"] / 1e6

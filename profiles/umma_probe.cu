@@ -5,6 +5,9 @@
 // sit in shared memory as K-major SWIZZLE_128B tiles, B is a window starting `b_row_off` rows into
 // a taller tile (the shifted-window trick of the 3x3 taps) and D starts `d_col_off` columns into
 // the TMEM allocation.  use_bulk = 1 loads the operands with cp.async.bulk + mbarrier.
+// bmode (7th argument): 0 = B K-major SWIZZLE_128B; 1 = B MN-major, no swizzle (core matrix = 8 k
+// x 8 positions, positions contiguous; LBO = K-direction stride, SBO = MN-direction stride);
+// 2 = the same image with LBO/SBO swapped in the descriptor (must FAIL if 1 is right).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,8 +22,19 @@ constexpr int MAXROWS_B = 288;
 constexpr int A_BYTES = 128 * 128;          // one k-block: 128 rows x 64 bf16
 constexpr int B_BYTES = MAXROWS_B * 128;
 
+constexpr int LBO_B = (MAXROWS_B / 8) * 128;   // MN-major image: stride between 8-channel groups
+
+__device__ __forceinline__ uint64_t smem_desc_mn_none(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
 __global__ void __launch_bounds__(128) probe(const uint8_t* Aimg, const uint8_t* Bimg, float* D, int N, int brow_off, int dcol_off,
-                                             int use_bulk, int nkb, unsigned int* fault) {
+                                             int use_bulk, int nkb, unsigned int* fault, int bmode) {
     extern __shared__ uint8_t raw[];
     uint8_t* sm = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = sm;                         // [nkb][16 KB]
@@ -57,11 +71,16 @@ __global__ void __launch_bounds__(128) probe(const uint8_t* Aimg, const uint8_t*
     }
     if (tid == 0) {
         tc_fence_after();
-        uint32_t idesc = idesc_bf16_f32(128, N);
+        uint32_t idesc = idesc_bf16_f32(128, N) | (bmode ? (1u << 16) : 0u);
         for (int kb = 0; kb < nkb; kb++)
             for (int k = 0; k < 4; k++) {
                 uint64_t da = smem_desc_sw128(smem_u32(sA + kb * A_BYTES) + k * 32);
-                uint64_t db = smem_desc_sw128(smem_u32(sB + kb * B_BYTES) + brow_off * 128 + k * 32);
+                uint64_t db;
+                if (bmode == 0) db = smem_desc_sw128(smem_u32(sB + kb * B_BYTES) + brow_off * 128 + k * 32);
+                else {
+                    uint32_t a = smem_u32(sB + kb * B_BYTES) + (brow_off >> 3) * 128 + k * 2 * LBO_B;
+                    db = bmode == 1 ? smem_desc_mn_none(a, LBO_B, 128) : smem_desc_mn_none(a, 128, LBO_B);
+                }
                 umma_bf16(tbase + dcol_off, da, db, idesc, (kb | k) ? 1u : 0u);
             }
         umma_commit(smem_u32(&bars[1]));
@@ -95,7 +114,7 @@ static size_t sw128(int row, int k) { return (size_t)row * 128 + ((((k >> 3) ^ (
 
 int main(int argc, char** argv) {
     int N = argc > 1 ? atoi(argv[1]) : 112, brow = argc > 2 ? atoi(argv[2]) : 0, dcol = argc > 3 ? atoi(argv[3]) : 0;
-    int bulk = argc > 4 ? atoi(argv[4]) : 0, nkb = argc > 5 ? atoi(argv[5]) : 1;
+    int bulk = argc > 4 ? atoi(argv[4]) : 0, nkb = argc > 5 ? atoi(argv[5]) : 1, bmode = argc > 6 ? atoi(argv[6]) : 0;
     if (brow + N > MAXROWS_B || dcol + N > 512 || nkb < 1 || nkb > 2) { printf("bad args\n"); return 2; }
     std::vector<uint16_t> A((size_t)nkb * 128 * 64), B((size_t)nkb * MAXROWS_B * 64);
     std::vector<uint8_t> Aimg((size_t)nkb * A_BYTES), Bimg((size_t)nkb * B_BYTES);
@@ -106,7 +125,10 @@ int main(int argc, char** argv) {
         for (int r = 0; r < 128; r++)
             for (int k = 0; k < 64; k++) memcpy(&Aimg[(size_t)kb * A_BYTES + sw128(r, k)], &A[((size_t)kb * 128 + r) * 64 + k], 2);
         for (int r = 0; r < MAXROWS_B; r++)
-            for (int k = 0; k < 64; k++) memcpy(&Bimg[(size_t)kb * B_BYTES + sw128(r, k)], &B[((size_t)kb * MAXROWS_B + r) * 64 + k], 2);
+            for (int k = 0; k < 64; k++) {
+                size_t off = bmode == 0 ? sw128(r, k) : (size_t)(k >> 3) * LBO_B + (size_t)(r >> 3) * 128 + (k & 7) * 16 + (r & 7) * 2;
+                memcpy(&Bimg[(size_t)kb * B_BYTES + off], &B[((size_t)kb * MAXROWS_B + r) * 64 + k], 2);
+            }
     }
     uint8_t *dA, *dB;
     float* dD;
@@ -121,10 +143,10 @@ int main(int argc, char** argv) {
     cudaMemset(dD, 0, 128 * 512 * 4);
     int smem = 2 * A_BYTES + 2 * B_BYTES + 1024 + 256;
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    probe<<<1, 128, smem>>>(dA, dB, dD, N, brow, dcol, bulk, nkb, fault);
+    probe<<<1, 128, smem>>>(dA, dB, dD, N, brow, dcol, bulk, nkb, fault, bmode);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
-        printf("N=%d brow=%d dcol=%d bulk=%d nkb=%d: CUDA ERROR %s (fault code %u)\n", N, brow, dcol, bulk, nkb, cudaGetErrorString(e), *fault);
+        printf("N=%d brow=%d dcol=%d bulk=%d nkb=%d bmode=%d: CUDA ERROR %s (fault code %u)\n", N, brow, dcol, bulk, nkb, bmode, cudaGetErrorString(e), *fault);
         return 1;
     }
     std::vector<float> D(128 * 512);
@@ -144,6 +166,6 @@ int main(int argc, char** argv) {
                 bad++;
             }
         }
-    printf("N=%d brow=%d dcol=%d bulk=%d nkb=%d: maxerr=%g bad=%d -> %s\n", N, brow, dcol, bulk, nkb, maxerr, bad, bad ? "FAIL" : "OK");
+    printf("N=%d brow=%d dcol=%d bulk=%d nkb=%d bmode=%d: maxerr=%g bad=%d -> %s\n", N, brow, dcol, bulk, nkb, bmode, maxerr, bad, bad ? "FAIL" : "OK");
     return bad ? 1 : 0;
 }

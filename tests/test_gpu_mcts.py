@@ -222,6 +222,23 @@ def test_arena_overflow_is_reported(mods):
         t.check_status()
 
 
+def test_overflow_survives_reset(mods):
+    """hz_tree_reset starts a new search but keeps the record of a truncated one (sticky high
+    nibble): a caller that checks only every few searches still sees it."""
+    hb, tr = mods
+    n = 8
+    st = hb.init_states(n, seed=1)
+    t = tr.BatchedMCTS(n, 50, max_nodes=40)
+    t.reset(st, tr.search_keys_tensor(np.arange(n, dtype=np.uint64)))
+    t.run_synthetic(50, 2.0)
+    t.reset(st, tr.search_keys_tensor(np.arange(n, dtype=np.uint64)))
+    t.run_synthetic(2, 2.0)                      # a tiny search that fits
+    status = t.stats()[2].cpu().numpy()
+    assert (status & 0x0F == 0).all() and (status & 0xF0 != 0).any()
+    with pytest.raises(RuntimeError):
+        t.check_status()
+
+
 def test_terminal_root(mods):
     hb, tr = mods
     st = hb.init_states(4, seed=3)

@@ -3,9 +3,9 @@ through the C ABI.
 
 * exact: with small-integer activations / weights every fp32 partial sum is an integer below
   2^24, so tcgen05 accumulation order cannot matter and the bf16 outputs must equal
-  RNE(conv2d) BIT FOR BIT — for the stem shape (one 64-channel half), the residual shape (two
-  halves), with and without residual / ReLU, in both output layouts, and with many tiles pushed
-  through few CTAs (ring, tile-buffer and TMEM-unit phase wrap-around).
+  RNE(conv2d) BIT FOR BIT — for the stem shape (one 64-channel half, K-major input image), the
+  residual shape (two halves, MN-major image), with and without residual / ReLU, and with many
+  tiles pushed through few CTAs (ring, tile-buffer and TMEM-unit phase wrap-around).
 * model: the whole tower against the cuDNN path of InferenceNet (same folded bf16 weights) and the
   fp32 reference architecture (model.py:325-357), at bf16 tolerance (stated in the test).
 """
@@ -40,29 +40,25 @@ class _Raw:
         self.tower = tower
 
     def tiles(self, x_nchw):
-        """bf16 [B,C,5,7] -> T16 tiles (C <= 64: one half, else two)"""
+        """bf16 [B,C,5,7] -> tiles: C <= 64: T16K (one half, the stem's input), C == 128: T16"""
         B, C = x_nchw.shape[:2]
         halves = 1 if C <= 64 else 2
         n_pad = (B + 15) // 16 * 16
         nhwc = x_nchw.permute(0, 2, 3, 1).contiguous()
         dst = torch.zeros(n_pad // 16 * halves * self.tower.KH_BYTES, dtype=torch.uint8, device="cuda")
-        self.t.to_tiles(nhwc, C, halves, dst)
+        self.t.to_tiles(nhwc, C, halves == 1, dst)
         return dst, halves, n_pad
 
-    def conv(self, x_nchw, w, bias, res_nchw=None, relu=True, out_nhwc=False):
+    def conv(self, x_nchw, w, bias, res_nchw=None, relu=True):
         B = x_nchw.shape[0]
         xt, halves, n_pad = self.tiles(x_nchw)
         img, nkh = self.tower.pack_conv_weight(w)
         assert nkh == halves
         rt = None if res_nchw is None else self.tiles(res_nchw)[0]
-        if out_nhwc:
-            y = torch.zeros((n_pad, 35, 128), dtype=torch.bfloat16, device="cuda")
-        else:
-            y = torch.zeros(n_pad // 16 * 2 * self.tower.KH_BYTES, dtype=torch.uint8, device="cuda")
-        self.t.conv(xt, halves, (img.cuda(), bias.float().cuda(), nkh), rt, y, n_pad, relu=relu, out_nhwc=out_nhwc)
+        y = torch.zeros(n_pad // 16 * 2 * self.tower.KH_BYTES, dtype=torch.uint8, device="cuda")
+        self.t.conv(xt, halves, (img.cuda(), bias.float().cuda(), nkh), rt, y, n_pad, relu=relu, kmajor=halves == 1)
         torch.cuda.synchronize()
-        out = y if out_nhwc else self.t.from_tiles(y, n_pad)
-        return out[:B].view(B, 5, 7, 128).permute(0, 3, 1, 2)
+        return self.t.from_tiles(y, n_pad)[:B].view(B, 5, 7, 128).permute(0, 3, 1, 2)
 
 
 def _ref(x, w, bias, res, relu):
@@ -85,32 +81,39 @@ def test_tile_layout_roundtrip(tw):
     xt, halves, n_pad = raw.tiles(x)
     back = raw.t.from_tiles(xt, 37).view(37, 5, 7, 128).permute(0, 3, 1, 2)
     assert torch.equal(back, x)
-    # the documented address of an element: row = cell*16 + board, group g at g ^ (row & 7)
+    # the documented address of an element (include/harmonies_b200.h): p = cell*16 + board
     img = xt.cpu().numpy()
     xs = x.cpu()
     for (b, c, y, xx) in [(0, 0, 0, 0), (5, 77, 3, 4), (36, 127, 4, 6), (17, 64, 2, 1)]:
-        tile, bb, cell = b // 16, b % 16, y * 7 + xx
-        rr = cell * 16 + bb
-        off = (tile * 2 + c // 64) * tw.KH_BYTES + rr * 128 + ((((c % 64) // 8) ^ (rr & 7)) << 4) + (c % 8) * 2
+        tile, p = b // 16, (y * 7 + xx) * 16 + b % 16
+        off = tile * 2 * tw.KH_BYTES + (c // 8) * 8960 + (p // 8) * 128 + (c % 8) * 16 + (p % 8) * 2
         got = torch.from_numpy(img[off:off + 2].copy()).view(torch.bfloat16)[0]
         assert got == xs[b, c, y, xx]
+    # T16K, the stem's input image
+    x40 = _ints((19, 40, 5, 7), -3, 3, 2).to(torch.bfloat16).cuda()
+    kt = raw.tiles(x40)[0].cpu().numpy()
+    for (b, c, y, xx) in [(0, 0, 0, 0), (5, 37, 3, 4), (18, 39, 4, 6), (17, 8, 2, 1)]:
+        tile, p = b // 16, (y * 7 + xx) * 16 + b % 16
+        off = tile * tw.KH_BYTES + p * 128 + (((c // 8) ^ (p & 7)) << 4) + (c % 8) * 2
+        got = torch.from_numpy(kt[off:off + 2].copy()).view(torch.bfloat16)[0]
+        assert got == x40.cpu()[b, c, y, xx]
 
 
-@pytest.mark.parametrize("cin,boards,res,relu,nhwc", [
-    (128, 16, False, True, False),
-    (128, 16, True, True, False),
-    (128, 48, True, False, True),
-    (40, 16, False, True, False),
-    (40, 33, False, True, True),
-    (128, 16 * 9 + 5, True, True, False),
+@pytest.mark.parametrize("cin,boards,res,relu", [
+    (128, 16, False, True),
+    (128, 16, True, True),
+    (128, 48, True, False),
+    (40, 16, False, True),
+    (40, 33, False, False),
+    (128, 16 * 9 + 5, True, True),
 ])
-def test_conv_bit_exact_on_integers(tw, cin, boards, res, relu, nhwc):
+def test_conv_bit_exact_on_integers(tw, cin, boards, res, relu):
     raw = _Raw(tw)
     x = _ints((boards, cin, 5, 7), -2, 2, 10 + boards).to(torch.bfloat16).cuda()
     w = _ints((128, cin, 3, 3), -1, 1, 20 + cin)
     bias = _ints((128,), -4, 4, 30)
     r = _ints((boards, 128, 5, 7), -8, 8, 40).to(torch.bfloat16).cuda() if res else None
-    got = raw.conv(x, w, bias, r, relu=relu, out_nhwc=nhwc)
+    got = raw.conv(x, w, bias, r, relu=relu)
     want = _ref(x, w, bias, r, relu)
     assert torch.equal(got.cpu(), want), f"max abs diff {(got.cpu().float() - want.float()).abs().max()}"
 
