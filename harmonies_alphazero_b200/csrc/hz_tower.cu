@@ -32,7 +32,7 @@
 //     is drained before the next tile's row 0 needs the unit.  The epilogue of one row therefore
 //     always overlaps the MMAs of the others.
 //   * warp roles: 0 = weight producer, 1 = MMA issuer, 2 = activation producer, 3 = TMEM
-//     allocator, 4..7 = epilogue (bias + residual + ReLU + bf16, thread = output channel).
+//     allocator, 4..11 = epilogue (bias + residual + ReLU + bf16, thread = output channel).
 #include "hz_common.cuh"
 #include "hz_sm100.cuh"
 
@@ -49,15 +49,15 @@ constexpr int ROW_BYTES = BCOLS * G * 128;     // 14,336: one board row of one c
 constexpr int W_BYTES = 128 * 128;             // 16,384: [128 out][64 in] bf16
 constexpr int NSTAGE = 5;
 constexpr int NUNIT = 4, UNIT_COLS = 128;
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 384;                  // 4 control warps + 8 epilogue warps
 constexpr int OFF_X = 0;
 constexpr int OFF_W = 2 * KH_BYTES;
 constexpr int OFF_BAR = OFF_W + NSTAGE * W_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // + alignment slack
+constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;   // barriers + alignment slack
 
 // barrier indices
 constexpr int B_WFULL = 0, B_WEMPTY = NSTAGE, B_AFULL = 2 * NSTAGE, B_AEMPTY = 2 * NSTAGE + 2, B_TFULL = 2 * NSTAGE + 4,
-              B_TEMPTY = 2 * NSTAGE + 4 + NUNIT, B_DONE = 2 * NSTAGE + 4 + 2 * NUNIT, N_BARS = B_DONE + 1;
+              B_TEMPTY = 2 * NSTAGE + 4 + NUNIT, B_DONE = 2 * NSTAGE + 4 + 2 * NUNIT, B_YDONE = B_DONE + 1, N_BARS = B_YDONE + 8;
 
 // tap = ky*3 + kx (dy = ky-1, dx = kx-1).  Within a dy group the dx = 0 tap comes first: the first
 // MMA into a row accumulator overwrites it and must cover all 112 columns.
@@ -69,16 +69,33 @@ __constant__ int8_t EPI_ORDER[5] = {0, 1, 2, 4, 3};  // order in which the row a
 __device__ __forceinline__ int unit_of(int r) { return r == 4 ? 0 : r; }
 __device__ __forceinline__ int use_of(int r, int it) { return r == 0 ? 2 * it : r == 4 ? 2 * it + 1 : it; }
 
-struct Params {
-    const uint8_t* x;      // input tiles: T16 [n_tiles][nkh*8 groups][8960 B] or T16K [n_tiles][nkh][560][128 B]
+constexpr int MAX_LAYERS = 20;   // stem + 8 residual blocks = 17
+constexpr int MAX_SLOTS = 8;     // tiles per CTA the fused (multi-layer) launch supports
+
+struct Layer {
     const uint8_t* w;      // weight tiles [9][nkh][128][128 B]
     const float* bias;     // [128]
-    const uint8_t* res;    // residual, T16 tiles (2 halves), or null
-    uint8_t* y;            // output, T16 tiles (2 halves)
-    int n_tiles, nkh, relu, in_kmajor;
+    int in_buf, res_buf, out_buf;   // indices into Params::buf; res_buf < 0: no residual
+    int nkh, kmajor, relu; // input channel halves; input image T16K (stem) or T16
+};
+// One launch runs layers[0..n_layers) for every tile the CTA owns.  Boards are independent, so a CTA
+// needs no other CTA's output: layer l+1 of a tile only waits for the CTA's own epilogue of layer l.
+struct Params {
+    uint8_t* buf[4];       // activation tile buffers (T16; a kmajor layer's input buffer is T16K with one half)
+    Layer layers[MAX_LAYERS];
+    int n_layers, n_tiles;
     int dbg;               // profiling only (hz_tower_set_debug): 1 skip MMAs, 2 skip epilogue memory traffic, 4 skip weight copies, 8 skip activation copies
     unsigned int* fault;
+    unsigned long long* trace;   // profiling only (hz_tower_set_trace): SM-clock timestamps of CTA 0's roles
 };
+// trace slots (CTA 0 only): [0] start, [1] end; MMA warp per weight stage i: [16+3i] before the wait on the
+// stage, [+1] after it, [+2] after the MMAs and commits were issued; weight producer [400+i] when it issues
+// stage i; epilogue warp 4 per row j: [600+4j] before the accumulator wait, [+1] after, [+2] after the TMEM
+// loads, [+3] after the stores; activation producer [700+j] when it issues half j.
+#define HZ_TRACE(slot)                                                                  \
+    do {                                                                                \
+        if (P.trace && blockIdx.x == 0 && lane == 0 && (slot) < 1024) P.trace[slot] = clock64(); \
+    } while (0)
 
 // B operand, MN-major without swizzle: core matrices of [8 channels][8 positions]; LBO = stride
 // between 8-channel groups (K direction), SBO = stride between 8-position groups (N direction)
@@ -92,8 +109,15 @@ __device__ __forceinline__ uint64_t smem_desc_t16(uint32_t saddr) {
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&h);
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// max(x, 0) and round-to-nearest-even to bf16 in one instruction (NaN -> canonical NaN, as cuDNN's ReLU epilogue)
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
 }
 
 // ---- MMA issue, fully unrolled -------------------------------------------------------------------
@@ -149,12 +173,14 @@ struct StageLoop {
     static __device__ __forceinline__ void run(Ctx& c, int kh, int it, bool last_kh) {
         constexpr int tap = tap_at(PASS, TI);
         constexpr int r0 = PASS ? 3 : 0, r1 = PASS ? 5 : 3;
+        if (c.trace && c.nstage < 120) c.trace[16 + 3 * c.nstage] = clock64();
         mbar_wait(c.bar0 + 8u * (B_WFULL + c.stage), c.ph, c.fault, 0x400 + c.stage);
         if (TI == 0 && kh == 0) {       // first touch of the pass's accumulators for this tile: previous tenants must be drained
 #pragma unroll
             for (int r = r0; r < r1; r++) mbar_wait(c.bar0 + 8u * (B_TEMPTY + unit_of(r)), (use_of(r, it) & 1) ^ 1, c.fault, 0x500 + r);
         }
         tc_fence_after();
+        if (c.trace && c.nstage < 120) c.trace[16 + 3 * c.nstage + 1] = clock64();
         if (elect_one()) {
             const uint32_t a_lo = DESC_LO_SW128 | ((c.sW + c.stage * W_BYTES) >> 4);
             const uint32_t b_lo = (KMAJOR ? DESC_LO_SW128 : DESC_LO_T16) | ((c.sX + (uint32_t)kh * KH_BYTES) >> 4);
@@ -167,6 +193,8 @@ struct StageLoop {
             }
         }
         __syncwarp();
+        if (c.trace && c.nstage < 120) c.trace[16 + 3 * c.nstage + 2] = clock64();
+        c.nstage++;
         if (++c.stage == NSTAGE) { c.stage = 0; c.ph ^= 1; }
         if constexpr (TI < 8) StageLoop<KMAJOR, PASS, TI + 1>::run(c, kh, it, last_kh);
     }
@@ -176,23 +204,24 @@ struct IssueCtx {
     uint32_t bar0, sW, sX, tbase, stage, ph;
     unsigned int* fault;
     int dbg;
+    unsigned long long* trace;   // null unless CTA 0 is being traced
+    int nstage;                  // running stage count (trace index)
 };
 
-template <bool KMAJOR>
-__global__ void __launch_bounds__(NTHREADS, 1) k_conv3x3(Params P) {
+__global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ Params P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sX = smem_u32(sm + OFF_X), sW = smem_u32(sm + OFF_W), sBar = smem_u32(sm + OFF_BAR);
     uint32_t* tmem_slot = (uint32_t*)(sm + OFF_BAR + N_BARS * 8);
     auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkh = P.nkh;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; i++) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
         for (int i = 0; i < 2; i++) { mbar_init(bar(B_AFULL + i), 1); mbar_init(bar(B_AEMPTY + i), 1); }
-        for (int i = 0; i < NUNIT; i++) { mbar_init(bar(B_TFULL + i), 1); mbar_init(bar(B_TEMPTY + i), 4); }
+        for (int i = 0; i < NUNIT; i++) { mbar_init(bar(B_TFULL + i), 1); mbar_init(bar(B_TEMPTY + i), 8); }
         mbar_init(bar(B_DONE), 1);
+        for (int i = 0; i < MAX_SLOTS; i++) mbar_init(bar(B_YDONE + i), 8);
         mbar_init_fence();
     }
     if (warp == 3) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -200,110 +229,173 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv3x3(Params P) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tmem_slot;
+    if (warp == 0) HZ_TRACE(0);
 
+    // every role walks the same sequence of work items: for layer, for this CTA's tiles (slot = 0, 1, ..)
     if (warp == 0 && lane == 0) {
-        // ---- weight producer: the tap stream of every pass of every tile, through the ring ----
+        // ---- weight producer: the tap stream of every pass of every item, through the ring ----
         uint32_t stage = 0, ph = 0;
-        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
-            for (int pass = 0; pass < 2; pass++)
-                for (int kh = 0; kh < nkh; kh++)
-                    for (int ti = 0; ti < 9; ti++) {
-                        int tap = TAP_ORDER[pass][ti];
-                        mbar_wait(bar(B_WEMPTY + stage), ph ^ 1, P.fault, 0x100 + stage);
-                        if (P.dbg & 4) mbar_arrive(bar(B_WFULL + stage));
-                        else {
-                            mbar_expect_tx(bar(B_WFULL + stage), W_BYTES);
-                            bulk_g2s(sW + stage * W_BYTES, P.w + (size_t)(tap * nkh + kh) * W_BYTES, W_BYTES, bar(B_WFULL + stage));
+        int ns = 0;
+        for (int l = 0; l < P.n_layers; l++) {
+            const uint8_t* w = P.layers[l].w;
+            const int nkh = P.layers[l].nkh;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
+                for (int pass = 0; pass < 2; pass++)
+                    for (int kh = 0; kh < nkh; kh++)
+                        for (int ti = 0; ti < 9; ti++, ns++) {
+                            int tap = TAP_ORDER[pass][ti];
+                            mbar_wait(bar(B_WEMPTY + stage), ph ^ 1, P.fault, 0x100 + stage);
+                            HZ_TRACE(400 + ns);
+                            if (P.dbg & 4) mbar_arrive(bar(B_WFULL + stage));
+                            else {
+                                mbar_expect_tx(bar(B_WFULL + stage), W_BYTES);
+                                bulk_g2s(sW + stage * W_BYTES, w + (size_t)(tap * nkh + kh) * W_BYTES, W_BYTES, bar(B_WFULL + stage));
+                            }
+                            if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
                         }
-                        if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
-                    }
+        }
     } else if (warp == 2 && lane == 0) {
         // ---- activation producer: one channel half of a tile per buffer ----
-        int it = 0;
-        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, it++)
-            for (int kh = 0; kh < nkh; kh++) {
-                mbar_wait(bar(B_AEMPTY + kh), (it & 1) ^ 1, P.fault, 0x200 + kh);
-                if (P.dbg & 8) { mbar_arrive(bar(B_AFULL + kh)); continue; }
-                mbar_expect_tx(bar(B_AFULL + kh), KH_BYTES);
-                const uint8_t* src = P.x + ((size_t)tile * nkh + kh) * KH_BYTES;
-                for (int r = 0; r < BROWS; r++)
-                    bulk_g2s(sX + kh * KH_BYTES + r * ROW_BYTES, src + (size_t)r * ROW_BYTES, ROW_BYTES, bar(B_AFULL + kh));
+        uint32_t cnt0 = 0, cnt1 = 0;       // uses of each half buffer so far (barrier phase)
+        int na = 0;
+        for (int l = 0; l < P.n_layers; l++) {
+            const Layer& L = P.layers[l];
+            int slot = 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, slot++) {
+                // the tile's input is the CTA's own output of the previous layer: wait for that epilogue
+                if (l > 0) mbar_wait(bar(B_YDONE + slot), (uint32_t)(l - 1) & 1u, P.fault, 0x800 + slot);
+                for (int kh = 0; kh < L.nkh; kh++, na++) {
+                    mbar_wait(bar(B_AEMPTY + kh), ((kh ? cnt1 : cnt0) & 1u) ^ 1u, P.fault, 0x200 + kh);
+                    if (kh) cnt1++; else cnt0++;
+                    HZ_TRACE(700 + na);
+                    if (P.dbg & 8) { mbar_arrive(bar(B_AFULL + kh)); continue; }
+                    mbar_expect_tx(bar(B_AFULL + kh), KH_BYTES);
+                    const uint8_t* src = P.buf[L.in_buf] + ((size_t)tile * L.nkh + kh) * KH_BYTES;
+                    for (int r = 0; r < BROWS; r++)
+                        bulk_g2s(sX + kh * KH_BYTES + r * ROW_BYTES, src + (size_t)r * ROW_BYTES, ROW_BYTES, bar(B_AFULL + kh));
+                }
             }
+        }
     } else if (warp == 1) {
         // ---- MMA issuer: the whole warp runs the loop, one elected lane issues ----
-        IssueCtx c{sBar, sW, sX, tbase, 0u, 0u, P.fault, P.dbg};
-        int it = 0;
-        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, it++) {
-            for (int kh = 0; kh < nkh; kh++) {
-                mbar_wait(bar(B_AFULL + kh), it & 1, P.fault, 0x300 + kh);
-                StageLoop<KMAJOR, 0, 0>::run(c, kh, it, kh == nkh - 1);
-            }
-            for (int kh = 0; kh < nkh; kh++) {
-                StageLoop<KMAJOR, 1, 0>::run(c, kh, it, kh == nkh - 1);
-                if (elect_one()) umma_commit(bar(B_AEMPTY + kh));   // the tile's channel half is no longer read
-                __syncwarp();
+        IssueCtx c{sBar, sW, sX, tbase, 0u, 0u, P.fault, P.dbg, (blockIdx.x == 0 && lane == 0) ? P.trace : nullptr, 0};
+        uint32_t cnt0 = 0, cnt1 = 0;
+        int wi = 0;                        // work item counter (phase of the accumulator units)
+        for (int l = 0; l < P.n_layers; l++) {
+            const int nkh = P.layers[l].nkh;
+            const bool kmajor = P.layers[l].kmajor != 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, wi++) {
+                for (int kh = 0; kh < nkh; kh++) {
+                    mbar_wait(bar(B_AFULL + kh), (kh ? cnt1 : cnt0) & 1u, P.fault, 0x300 + kh);
+                    if (kmajor) StageLoop<true, 0, 0>::run(c, kh, wi, kh == nkh - 1);
+                    else StageLoop<false, 0, 0>::run(c, kh, wi, kh == nkh - 1);
+                }
+                for (int kh = 0; kh < nkh; kh++) {
+                    if (kmajor) StageLoop<true, 1, 0>::run(c, kh, wi, kh == nkh - 1);
+                    else StageLoop<false, 1, 0>::run(c, kh, wi, kh == nkh - 1);
+                    if (elect_one()) umma_commit(bar(B_AEMPTY + kh));   // the tile's channel half is no longer read
+                    __syncwarp();
+                    if (kh) cnt1++; else cnt0++;
+                }
             }
         }
         if (elect_one()) umma_commit(bar(B_DONE));
         __syncwarp();
         mbar_wait(bar(B_DONE), 0, P.fault, 0x600);
     } else if (warp >= 4) {
-        // ---- epilogue: thread = output channel c; one TMEM load = the 16 boards of a cell, which are
-        // 2 x 16 contiguous bytes of channel c's row in the T16 image (vector stores, vector residual loads)
+        // ---- epilogue: 8 warps.  thread = output channel c (TMEM lane); warps 4-7 take cells x = 0..3
+        // of a board row, warps 8-11 cells x = 4..6.  One TMEM load = the 16 boards of a cell = 2 x 16
+        // contiguous bytes of channel c's row in the T16 image (vector stores, vector residual loads).
+        // All TMEM loads of the row are issued back to back and the unit is released as soon as they
+        // have landed in registers, before the arithmetic and the stores.
         const int q = warp & 3, c = q * 32 + lane;
-        const float bias = P.bias[c];
+        const int half = (warp - 4) >> 2;
+        const int x0 = half ? 4 : 0;
         const uint32_t chan_off = (uint32_t)(c >> 3) * KG_BYTES + (uint32_t)(c & 7) * 16u;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, it++) {
-            const size_t tile_off = (size_t)tile * 2 * KH_BYTES + chan_off;
-            for (int ri = 0; ri < BROWS; ri++) {
-                const int r = EPI_ORDER[ri], unit = unit_of(r);
-                // the residual of the whole board row is requested before the accumulator is waited for
-                uint4 rv[2 * BCOLS];
-                const bool mem = !(P.dbg & 2);
-                if (P.res && mem) {
+        const bool mem = !(P.dbg & 2);
+        int wi = 0, nrow = 0;
+        for (int l = 0; l < P.n_layers; l++) {
+            const Layer& L = P.layers[l];
+            const float bias = L.bias[c];
+            const uint8_t* resb = (L.res_buf >= 0 && mem) ? P.buf[L.res_buf] : nullptr;
+            uint8_t* yb = P.buf[L.out_buf];
+            const bool relu = L.relu != 0;
+            int slot = 0;
+            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, wi++, slot++) {
+                const size_t tile_off = (size_t)tile * 2 * KH_BYTES + chan_off;
+                for (int ri = 0; ri < BROWS; ri++, nrow++) {
+                    const int r = EPI_ORDER[ri], unit = unit_of(r);
+                    const size_t row_off = tile_off + (size_t)(r * BCOLS + x0) * (G * 16);
+                    // the residual of this warp's cells is requested before the accumulator is waited for
+                    // (this thread wrote those bytes itself two layers ago: program order makes them visible)
+                    uint4 rv[8];
+                    if (resb) {
 #pragma unroll
-                    for (int x = 0; x < BCOLS; x++) {
-                        const uint8_t* rp = P.res + tile_off + (size_t)(r * BCOLS + x) * (G * 16);
-                        rv[2 * x] = *reinterpret_cast<const uint4*>(rp);
-                        rv[2 * x + 1] = *reinterpret_cast<const uint4*>(rp + 128);
+                        for (int j = 0; j < 4; j++)
+                            if (j < 3 || !half) {
+                                const uint8_t* rp = resb + row_off + (size_t)j * (G * 16);
+                                rv[2 * j] = *reinterpret_cast<const uint4*>(rp);
+                                rv[2 * j + 1] = *reinterpret_cast<const uint4*>(rp + 128);
+                            }
                     }
-                }
-                mbar_wait(bar(B_TFULL + unit), use_of(r, it) & 1, P.fault, 0x700 + unit);
-                tc_fence_after();
-#pragma unroll
-                for (int x = 0; x < BCOLS; x++) {
-                    uint32_t v[16];
-                    tmem_ld16(tbase + ((uint32_t)(q * 32) << 16) + unit * UNIT_COLS + x * G, v);
+                    if (warp == 4) HZ_TRACE(600 + 4 * nrow);
+                    mbar_wait(bar(B_TFULL + unit), use_of(r, wi) & 1, P.fault, 0x700 + unit);
+                    tc_fence_after();
+                    if (warp == 4) HZ_TRACE(600 + 4 * nrow + 1);
+                    uint32_t v[4][16];
+                    const uint32_t ta = tbase + ((uint32_t)(q * 32) << 16) + unit * UNIT_COLS + x0 * G;
+                    tmem_ld16(ta, v[0]);
+                    tmem_ld16(ta + G, v[1]);
+                    tmem_ld16(ta + 2 * G, v[2]);
+                    if (!half) tmem_ld16(ta + 3 * G, v[3]);
                     tmem_ld_wait();
-                    float o[16];
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(B_TEMPTY + unit));      // the accumulator may be overwritten from here on
+                    if (warp == 4) HZ_TRACE(600 + 4 * nrow + 2);
 #pragma unroll
-                    for (int b = 0; b < G; b++) o[b] = __uint_as_float(v[b]) + bias;
-                    if (P.res && mem) {
-                        const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rv[2 * x]);
+                    for (int j = 0; j < 4; j++) {
+                        if (j == 3 && half) break;
+                        float o[16];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            o[2 * j] += __uint_as_float(rw[j] << 16);
-                            o[2 * j + 1] += __uint_as_float(rw[j] & 0xFFFF0000u);
+                        for (int b = 0; b < G; b++) o[b] = __uint_as_float(v[j][b]) + bias;
+                        if (resb) {
+                            const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rv[2 * j]);
+#pragma unroll
+                            for (int e = 0; e < 8; e++) {
+                                o[2 * e] += __uint_as_float(rw[e] << 16);
+                                o[2 * e + 1] += __uint_as_float(rw[e] & 0xFFFF0000u);
+                            }
                         }
-                    }
-                    if (P.relu) {
+                        uint8_t* yp = yb + row_off + (size_t)j * (G * 16);
+                        if (!mem) { if (o[0] + o[5] + o[10] + o[15] == 12345.678f) *reinterpret_cast<float*>(yp) = o[3]; continue; }
+                        uint32_t pk[8];
+                        if (relu) {
 #pragma unroll
-                        for (int b = 0; b < G; b++) o[b] = fmaxf(o[b], 0.0f);
+                            for (int e = 0; e < 8; e++) pk[e] = pack_bf16x2_relu(o[2 * e], o[2 * e + 1]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; e++) pk[e] = pack_bf16x2(o[2 * e], o[2 * e + 1]);
+                        }
+                        *reinterpret_cast<uint4*>(yp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(yp + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     }
-                    uint8_t* yp = P.y + tile_off + (size_t)(r * BCOLS + x) * (G * 16);
-                    if (!mem) { if (o[0] + o[5] + o[10] + o[15] == 12345.678f) *reinterpret_cast<float*>(yp) = o[3]; continue; }
-                    *reinterpret_cast<uint4*>(yp) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-                    *reinterpret_cast<uint4*>(yp + 128) = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]), pack_bf16x2(o[14], o[15]));
+                    if (warp == 4) HZ_TRACE(600 + 4 * nrow + 3);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(B_TEMPTY + unit));
+                if (l + 1 < P.n_layers) {
+                    // hand the tile's output to the activation producer of the next layer: the stores go
+                    // through the generic proxy, the bulk copy reads through the async proxy
+                    __threadfence();
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(B_YDONE + slot));
+                }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (warp == 0) HZ_TRACE(1);
     if (warp == 3) tmem_dealloc(tbase, 512);
 }
 
@@ -363,6 +455,7 @@ __global__ void k_from_tiles(const __nv_bfloat16* __restrict__ src, __nv_bfloat1
 }
 
 static int g_debug = 0;
+static unsigned long long* g_trace = nullptr;
 static int g_max_ctas = 0;   // 0 = one CTA per SM; tests lower it to drive several tiles through one CTA
 
 static int ensure_attr() {
@@ -370,12 +463,19 @@ static int ensure_attr() {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_conv3x3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv3x3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_tower, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return hz_record_launch(0, e);
         if (dev >= 0 && dev < 64) done[dev] = true;
     }
     return HZ_OK;
+}
+
+static int grid_for(int n_tiles) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_max_ctas > 0 && g_max_ctas < sms) sms = g_max_ctas;
+    return n_tiles < sms ? n_tiles : sms;
 }
 
 }  // namespace tower
@@ -396,6 +496,11 @@ int hz_tower_set_max_ctas(int max_ctas) {
 
 int hz_tower_set_debug(int flags) {
     hz::tower::g_debug = flags;
+    return HZ_OK;
+}
+
+int hz_tower_set_trace(unsigned long long* device_buffer_1024) {
+    hz::tower::g_trace = device_buffer_1024;
     return HZ_OK;
 }
 
@@ -429,26 +534,68 @@ int hz_tower_conv3x3(const void* x_tiles, int in_channel_halves, int in_kmajor, 
     if (((uintptr_t)x_tiles | (uintptr_t)w_tiles | (uintptr_t)y | (uintptr_t)residual_tiles) & 15) return HZ_ERR_ARG;
     int st = ensure_attr();
     if (st != HZ_OK) return st;
-    Params P;
-    P.x = (const uint8_t*)x_tiles;
-    P.w = (const uint8_t*)w_tiles;
-    P.bias = bias;
-    P.res = (const uint8_t*)residual_tiles;
-    P.y = (uint8_t*)y;
+    Params P{};
+    P.buf[0] = (uint8_t*)x_tiles;
+    P.buf[1] = (uint8_t*)residual_tiles;
+    P.buf[2] = (uint8_t*)y;
+    P.layers[0] = Layer{(const uint8_t*)w_tiles, bias, 0, residual_tiles ? 1 : -1, 2, in_channel_halves, in_kmajor, relu};
+    P.n_layers = 1;
     P.n_tiles = (int)(n_boards / G);
-    P.nkh = in_channel_halves;
-    P.relu = relu;
-    P.in_kmajor = in_kmajor;
     P.fault = fault;
     P.dbg = g_debug;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_max_ctas > 0 && g_max_ctas < sms) sms = g_max_ctas;
-    int grid = P.n_tiles < sms ? P.n_tiles : sms;
-    if (in_kmajor) k_conv3x3<true><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(P);
-    else k_conv3x3<false><<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    P.trace = g_trace;
+    k_tower<<<grid_for(P.n_tiles), NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(P);
     return hz_launched(1);
+}
+
+int hz_tower_forward(const void* x0_tiles, const void* const* w_tiles, const float* const* biases, int n_blocks, void* buf_a,
+                     void* buf_b, void* buf_c, void** out_tiles, int64_t n_boards, unsigned int* fault, void* stream) {
+    using namespace hz::tower;
+    if (!x0_tiles || !w_tiles || !biases || !buf_a || !buf_b || !buf_c || n_boards <= 0 || (n_boards % G) || n_blocks < 0 ||
+        1 + 2 * n_blocks > MAX_LAYERS)
+        return HZ_ERR_ARG;
+    if (((uintptr_t)x0_tiles | (uintptr_t)buf_a | (uintptr_t)buf_b | (uintptr_t)buf_c) & 15) return HZ_ERR_ARG;
+    int st = ensure_attr();
+    if (st != HZ_OK) return st;
+    Params P{};
+    P.buf[0] = (uint8_t*)x0_tiles;
+    P.buf[1] = (uint8_t*)buf_a;
+    P.buf[2] = (uint8_t*)buf_b;
+    P.buf[3] = (uint8_t*)buf_c;
+    // stem: x0 -> a; block i: conv1 cur -> b, conv2 b (+ cur) -> nxt; cur and nxt alternate between a and c
+    int n = 0, cur = 1, nxt = 3;
+    for (int i = 0; i < 1 + 2 * n_blocks; i++)
+        if (!w_tiles[i] || !biases[i] || ((uintptr_t)w_tiles[i] & 15)) return HZ_ERR_ARG;
+    P.layers[n] = Layer{(const uint8_t*)w_tiles[0], biases[0], 0, -1, cur, 1, 1, 1};
+    n++;
+    for (int b = 0; b < n_blocks; b++) {
+        P.layers[n] = Layer{(const uint8_t*)w_tiles[n], biases[n], cur, -1, 2, 2, 0, 1};
+        n++;
+        P.layers[n] = Layer{(const uint8_t*)w_tiles[n], biases[n], 2, cur, nxt, 2, 0, 1};
+        n++;
+        int t = cur; cur = nxt; nxt = t;
+    }
+    P.n_layers = n;
+    P.n_tiles = (int)(n_boards / G);
+    P.fault = fault;
+    P.dbg = g_debug;
+    P.trace = g_trace;
+    if (out_tiles) *out_tiles = P.buf[cur];
+    const int grid = grid_for(P.n_tiles);
+    if ((P.n_tiles + grid - 1) / grid <= MAX_SLOTS) {
+        k_tower<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(P);
+        return hz_launched(1);
+    }
+    // more tiles per CTA than the fused launch tracks: one launch per layer (stream order is the dependency)
+    for (int l = 0; l < n; l++) {
+        Params Q = P;
+        Q.layers[0] = P.layers[l];
+        Q.n_layers = 1;
+        k_tower<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(Q);
+        int r = hz_launched(1);
+        if (r != HZ_OK) return r;
+    }
+    return HZ_OK;
 }
 
 }  // extern "C"

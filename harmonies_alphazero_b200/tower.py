@@ -9,6 +9,8 @@ There is no fallback: without the CUDA library every call raises.  ``InferenceNe
 is the A/B switch for measurements.
 """
 
+import ctypes as C
+
 import torch
 
 from . import _lib
@@ -60,6 +62,10 @@ class HandTower:
         self.blocks = [(conv(b.conv1, b.bn1), conv(b.conv2, b.bn2)) for b in model.residual_blocks]
         self._bufs = {}
         self.fault = None     # optional host-mapped fault word (tests)
+        self.fused_layers = True   # one persistent launch for all layers (False: one launch per layer)
+        layers = [self.stem] + [cv for blk in self.blocks for cv in blk]
+        self._w_ptrs = (C.c_void_p * len(layers))(*[l[0].data_ptr() for l in layers])
+        self._b_ptrs = (C.c_void_p * len(layers))(*[l[1].data_ptr() for l in layers])
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -109,11 +115,20 @@ class HandTower:
         x, y, z = buf["a"], buf["b"], buf["c"]
         if out is None:
             out = buf["out"]       # static: the same addresses every call (CUDA graphs)
-        self.conv(buf["x0"], 1, self.stem, None, x, n_pad, kmajor=True)
-        for c1, c2 in self.blocks:
-            self.conv(x, 2, c1, None, y, n_pad)
-            self.conv(y, 2, c2, x, z, n_pad)
-            x, z = z, x
+        if self.fused_layers:
+            res = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.hz_tower_forward(
+                    buf["x0"].data_ptr(), self._w_ptrs, self._b_ptrs, len(self.blocks), x.data_ptr(), y.data_ptr(), z.data_ptr(),
+                    C.byref(res), n_pad, self.fault, self._stream()), "hz_tower_forward")
+            x_ptr = res.value
+        else:
+            self.conv(buf["x0"], 1, self.stem, None, x, n_pad, kmajor=True)
+            for c1, c2 in self.blocks:
+                self.conv(x, 2, c1, None, y, n_pad)
+                self.conv(y, 2, c2, x, z, n_pad)
+                x, z = z, x
+            x_ptr = x.data_ptr()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.hz_tower_from_tiles(x.data_ptr(), out.data_ptr(), n_pad, self._stream()), "hz_tower_from_tiles")
+            _lib.check(self.lib.hz_tower_from_tiles(x_ptr, out.data_ptr(), n_pad, self._stream()), "hz_tower_from_tiles")
         return out[:B].view(B, 5, 7, 128).permute(0, 3, 1, 2)

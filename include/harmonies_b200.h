@@ -314,6 +314,10 @@ int hz_tower_set_max_ctas(int max_ctas);
  * 1 skip the MMAs, 2 skip the epilogue's memory traffic, 4 skip the weight copies, 8 skip the
  * activation copies.  Used by profiles/tower_bench.py to attribute the kernel's time. */
 int hz_tower_set_debug(int flags);
+/* Profiling: a device buffer of 1024 uint64 (or NULL to switch off) into which CTA 0 of every
+ * following hz_tower_conv3x3 launch writes SM-clock timestamps of its producer / MMA / epilogue
+ * roles (slot map in csrc/hz_tower.cu). */
+int hz_tower_set_trace(unsigned long long *device_buffer_1024);
 
 /* NHWC bf16 [n,35,channels] -> tiles.  kmajor != 0: T16K (channels % 8 == 0, <= 64; missing
  * channels zero); kmajor == 0: T16 (channels must be 128).  Boards that pad n up to a multiple
@@ -331,6 +335,16 @@ int hz_tower_from_tiles(const void *src_tiles, void *dst_nhwc, int64_t n_boards,
 int hz_tower_conv3x3(const void *x_tiles, int in_channel_halves, int in_kmajor, const void *w_tiles,
                      const float *bias, const void *residual_tiles, void *y, int64_t n_boards,
                      int relu, unsigned int *fault, void *stream);
+/* The whole body in ONE persistent launch: stem (layer 0, input x0 = T16K tiles) followed by
+ * n_blocks residual blocks (layers 1 + 2i: conv+bn+relu, 2 + 2i: conv+bn, + block input, relu).
+ * w_tiles / biases: HOST arrays of 1 + 2*n_blocks DEVICE pointers (weight tiles as above, fp32
+ * bias[128]).  buf_a/b/c: three T16 scratch buffers of hz_tower_tile_bytes(n_boards, 2) bytes;
+ * *out_tiles receives the one that holds the result (buf_a or buf_c).  Boards are independent,
+ * so each CTA carries its own tiles through all layers with no grid-wide synchronisation: layer
+ * l+1 of a tile starts as soon as the CTA's own epilogue of layer l has stored it. */
+int hz_tower_forward(const void *x0_tiles, const void *const *w_tiles, const float *const *biases,
+                     int n_blocks, void *buf_a, void *buf_b, void *buf_c, void **out_tiles,
+                     int64_t n_boards, unsigned int *fault, void *stream);
 
 #define HZ_PLAYOUT_SALT 0xA5A5F00DC0FFEE11ull
 #define HZ_SEARCH_SALT  0x5EA2C47EE5A17B00ull

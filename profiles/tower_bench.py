@@ -74,6 +74,27 @@ def main():
         attr[name] = timeit(lambda: ht.conv(buf["a"], 2, c2, buf["b"], buf["c"], n_pad), a.iters)["us_min"]
     ht.lib.hz_tower_set_debug(0)
     out["hand_conv_attribution_us"] = attr
+    # role timeline of CTA 0 (SM clocks): where does a tile's time go?
+    tr = torch.zeros(1024, dtype=torch.int64, device="cuda")
+    ht.lib.hz_tower_set_trace(tr.data_ptr())
+    ht.conv(buf["a"], 2, c2, buf["b"], buf["c"], n_pad)
+    torch.cuda.synchronize()
+    ht.lib.hz_tower_set_trace(None)
+    t = tr.cpu().numpy().astype("int64")
+    t0 = int(t[0])
+    rel = lambda v: int(v - t0) if v else None  # noqa: E731
+    stages = [(rel(t[16 + 3 * i]), rel(t[16 + 3 * i + 1]), rel(t[16 + 3 * i + 2])) for i in range(72) if t[16 + 3 * i]]
+    out["trace"] = {
+        "total_cycles": rel(t[1]),
+        "mma_stage(before_wait,after_wait,after_issue)": stages,
+        "weight_issue": [rel(t[400 + i]) for i in range(72) if t[400 + i]],
+        "act_issue": [rel(t[700 + i]) for i in range(4) if t[700 + i]],
+        "epilogue_rows(before_wait,after_wait,after_tmem_ld,after_stores)": [tuple(rel(t[600 + 4 * j + k]) for k in range(4)) for j in range(10) if t[600 + 4 * j]],
+    }
+    waits = [b - a for a, b, _ in stages]
+    issues = [c - b for _, b, c in stages]
+    out["trace_summary"] = {"mma_wait_cycles_total": sum(waits), "mma_issue_cycles_total": sum(issues),
+                            "mma_wait_max": max(waits) if waits else None}
     hand.tower_out(board)
     x = lib.tower_out(board)
     r = timeit(lambda: lib._conv_relu(x, lib.blocks[0][1], 1, residual=x), a.iters, flush)
@@ -83,7 +104,9 @@ def main():
     r["dense_equiv_tflops"] = dense_flop / r["us_min"] / 1e6
     out["cudnn_conv_warm"] = r
     # whole tower and whole forward (tower + heads), CUDA graph replay like self-play
-    for name, net in (("hand", hand), ("cudnn", lib)):
+    hand_layers = hnet.InferenceNet(model, tower="hand")
+    hand_layers.hand.fused_layers = False
+    for name, net in (("hand", hand), ("hand_per_layer", hand_layers), ("cudnn", lib)):
         logits = torch.zeros((B, 143), dtype=torch.float32, device="cuda")
         value = torch.zeros(B, dtype=torch.float32, device="cuda")
         s = torch.cuda.Stream()

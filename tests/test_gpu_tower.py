@@ -150,6 +150,33 @@ def test_conv_random_values_bf16_tolerance(tw):
     assert float((err - want.abs() * 2.0 ** -8).max()) <= 1e-3
 
 
+def test_fused_launch_equals_layer_by_layer(tw):
+    """The persistent all-layers launch (each CTA carries its tiles through the 17 layers) must
+    reproduce the one-launch-per-layer result bit for bit — also with several tiles per CTA and
+    with more tiles per CTA than the fused launch tracks (it then falls back to per-layer launches)."""
+    from harmonies_alphazero_b200 import net as hnet
+
+    torch.manual_seed(2)
+    model = hnet.AlphaZeroNet.from_config(hnet.DEFAULT_MODEL_CONFIG).eval()
+    hand = hnet.InferenceNet(model, device="cuda", tower="hand")
+    ht = hand.hand
+    B = 16 * 9 + 3
+    g = torch.Generator().manual_seed(4)
+    b40 = torch.zeros((B, 40, 5, 7), dtype=torch.bfloat16, device="cuda").contiguous(memory_format=torch.channels_last)
+    b40[:, :38] = (torch.rand((B, 38, 5, 7), generator=g) < 0.2).to(torch.bfloat16).cuda()
+    ht.fused_layers = False
+    want = ht.forward(b40).clone()
+    ht.fused_layers = True
+    try:
+        for ctas in (0, 4, 1):       # 10 tiles: one per CTA / 3 per CTA / 10 per CTA (> 8: fallback path)
+            ht.lib.hz_tower_set_max_ctas(ctas)
+            got = ht.forward(b40).clone()
+            torch.cuda.synchronize()
+            assert torch.equal(got, want), ctas
+    finally:
+        ht.lib.hz_tower_set_max_ctas(0)
+
+
 def test_whole_tower_against_cudnn_and_fp32(tw):
     from harmonies_alphazero_b200 import net as hnet
 
