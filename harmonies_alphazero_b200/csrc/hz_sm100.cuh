@@ -122,6 +122,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The same MMA with a collector hint for the A operand: consecutive MMAs that share A (here: one
+// weight tile applied to several board rows) read it from shared memory once.  FILL = read A and keep
+// it in the collector (SASS .A_KEEP), USE = take it from the collector and keep it (.A_REUSE.A_KEEP),
+// LASTUSE = take it from the collector and release it (.A_REUSE).
+enum { COLL_DISCARD = 0, COLL_FILL = 1, COLL_USE = 2, COLL_LASTUSE = 3 };
+template <int COLL>
+__device__ __forceinline__ void umma_bf16_coll(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (COLL == COLL_FILL)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b),
+                     "r"(idesc), "r"(accumulate) : "memory");
+    else if (COLL == COLL_USE)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::use [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b),
+                     "r"(idesc), "r"(accumulate) : "memory");
+    else if (COLL == COLL_LASTUSE)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b),
+                     "r"(idesc), "r"(accumulate) : "memory");
+    else
+        umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
 // arrives (count 1) on the mbarrier once every tcgen05 operation issued so far by this thread is done
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -120,6 +120,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
     return d;
 }
 
+// A-operand collector hints (csrc/hz_sm100.cuh): compile-time A/B switch, -DHZ_TOWER_COLLECTOR=0 to disable
+#ifndef HZ_TOWER_COLLECTOR
+#define HZ_TOWER_COLLECTOR 1
+#endif
+
 // ---- MMA issue, fully unrolled -------------------------------------------------------------------
 // One thread issues ~312 MMAs of ~50 tensor-core cycles each per tile, so the issue path has to be
 // a handful of instructions per MMA: the whole warp runs the (warp-uniform) control flow, taps /
@@ -151,17 +156,24 @@ __device__ __forceinline__ void issue_stage(uint32_t a_lo, uint32_t b_lo, uint32
     constexpr int tap = tap_at(PASS, TI), dy = tap / 3 - 1, dx = tap % 3 - 1;
     constexpr int r0 = PASS ? 3 : 0, r1 = PASS ? 5 : 3;
     constexpr uint32_t idesc = idesc_bf16_f32(128, dx ? 96 : 112) | (KMAJOR ? 0u : (1u << 16));
+    // rows of the pass this tap touches: [ra, rb) (always a contiguous range)
+    constexpr int ra = (r0 + dy < 0) ? r0 + 1 : r0, rb = (r1 - 1 + dy >= BROWS) ? r1 - 1 : r1;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
+        const uint64_t da = desc64(a_lo + (uint32_t)(k * 2), DESC_HI_SW128);
 #pragma unroll
-        for (int r = r0; r < r1; r++) {
+        for (int r = ra; r < rb; r++) {
             const int sr = r + dy;
-            if (sr < 0 || sr >= BROWS) continue;
             const int cell0 = sr * BCOLS + (dx > 0 ? 1 : 0);
             const uint32_t boff = KMAJOR ? (uint32_t)((cell0 * (G * 128) + k * 32) >> 4) : (uint32_t)((k * 2 * KG_BYTES + cell0 * (G * 16)) >> 4);
             const uint32_t d = tbase + (uint32_t)(unit_of(r) * UNIT_COLS + (dx < 0 ? G : 0));
-            umma_bf16(d, desc64(a_lo + (uint32_t)(k * 2), DESC_HI_SW128), desc64(b_lo + boff, KMAJOR ? DESC_HI_SW128 : DESC_HI_T16), idesc,
-                      (TI == 0 && k == 0) ? acc_first : 1u);
+            const uint64_t db = desc64(b_lo + boff, KMAJOR ? DESC_HI_SW128 : DESC_HI_T16);
+            const uint32_t acc = (TI == 0 && k == 0) ? acc_first : 1u;
+            // the rows share the weight tile: it is read from shared memory for the first one only
+            if (rb - ra == 1 || !HZ_TOWER_COLLECTOR) umma_bf16_coll<COLL_DISCARD>(d, da, db, idesc, acc);
+            else if (r == ra) umma_bf16_coll<COLL_FILL>(d, da, db, idesc, acc);
+            else if (r == rb - 1) umma_bf16_coll<COLL_LASTUSE>(d, da, db, idesc, acc);
+            else umma_bf16_coll<COLL_USE>(d, da, db, idesc, acc);
         }
     }
 }

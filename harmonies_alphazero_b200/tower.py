@@ -9,7 +9,7 @@ There is no fallback: without the CUDA library every call raises.  ``InferenceNe
 is the A/B switch for measurements.
 """
 
-import ctypes as C
+import ctypes as ct
 
 import torch
 
@@ -64,8 +64,8 @@ class HandTower:
         self.fault = None     # optional host-mapped fault word (tests)
         self.fused_layers = True   # one persistent launch for all layers (False: one launch per layer)
         layers = [self.stem] + [cv for blk in self.blocks for cv in blk]
-        self._w_ptrs = (C.c_void_p * len(layers))(*[l[0].data_ptr() for l in layers])
-        self._b_ptrs = (C.c_void_p * len(layers))(*[l[1].data_ptr() for l in layers])
+        self._w_ptrs = (ct.c_void_p * len(layers))(*[l[0].data_ptr() for l in layers])
+        self._b_ptrs = (ct.c_void_p * len(layers))(*[l[1].data_ptr() for l in layers])
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -116,11 +116,11 @@ class HandTower:
         if out is None:
             out = buf["out"]       # static: the same addresses every call (CUDA graphs)
         if self.fused_layers:
-            res = C.c_void_p()
+            res = ct.c_void_p()
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.hz_tower_forward(
                     buf["x0"].data_ptr(), self._w_ptrs, self._b_ptrs, len(self.blocks), x.data_ptr(), y.data_ptr(), z.data_ptr(),
-                    C.byref(res), n_pad, self.fault, self._stream()), "hz_tower_forward")
+                    ct.byref(res), n_pad, self.fault, self._stream()), "hz_tower_forward")
             x_ptr = res.value
         else:
             self.conv(buf["x0"], 1, self.stem, None, x, n_pad, kmajor=True)
