@@ -39,6 +39,8 @@ SIGNATURES = {
     "hz_tree_stats": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "hz_tree_root_edges": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "hz_net_heads": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
+    "hz_net_head_conv_t16": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "hz_net_heads_fc": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "hz_tower_tile_bytes": (C.c_size_t, [_i64, _i]),
     "hz_tower_set_max_ctas": (_i, [_i]),
     "hz_tower_set_debug": (_i, [_i]),

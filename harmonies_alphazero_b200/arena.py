@@ -18,10 +18,14 @@ from .tree import BatchedMCTS
 def _search(tree, net, states, sims, cpuct, bufs):
     board, glob, logits, value = bufs
     tree.reset(states)
-    pad40 = board.shape[1] == 40
+    tiles = board.dtype == torch.uint8
+    pad40 = not tiles and board.shape[1] == 40
     for _ in range(sims // tree.leaves):
-        tree.select(cpuct, board, glob, dtype=net.dtype, channels_last=True, pad40=pad40)
-        net(board, glob, out=(logits, value))
+        tree.select(cpuct, board, glob, dtype=net.dtype, channels_last=True, pad40=pad40, tiles=tiles)
+        if tiles:
+            net.forward_tiles(board, glob, glob.shape[0], out=(logits, value))
+        else:
+            net(board, glob, out=(logits, value))
         tree.expand_backup(logits, value, is_logits=True)
 
 
@@ -52,13 +56,17 @@ def play_match(candidate_net, best_net, num_games, mcts_config_eval, device="cud
         if anynet is not None:                                       # greedy vs greedy needs no search arena
             tree = BatchedMCTS(n, sims, device=dev, key_mode=key_mode, leaves=leaves)
             rows = n * leaves
-            C = 40 if hasattr(anynet, "stem40") else 38
-            bufs = (
-                torch.empty((rows, C, 5, 7), dtype=anynet.dtype, device=dev, memory_format=torch.channels_last).zero_(),
-                torch.zeros((rows, 42), dtype=anynet.dtype, device=dev),
-                torch.zeros((rows, 143), dtype=torch.float32, device=dev),
-                torch.zeros(rows, dtype=torch.float32, device=dev),
-            )
+            both_tiles = all(x is GREEDY or getattr(x, "wants_tiles", False) for x in (candidate_net, best_net))
+            if both_tiles:                       # both sides evaluate from the hand-written tower's input image
+                bufs = anynet.leaf_buffers(rows)
+            else:
+                C = 40 if hasattr(anynet, "stem40") else 38
+                bufs = (
+                    torch.empty((rows, C, 5, 7), dtype=anynet.dtype, device=dev, memory_format=torch.channels_last).zero_(),
+                    torch.zeros((rows, 42), dtype=anynet.dtype, device=dev),
+                    torch.zeros((rows, 143), dtype=torch.float32, device=dev),
+                    torch.zeros(rows, dtype=torch.float32, device=dev),
+                )
         for _ in range(200):
             over, oc = hb.outcome(states)
             if bool(over.all()):

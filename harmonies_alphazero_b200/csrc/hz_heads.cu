@@ -215,9 +215,11 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 lo, __nv_bfloat16 hi
     return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
 }
 
+// hc (nullable): the 1x1 head convolutions already evaluated (hz_net_head_conv_t16): [n][105] fp32 =
+// relu(conv + bias) as policy ch0 [35 cells], policy ch1 [35], value ch0 [35]; phase 1 is then a copy.
 __global__ void __launch_bounds__(FTPB, 1) k_heads_p(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ glob,
                                                      int64_t n, HeadParams P, float* __restrict__ logits,
-                                                     float* __restrict__ value) {
+                                                     float* __restrict__ value, const float* __restrict__ hc) {
     extern __shared__ __align__(16) float smem[];
     float* s_wp = smem;                      // [112][143] (+ slack)
     float* s_wv = s_wp + WPN;                // [77][256]
@@ -238,13 +240,14 @@ __global__ void __launch_bounds__(FTPB, 1) k_heads_p(const __nv_bfloat16* __rest
 #pragma unroll
         for (int w = 0; w < 2; w++) {
             int ch = 32 * (ks >> 1) + 8 * q4 + 4 * (ks & 1) + 2 * w;
-            float w0 = g8 < 3 ? P.w_conv[g8 * FC + ch] : 0.0f, w1 = g8 < 3 ? P.w_conv[g8 * FC + ch + 1] : 0.0f;
+            const bool live = g8 < 3 && !hc;
+            float w0 = live ? P.w_conv[g8 * FC + ch] : 0.0f, w1 = live ? P.w_conv[g8 * FC + ch + 1] : 0.0f;
             __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
             bh[ks * 2 + w] = pack_bf16(h0, h1);
             bl[ks * 2 + w] = pack_bf16(__float2bfloat16_rn(w0 - __bfloat162float(h0)), __float2bfloat16_rn(w1 - __bfloat162float(h1)));
         }
     }
-    const float bc0 = P.b_conv[0], bc1 = P.b_conv[1], bc2 = P.b_conv[2];
+    const float bc0 = hc ? 0.0f : P.b_conv[0], bc1 = hc ? 0.0f : P.b_conv[1], bc2 = hc ? 0.0f : P.b_conv[2];
     int64_t n_groups = (n + FG - 1) / FG;
     bool weights_pending = true;
     for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
@@ -252,8 +255,16 @@ __global__ void __launch_bounds__(FTPB, 1) k_heads_p(const __nv_bfloat16* __rest
         int cnt = (int)min((int64_t)FG, n - base), ncell = cnt * CELLS;
         __syncthreads();
         // ---- phase 1: 1x1 convs + ReLU (model.py:340-343,349-351)
+        if (hc) {
+            for (int i = t; i < cnt * 3 * CELLS; i += FTPB) {
+                int p = i / (3 * CELLS), j = i - 3 * CELLS * p;
+                float v = hc[(base + p) * (3 * CELLS) + j];
+                if (j < 2 * CELLS) s_pin[p * PIN + j] = v;
+                else s_vin[p * 80 + j - 2 * CELLS] = v;
+            }
+        }
         const uint4* rows = reinterpret_cast<const uint4*>(x + base * CELLS * (int64_t)FC);
-        for (int tile = warp; tile * 16 < ncell; tile += FTPB / 32) {
+        for (int tile = warp; !hc && tile * 16 < ncell; tile += FTPB / 32) {
             int r0 = tile * 16 + g8, r1 = r0 + 8;
             uint4 qa[4], qb[4];
 #pragma unroll
@@ -373,7 +384,89 @@ __global__ void __launch_bounds__(FTPB, 1) k_heads_p(const __nv_bfloat16* __rest
     }
 }
 
+// ---- 1x1 head convolutions on the tower's T16 tiles (include/harmonies_b200.h) --------------------
+// One block per 16-board tile.  Thread = (8 consecutive positions, one quarter of the channels): a
+// 16-byte load is 8 positions of one channel, so the loads are coalesced without any transpose; the
+// four channel quarters meet in shared memory.  fp32 weights, fp32 accumulation.
+constexpr int HCT = 320;
+__global__ void __launch_bounds__(HCT) k_head_conv_t16(const uint8_t* __restrict__ tiles, int64_t n, const float* __restrict__ w_conv,
+                                                       const float* __restrict__ b_conv, float* __restrict__ hc) {
+    __shared__ float s_w[3 * 128];
+    __shared__ float s_part[4][3][560];
+    const int t = threadIdx.x;
+    for (int i = t; i < 3 * 128; i += HCT) s_w[i] = w_conv[i];
+    __syncthreads();
+    const int64_t tile = blockIdx.x;
+    const uint8_t* base = tiles + tile * (size_t)(2 * 71680);
+    if (t < 280) {
+        const int pg = t % 70, cq = t / 70;
+        float acc[3][8];
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int e = 0; e < 8; e++) acc[j][e] = 0.0f;
+#pragma unroll 8
+        for (int ci = 0; ci < 32; ci++) {
+            const int c = cq * 32 + ci;
+            const uint4 q = *reinterpret_cast<const uint4*>(base + (size_t)(c >> 3) * 8960 + pg * 128 + (c & 7) * 16);
+            const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+            const float w0 = s_w[c], w1 = s_w[128 + c], w2 = s_w[256 + c];
+#pragma unroll
+            for (int h = 0; h < 4; h++) {
+                const float lo = __uint_as_float(qw[h] << 16), hi = __uint_as_float(qw[h] & 0xFFFF0000u);
+                acc[0][2 * h] = fmaf(w0, lo, acc[0][2 * h]); acc[0][2 * h + 1] = fmaf(w0, hi, acc[0][2 * h + 1]);
+                acc[1][2 * h] = fmaf(w1, lo, acc[1][2 * h]); acc[1][2 * h + 1] = fmaf(w1, hi, acc[1][2 * h + 1]);
+                acc[2][2 * h] = fmaf(w2, lo, acc[2][2 * h]); acc[2][2 * h + 1] = fmaf(w2, hi, acc[2][2 * h + 1]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int e = 0; e < 8; e++) s_part[cq][j][pg * 8 + e] = acc[j][e];
+    }
+    __syncthreads();
+    for (int i = t; i < 3 * 560; i += HCT) {
+        const int j = i / 560, p = i - 560 * j;
+        const int cell = p >> 4;
+        const int64_t board = tile * 16 + (p & 15);
+        if (board < n) {
+            float v = ((s_part[0][j][p] + s_part[1][j][p]) + (s_part[2][j][p] + s_part[3][j][p])) + b_conv[j];
+            hc[board * (3 * CELLS) + j * CELLS + cell] = fmaxf(v, 0.0f);
+        }
+    }
+}
+
 }  // namespace hz
+
+extern "C" int hz_net_head_conv_t16(const void* x_tiles, int64_t n, const float* w_conv, const float* b_conv, float* head_conv,
+                                    void* stream) {
+    if (n == 0) return HZ_OK;
+    if (!x_tiles || !w_conv || !b_conv || !head_conv || n < 0 || ((uintptr_t)x_tiles & 15)) return HZ_ERR_ARG;
+    int64_t tiles = (n + 15) / 16;
+    hz::k_head_conv_t16<<<(unsigned)tiles, hz::HCT, 0, (cudaStream_t)stream>>>((const uint8_t*)x_tiles, n, w_conv, b_conv, head_conv);
+    return hz_launched(1);
+}
+
+extern "C" int hz_net_heads_fc(const float* head_conv, const void* glob, int64_t n, int H, const float* w_pol_t, const float* b_pol,
+                               const float* w_v1_t, const float* b_v1, const float* w_v2, float b_v2, float* logits, float* value,
+                               void* stream) {
+    if (n == 0) return HZ_OK;
+    if (!head_conv || !glob || !w_pol_t || !b_pol || !w_v1_t || !b_v1 || !w_v2 || !logits || !value || n < 0) return HZ_ERR_ARG;
+    if (H != hz::FH || (((uintptr_t)w_v1_t | (uintptr_t)w_pol_t) & 15)) return HZ_ERR_ARG;
+    hz::HeadParams P{nullptr, nullptr, w_pol_t, b_pol, w_v1_t, b_v1, w_v2, b_v2, hz::FC, H};
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(hz::k_heads_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hz::FSMEM);
+        if (e != cudaSuccess) return hz_record_launch(0, e);
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    int64_t fgroups = (n + hz::FG - 1) / hz::FG;
+    int fgrid = (int)(fgroups < 148 ? fgroups : 148);
+    hz::k_heads_p<<<fgrid, hz::FTPB, hz::FSMEM, (cudaStream_t)stream>>>(nullptr, (const __nv_bfloat16*)glob, n, P, logits, value, head_conv);
+    return hz_launched(1);
+}
 
 extern "C" int hz_net_heads(const void* x, const void* glob, int64_t n, int C, int H, const float* w_conv,
                             const float* b_conv, const float* w_pol_t, const float* b_pol, const float* w_v1_t,
@@ -397,7 +490,7 @@ extern "C" int hz_net_heads(const void* x, const void* glob, int64_t n, int C, i
         int64_t fgroups = (n + hz::FG - 1) / hz::FG;
         int fgrid = (int)(fgroups < 148 ? fgroups : 148);
         hz::k_heads_p<<<fgrid, hz::FTPB, hz::FSMEM, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)glob,
-                                                                            n, P, logits, value);
+                                                                            n, P, logits, value, nullptr);
         return hz_launched(1);
     }
     size_t smem = sizeof(float) * (size_t)(3 * C + hz::HP * hz::PIN + hz::HP * 80 + hz::HP * 8);

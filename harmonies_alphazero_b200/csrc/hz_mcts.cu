@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(TTPB) k_tree_reset(hz_tree T, const uint4* roo
 // ---- warp-level state encoding (shared with hz_encode's definition of the tensors) -----------
 // LAYOUT: HZ_LAYOUT_NCHW, HZ_LAYOUT_NHWC, or HZ_LAYOUT_NHWC40 (channel stride 40, channels 38
 // and 39 written as zero: the stem convolution then needs no cuDNN input-padding kernel)
-template <int LAYOUT> struct RowElems { static constexpr int value = LAYOUT == HZ_LAYOUT_NHWC40 ? 1400 : 1330; };
+template <int LAYOUT> struct RowElems { static constexpr int value = LAYOUT == HZ_LAYOUT_NHWC40 ? 1400 : 1330; };   // (T16K never takes the generic path)
 template <typename T, int LAYOUT>
 __device__ __forceinline__ void warp_encode(const uint32_t* w, uint32_t* smask, T* board, T* glob, int lane) {
     for (int c = lane; c < 40; c += 32) smask[c] = c < 38 ? channel_mask(w, c) : 0u;
@@ -128,8 +128,12 @@ __device__ __forceinline__ void warp_encode(const uint32_t* w, uint32_t* smask, 
 // 5 bytes of bits (<= 3+3 tile codes + player + phase), and 8 bits expand to a 16-byte vector
 // of bf16 0.0/1.0 by one table lookup: 35 cells x 5 vectors = 175 16-byte stores per leaf
 // instead of 1,400 scalar ones.
+// T16K = true: the 16-byte groups go straight into the stem's tensor-core operand image
+// (include/harmonies_b200.h "T16K": tile of 16 leaves, row p = cell*16 + leaf, group j at j ^ (p & 7));
+// groups 5..7 (channels 40..63) of a row are never written and must have been zeroed once.
+template <bool T16K>
 __device__ __forceinline__ void warp_encode_fast40(const uint32_t* w, uint8_t* sbytes, const uint4* vlut8,
-                                                   const uint8_t* scell, __nv_bfloat16* board, __nv_bfloat16* glob, int lane) {
+                                                   const uint8_t* scell, __nv_bfloat16* board, size_t row, __nv_bfloat16* glob, int lane) {
     uint32_t m = w[HZ_W_BAG1META] >> 24, ph = (m >> 1) & 7u;
     bool player1 = (m & 1u) != 0, phase_on = ph >= 1 && ph <= 3;
     for (int cell = lane; cell < 35; cell += 32) {
@@ -151,12 +155,19 @@ __device__ __forceinline__ void warp_encode_fast40(const uint32_t* w, uint8_t* s
     __syncwarp();
     float pv = ph == 1 ? (float)(1.0 / 3.0) : ph == 2 ? (float)(2.0 / 3.0) : 1.0f;
     uint32_t pb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(pv));
-    uint4* out = reinterpret_cast<uint4*>(board);
+    uint4* out = reinterpret_cast<uint4*>(board + row * 1400);
+    uint8_t* tile = reinterpret_cast<uint8_t*>(board) + (row >> 4) * (size_t)(560 * 128);
+    const int leaf = (int)(row & 15);
     for (int v = lane; v < 175; v += 32) {
         uint32_t byte = sbytes[v];
         uint4 o = vlut8[byte];
         if (v % 5 == 4 && (byte & 0x20u)) o.z = (o.z & 0x0000FFFFu) | (pb << 16);   // channel 37 = phase/3
-        out[v] = o;
+        if (T16K) {
+            int cell = v / 5, j = v - 5 * cell, p = cell * 16 + leaf;
+            *reinterpret_cast<uint4*>(tile + p * 128 + ((j ^ (p & 7)) << 4)) = o;
+        } else {
+            out[v] = o;
+        }
     }
     for (int g = lane; g < 42; g += 32) glob[g] = __float2bfloat16_rn(global_feature(w, g));
     __syncwarp();
@@ -167,7 +178,8 @@ template <typename OT, int LAYOUT>
 __global__ void __launch_bounds__(TTPB) k_tree_select(hz_tree T, float cpuct, uint4* leaf_states, OT* board, OT* glob) {
     __shared__ uint32_t sm_words[WPB][32];
     __shared__ uint32_t sm_mask[WPB][40];
-    constexpr bool FAST40 = LAYOUT == HZ_LAYOUT_NHWC40 && sizeof(OT) == 2;
+    constexpr bool FAST40 = (LAYOUT == HZ_LAYOUT_NHWC40 || LAYOUT == HZ_LAYOUT_T16K) && sizeof(OT) == 2;
+    static_assert(LAYOUT != HZ_LAYOUT_T16K || sizeof(OT) == 2, "the T16K image is bf16");
     __shared__ uint4 vlut8[FAST40 ? 256 : 1];
     __shared__ uint8_t sbytes[FAST40 ? WPB : 1][176];
     __shared__ uint8_t scell[36];
@@ -269,8 +281,8 @@ __global__ void __launch_bounds__(TTPB) k_tree_select(hz_tree T, float cpuct, ui
         if (leaf_states) reinterpret_cast<uint32_t*>(leaf_states + row * 8)[lane] = sm_words[warp][lane];
         if (board) {
             if constexpr (FAST40)
-                warp_encode_fast40(sm_words[warp], sbytes[warp], vlut8, scell, (__nv_bfloat16*)board + row * 1400,
-                                   (__nv_bfloat16*)glob + row * 42, lane);
+                warp_encode_fast40<LAYOUT == HZ_LAYOUT_T16K>(sm_words[warp], sbytes[warp], vlut8, scell, (__nv_bfloat16*)board, row,
+                                                             (__nv_bfloat16*)glob + row * 42, lane);
             else
                 warp_encode<OT, LAYOUT>(sm_words[warp], sm_mask[warp], board + row * RowElems<LAYOUT>::value, glob + row * 42, lane);
         }
@@ -677,14 +689,16 @@ int hz_tree_select(hz_tree* t, float cpuct, void* leaf_states, void* board, void
     cudaStream_t st = (cudaStream_t)stream;
     int grid = tree_blocks(t->n_trees, WPB);
     uint4* ls = (uint4*)leaf_states;
-    if (layout != HZ_LAYOUT_NCHW && layout != HZ_LAYOUT_NHWC && layout != HZ_LAYOUT_NHWC40) return HZ_ERR_ARG;
+    if (layout != HZ_LAYOUT_NCHW && layout != HZ_LAYOUT_NHWC && layout != HZ_LAYOUT_NHWC40 && layout != HZ_LAYOUT_T16K) return HZ_ERR_ARG;
+    if (layout == HZ_LAYOUT_T16K && dtype != HZ_DTYPE_BF16) return HZ_ERR_ARG;
 #define HZ_SELECT(T, L) k_tree_select<T, L><<<grid, TTPB, 0, st>>>(*t, cpuct, ls, (T*)board, (T*)glob)
     if (dtype == HZ_DTYPE_F32) {
         if (layout == HZ_LAYOUT_NHWC40) HZ_SELECT(float, HZ_LAYOUT_NHWC40);
         else if (layout == HZ_LAYOUT_NHWC) HZ_SELECT(float, HZ_LAYOUT_NHWC);
         else HZ_SELECT(float, HZ_LAYOUT_NCHW);
     } else if (dtype == HZ_DTYPE_BF16) {
-        if (layout == HZ_LAYOUT_NHWC40) HZ_SELECT(__nv_bfloat16, HZ_LAYOUT_NHWC40);
+        if (layout == HZ_LAYOUT_T16K) HZ_SELECT(__nv_bfloat16, HZ_LAYOUT_T16K);
+        else if (layout == HZ_LAYOUT_NHWC40) HZ_SELECT(__nv_bfloat16, HZ_LAYOUT_NHWC40);
         else if (layout == HZ_LAYOUT_NHWC) HZ_SELECT(__nv_bfloat16, HZ_LAYOUT_NHWC);
         else HZ_SELECT(__nv_bfloat16, HZ_LAYOUT_NCHW);
     } else {

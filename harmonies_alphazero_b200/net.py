@@ -102,6 +102,7 @@ class InferenceNet:
             raise ValueError("the hand-written tower is bf16 on CUDA only")
         self.tower = tower
         self.hand = None
+        self._hc = {}
         self.load(model)
 
     def load(self, model):
@@ -194,6 +195,59 @@ class InferenceNet:
                 h["w_v2"].data_ptr(), h["b_v2"], logits.data_ptr(), value.data_ptr(),
                 torch.cuda.current_stream(x.device).cuda_stream), "hz_net_heads")
         return logits, value
+
+    # ---- leaf-evaluation plumbing shared by selfplay / arena -----------------------------------
+    @property
+    def wants_tiles(self):
+        """True when leaves should be encoded straight into the hand-written tower's input image
+        (hz_tree_select layout HZ_LAYOUT_T16K) and evaluated with ``forward_tiles``."""
+        return self.hand is not None and self.heads is not None and self.use_fused_heads and self.heads["C"] == 128 and self.heads["H"] == 256
+
+    def leaf_buffers(self, rows):
+        """(board, glob, logits, value) static buffers for ``rows`` leaves per step."""
+        dev = self.device
+        if self.wants_tiles:
+            board = self.hand.x0_buffer(rows)
+        else:
+            cl = dev.type == "cuda"
+            board = torch.empty((rows, 40 if (cl and hasattr(self, "stem40")) else 38, 5, 7), dtype=self.dtype, device=dev,
+                                memory_format=torch.channels_last if cl else torch.contiguous_format).zero_()
+        return (board, torch.zeros((rows, 42), dtype=self.dtype, device=dev),
+                torch.zeros((rows, 143), dtype=torch.float32, device=dev), torch.zeros(rows, dtype=torch.float32, device=dev))
+
+    @torch.no_grad()
+    def forward_tiles(self, x0, glob, n, out=None):
+        """Leaves already in the T16K image (hz_tree_select, HZ_LAYOUT_T16K): hand-written tower, the
+        1x1 head convolutions straight from its T16 output, then the FC heads.  No layout-conversion
+        kernels on this path."""
+        from . import _lib
+
+        if not self.wants_tiles:
+            raise ValueError("forward_tiles needs tower='hand' and the default head shape")
+        h = self.heads
+        if out is None:
+            out = (torch.empty((n, 143), dtype=torch.float32, device=self.device), torch.empty(n, dtype=torch.float32, device=self.device))
+        logits, value = out
+        hc = self._hc.get(n)
+        if hc is None:
+            hc = self._hc[n] = torch.zeros((n, 105), dtype=torch.float32, device=self.device)
+        x_ptr = self.hand.forward_tiles(x0, n)
+        lib = _lib.load()
+        glob = glob.contiguous()
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(lib.hz_net_head_conv_t16(x_ptr, n, h["w_conv"].data_ptr(), h["b_conv"].data_ptr(), hc.data_ptr(), st), "hz_net_head_conv_t16")
+            _lib.check(lib.hz_net_heads_fc(hc.data_ptr(), glob.data_ptr(), n, h["H"], h["w_pol_t"].data_ptr(), h["b_pol"].data_ptr(),
+                                           h["w_v1_t"].data_ptr(), h["b_v1"].data_ptr(), h["w_v2"].data_ptr(), h["b_v2"],
+                                           logits.data_ptr(), value.data_ptr(), st), "hz_net_heads_fc")
+        return logits, value
+
+    @torch.no_grad()
+    def evaluate(self, board, glob, out):
+        """``board`` as produced for this net by ``leaf_buffers`` (tiles or a tensor)."""
+        if self.wants_tiles:
+            return self.forward_tiles(board, glob, glob.shape[0], out=out)
+        return self.forward(board, glob, out=out)
 
     @torch.no_grad()
     def forward(self, board, glob, out=None):

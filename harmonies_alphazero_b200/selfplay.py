@@ -132,11 +132,15 @@ class _Group:
         self.tree = BatchedMCTS(n, cfg.num_simulations, device=dev, key_mode=cfg.key_mode, max_nodes=cfg.max_nodes, leaves=K)
         rows = n * K                  # the network sees K leaves per tree and step
         dt, cl = net.dtype, owner.channels_last
-        self.board = torch.empty((rows, 40 if owner.pad40 else 38, 5, 7), dtype=dt, device=dev,
-                                 memory_format=torch.channels_last if cl else torch.contiguous_format).zero_()
-        self.glob = torch.zeros((rows, 42), dtype=dt, device=dev)
-        self.logits = torch.zeros((rows, 143), dtype=torch.float32, device=dev)
-        self.value = torch.zeros(rows, dtype=torch.float32, device=dev)
+        self.tiles = bool(getattr(net, "wants_tiles", False))   # leaves go straight into the hand-written tower's input image
+        if self.tiles:
+            self.board, self.glob, self.logits, self.value = net.leaf_buffers(rows)
+        else:
+            self.board = torch.empty((rows, 40 if owner.pad40 else 38, 5, 7), dtype=dt, device=dev,
+                                     memory_format=torch.channels_last if cl else torch.contiguous_format).zero_()
+            self.glob = torch.zeros((rows, 42), dtype=dt, device=dev)
+            self.logits = torch.zeros((rows, 143), dtype=torch.float32, device=dev)
+            self.value = torch.zeros(rows, dtype=torch.float32, device=dev)
         self.noise = None if cfg.testing else torch.ones((n, 143), dtype=torch.float32, device=dev)
         self.alpha = None if cfg.testing else torch.full((n, 143), cfg.dirichlet_alpha, dtype=torch.float32, device=dev)
         self.graph = None
@@ -145,9 +149,11 @@ class _Group:
     def sim_step(self):
         """one simulation for every tree of the group: select -> network -> expand+backup"""
         o, t = self.o, self.tree
-        t.select(o.cfg.cpuct, self.board, self.glob, dtype=o.net.dtype, channels_last=o.channels_last, pad40=o.pad40)
+        t.select(o.cfg.cpuct, self.board, self.glob, dtype=o.net.dtype, channels_last=o.channels_last, pad40=o.pad40, tiles=self.tiles)
         if getattr(o.net, "tree_eval", False):
             t.fake_eval(self.logits, self.value)       # priors, not logits
+        elif self.tiles:
+            o.net.forward_tiles(self.board, self.glob, self.glob.shape[0], out=(self.logits, self.value))
         elif o._net_takes_out:        # InferenceNet writes straight into the static buffers
             o.net(self.board, self.glob, out=(self.logits, self.value))
         else:

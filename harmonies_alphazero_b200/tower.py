@@ -99,6 +99,32 @@ class HandTower:
                 x.data_ptr(), halves, 1 if kmajor else 0, img.data_ptr(), bias.data_ptr(), None if res is None else res.data_ptr(),
                 y.data_ptr(), n_pad, 1 if relu else 0, self.fault, self._stream()), "hz_tower_conv3x3")
 
+    def x0_buffer(self, n):
+        """Zeroed T16K input buffer for n boards (what hz_tree_select writes with HZ_LAYOUT_T16K)."""
+        n_pad = (n + G - 1) // G * G
+        return torch.zeros(n_pad // G * KH_BYTES, dtype=torch.uint8, device=self.device)
+
+    @torch.no_grad()
+    def forward_tiles(self, x0, n):
+        """x0: T16K tiles of n boards.  Returns the address of the T16 tiles holding the tower output
+        (one of this object's scratch buffers: valid until the next call with the same n)."""
+        n_pad = (n + G - 1) // G * G
+        buf = self._buffers(n_pad)
+        x, y, z = buf["a"], buf["b"], buf["c"]
+        if self.fused_layers:
+            res = ct.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.hz_tower_forward(
+                    x0.data_ptr(), self._w_ptrs, self._b_ptrs, len(self.blocks), x.data_ptr(), y.data_ptr(), z.data_ptr(),
+                    ct.byref(res), n_pad, self.fault, self._stream()), "hz_tower_forward")
+            return res.value
+        self.conv(x0, 1, self.stem, None, x, n_pad, kmajor=True)
+        for c1, c2 in self.blocks:
+            self.conv(x, 2, c1, None, y, n_pad)
+            self.conv(y, 2, c2, x, z, n_pad)
+            x, z = z, x
+        return x.data_ptr()
+
     @torch.no_grad()
     def forward(self, board, out=None):
         """board: bf16 [B, C, 5, 7] in channels-last memory (NHWC, C = 38 or 40 with zero planes
@@ -112,23 +138,9 @@ class HandTower:
         n_pad = (B + G - 1) // G * G
         buf = self._buffers(n_pad)
         self.to_tiles(board, C, True, buf["x0"])
-        x, y, z = buf["a"], buf["b"], buf["c"]
         if out is None:
             out = buf["out"]       # static: the same addresses every call (CUDA graphs)
-        if self.fused_layers:
-            res = ct.c_void_p()
-            with torch.cuda.device(self.device):
-                _lib.check(self.lib.hz_tower_forward(
-                    buf["x0"].data_ptr(), self._w_ptrs, self._b_ptrs, len(self.blocks), x.data_ptr(), y.data_ptr(), z.data_ptr(),
-                    ct.byref(res), n_pad, self.fault, self._stream()), "hz_tower_forward")
-            x_ptr = res.value
-        else:
-            self.conv(buf["x0"], 1, self.stem, None, x, n_pad, kmajor=True)
-            for c1, c2 in self.blocks:
-                self.conv(x, 2, c1, None, y, n_pad)
-                self.conv(y, 2, c2, x, z, n_pad)
-                x, z = z, x
-            x_ptr = x.data_ptr()
+        x_ptr = self.forward_tiles(buf["x0"], n_pad)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.hz_tower_from_tiles(x_ptr, out.data_ptr(), n_pad, self._stream()), "hz_tower_from_tiles")
         return out[:B].view(B, 5, 7, 128).permute(0, 3, 1, 2)

@@ -52,12 +52,15 @@ class BatchedMCTS:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.hz_tree_reset(self.handle, _ptr(root_states), _ptr(search_keys), self._stream()), "hz_tree_reset")
 
-    def select(self, cpuct, board=None, glob=None, leaf_states=None, dtype=torch.float32, channels_last=False, pad40=False):
+    def select(self, cpuct, board=None, glob=None, leaf_states=None, dtype=torch.float32, channels_last=False, pad40=False, tiles=False):
         """move_to_leaf for every tree + encoding of the leaves into (board, glob).
-        pad40: board is [n,40,5,7] channels-last (HZ_LAYOUT_NHWC40, two zero channels)."""
+        pad40: board is [n,40,5,7] channels-last (HZ_LAYOUT_NHWC40, two zero channels).
+        tiles: board is the uint8 T16K image of the hand-written tower (HZ_LAYOUT_T16K, bf16)."""
         code = {torch.float32: F32, torch.bfloat16: BF16}[dtype]
-        layout = 2 if pad40 else (NHWC if channels_last else NCHW)
-        if board is not None:
+        layout = 3 if tiles else 2 if pad40 else (NHWC if channels_last else NCHW)
+        if tiles:
+            assert board.dtype == torch.uint8 and board.numel() >= (self.rows + 15) // 16 * 71680 and glob.shape[0] == self.rows
+        elif board is not None:
             assert board.shape[1] == (40 if pad40 else 38) and board.shape[0] == self.rows and glob.shape[0] == self.rows
         with torch.cuda.device(self.device):
             _lib.check(

@@ -128,6 +128,8 @@ extern "C" {
 #define HZ_LAYOUT_NCHW 0
 #define HZ_LAYOUT_NHWC 1
 #define HZ_LAYOUT_NHWC40 2  /* hz_tree_select only: [n,5,7,40], channels 38,39 = 0 (8-aligned C for the stem conv) */
+#define HZ_LAYOUT_T16K   3  /* hz_tree_select only, bf16: the stem's tensor-core operand image of hz_tower_* ("T16K",
+                             * 71,680 bytes per 16 leaves); bytes of channels 40..63 are not written: zero the buffer once */
 
 /* node-key modes (hz_canon_hash, hz_tree_create):
  *  HZ_KEY_EXACT     identity = equality of get_canonical_tuple (harmonies_engine.py:81-118)
@@ -292,6 +294,17 @@ int hz_net_heads(const void *x, const void *glob, int64_t n, int C, int H, const
                  const float *b_conv, const float *w_pol_t, const float *b_pol,
                  const float *w_v1_t, const float *b_v1, const float *w_v2, float b_v2,
                  float *logits, float *value, void *stream);
+
+/* The same heads when the tower output is in T16 tiles (hz_tower_forward): first the 1x1 head
+ * convolutions + BatchNorm + ReLU straight from the tiles (model.py:340-343,349-351) into
+ * head_conv [n,105] fp32 = policy channel 0 [35 cells], policy channel 1 [35], value channel [35]
+ * (w_conv [3][128], b_conv [3] as for hz_net_heads), then the FC layers (model.py:344-355; the
+ * default network's shape only: 128 filters, H = 256). */
+int hz_net_head_conv_t16(const void *x_tiles, int64_t n, const float *w_conv, const float *b_conv,
+                         float *head_conv, void *stream);
+int hz_net_heads_fc(const float *head_conv, const void *glob, int64_t n, int H, const float *w_pol_t,
+                    const float *b_pol, const float *w_v1_t, const float *b_v1, const float *w_v2,
+                    float b_v2, float *logits, float *value, void *stream);
 
 /* ---- residual tower (model.py:325-339, ResidualBlock.forward model.py:380-392) -----------
  * Hand-written sm_100a 3x3 convolution (tcgen05.mma, accumulators in tensor memory, operands

@@ -219,3 +219,75 @@ def test_whole_tower_against_cudnn_and_fp32(tw):
             x = blk(x)
     tol = 0.03 * float(x.abs().max())
     assert float((xh - x).abs().max()) <= tol and float((xl - x).abs().max()) <= tol
+
+
+def test_leaf_encoder_writes_the_stem_image(tw):
+    """hz_tree_select with HZ_LAYOUT_T16K must produce byte for byte what hz_tower_to_tiles makes of
+    the NHWC40 encoding of the same leaves (no layout-conversion kernel on the self-play path)."""
+    from harmonies_alphazero_b200 import batched as hb
+    from harmonies_alphazero_b200 import tree as tr
+
+    n, K = 37, 2
+    st = hb.init_states(n, seed=5)
+    hb.playout(st, max_steps=11)
+    raw = _Raw(tw)
+    outs = []
+    for tiles in (False, True):
+        t = tr.BatchedMCTS(n, 8, leaves=K)
+        t.reset(st, tr.search_keys_tensor(np.arange(n, dtype=np.uint64)))
+        t.run_synthetic(4, 2.0)              # a few simulations so that the leaves are not all the root
+        rows = n * K
+        glob = torch.zeros((rows, 42), dtype=torch.bfloat16, device="cuda")
+        if tiles:
+            board = torch.zeros((rows + 15) // 16 * tw.KH_BYTES, dtype=torch.uint8, device="cuda")
+        else:
+            board = torch.zeros((rows, 40, 5, 7), dtype=torch.bfloat16, device="cuda").contiguous(memory_format=torch.channels_last)
+        t.select(2.0, board, glob, dtype=torch.bfloat16, channels_last=True, pad40=not tiles, tiles=tiles)
+        torch.cuda.synchronize()
+        outs.append((board, glob))
+    want = torch.zeros_like(outs[1][0])
+    raw.t.to_tiles(outs[0][0], 40, True, want)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[1][0], want)
+    assert torch.equal(outs[1][1], outs[0][1])
+
+
+def test_tile_path_equals_tensor_path(tw):
+    """InferenceNet.forward_tiles (encoder image -> tower -> head convs from T16 -> FC heads) against
+    the tensor path of the same network (to_tiles / from_tiles / hz_net_heads).  The towers are the
+    same kernel (identical bits); the 1x1 head convolutions differ in arithmetic only (fp32 FMA vs
+    bf16 hi+lo tensor-core split, both fp32-weight accurate): tolerance 1e-4 absolute on O(1) logits."""
+    from harmonies_alphazero_b200 import net as hnet
+
+    torch.manual_seed(3)
+    model = hnet.AlphaZeroNet.from_config(hnet.DEFAULT_MODEL_CONFIG).eval()
+    hand = hnet.InferenceNet(model, device="cuda", tower="hand")
+    assert hand.wants_tiles
+    B = 50
+    g = torch.Generator().manual_seed(9)
+    b40 = torch.zeros((B, 40, 5, 7), dtype=torch.bfloat16, device="cuda").contiguous(memory_format=torch.channels_last)
+    b40[:, :38] = (torch.rand((B, 38, 5, 7), generator=g) < 0.2).to(torch.bfloat16).cuda()
+    glob = torch.rand((B, 42), generator=g).to(torch.bfloat16).cuda()
+    l1, v1 = hand(b40, glob)
+    x0 = hand.hand.x0_buffer(B)
+    hand.hand.to_tiles(b40, 40, True, x0)
+    l2, v2 = hand.forward_tiles(x0, glob, B)
+    torch.cuda.synchronize()
+    assert float((l1 - l2).abs().max()) <= 1e-4 and float((v1 - v2).abs().max()) <= 1e-4
+
+
+def test_self_play_runs_on_the_hand_written_tower(tw):
+    from harmonies_alphazero_b200 import net as hnet
+    from harmonies_alphazero_b200 import selfplay as sp
+
+    torch.manual_seed(0)
+    model = hnet.AlphaZeroNet.from_config(hnet.DEFAULT_MODEL_CONFIG).eval()
+    hand = hnet.InferenceNet(model, device="cuda", tower="hand")
+    cfg = sp.SelfPlayConfig(n_slots=48, num_simulations=12, seed=3)
+    drv = sp.BatchedSelfPlay(hand, cfg)
+    assert drv.groups[0].tiles
+    traj = drv.play(60)
+    assert traj.stats["games"] == 60 and len(traj) > 60 * 40
+    v = traj.visits.to(torch.int64).sum(dim=1)
+    assert int(v.max()) == 11 and int(v.min()) >= 0          # sum N = sims - 1 (MCTS.py:355-381)
+    assert set(traj.z.unique().tolist()) <= {-1.0, 0.0, 1.0}
