@@ -232,7 +232,7 @@ def test_overflow_survives_reset(mods):
     t.reset(st, tr.search_keys_tensor(np.arange(n, dtype=np.uint64)))
     t.run_synthetic(50, 2.0)
     t.reset(st, tr.search_keys_tensor(np.arange(n, dtype=np.uint64)))
-    t.run_synthetic(2, 2.0)                      # a tiny search that fits
+    t.run_synthetic(1, 2.0)                      # a tiny search that fits (the root expansion: <= 5 children)
     status = t.stats()[2].cpu().numpy()
     assert (status & 0x0F == 0).all() and (status & 0xF0 != 0).any()
     with pytest.raises(RuntimeError):
