@@ -44,7 +44,27 @@ def parse():
     ap.add_argument("--mcts-leaves", type=int, default=1, help="simulations in flight per tree and step (1 = reference-exact; >1 = virtual loss)")
     ap.add_argument("--mcts-steps", type=int, default=5, help="timed moves (each = games x sims simulations)")
     ap.add_argument("--mcts-no-graph", action="store_true", help="launch the simulation steps eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--mcts-tower", default="hand", choices=["hand", "cudnn"], help="residual tower: the hand-written sm_100a kernel or cuDNN (A/B)")
+    ap.add_argument("--mcts-play-games", type=int, default=8192, help="whole self-play games per GPU for the configs[3] measurement (0 = skip)")
+    ap.add_argument("--no-python-reference", action="store_true", help="skip timing the staged Python reference (baseline/_ref)")
     return ap.parse_args()
+
+
+def kernel_counters(name, files):
+    """ncu-derived per-launch counters (profiles/regen.sh), accepted only if the kernel's sources still
+    hash to what was profiled."""
+    import hashlib
+
+    p = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(p):
+        return None, f"{name} missing (run profiles/regen.sh on a B200)"
+    d = json.load(open(p))
+    h = hashlib.sha256()
+    for f in sorted(os.path.join(ROOT, "harmonies_alphazero_b200", "csrc", x) for x in files):
+        h.update(open(f, "rb").read())
+    if h.hexdigest() != d.get("source_sha256"):
+        return None, f"{name} is stale: the kernel sources changed since it was captured (run profiles/regen.sh)"
+    return d, None
 
 
 def peaks():
@@ -139,6 +159,36 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def headline_roofline(n_games, steps_per_launch, launch_s, clocks, pk, pk_src):
+    """hz::k_playout keeps a game's state in registers for all of its ~62 steps, so DRAM sees one 128-byte
+    record per GAME and the kernel is bound by instruction issue, not HBM.  The roofline is therefore the
+    issue roofline (warp instructions per second against SMs x 4 schedulers x clock), from the warp-instruction
+    count ncu measured for exactly these sources (profiles/regen.sh) and the launch time measured live here.
+    The contract's HBM figure (258 algorithmic bytes per step) is kept beside it as `hbm_algorithmic`."""
+    algo = ALGO_BYTES_PER_STEP * steps_per_launch / launch_s / 1e9
+    hbm = {"achieved": algo, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": algo / pk["hbm_gbs"], "peak_source": pk_src + " (burst copy)",
+           "note": "258 B/step x steps per launch / launch time (SURVEY.md 8d): what an unfused legal+apply loop would move; "
+                   "above 1 because the fused kernel does not move it (see traffic), NOT because work is skipped — every final "
+                   "record equals the CPU oracle's bit for bit (tests/test_gpu_engine.py)"}
+    c, why = kernel_counters("r02_playout_counters.json", ["hz_engine.cu", "hz_core.cuh", "hz_tables.inc"])
+    if c is None or n_games != 65536:
+        return {"bound": "issue", "achieved": None, "peak": None, "unit": "Gwarp-inst/s", "frac": None, "traffic": None,
+                "kernel": "hz::k_playout", "note": why or "counters were captured at 65,536 games per launch", "hbm_algorithmic": hbm}
+    m = {k: v["value"] for k, v in c["metrics"].items()}
+    winst = m["smsp__inst_executed.sum"]
+    sm_mhz = (clocks or {}).get("sm_mhz") or pk.get("sm_max_mhz") or 1965.0
+    peak = 148 * 4 * sm_mhz * 1e6 / 1e9
+    ach = winst / launch_s / 1e9
+    return {"bound": "issue", "achieved": ach, "peak": peak, "unit": "Gwarp-inst/s", "frac": ach / peak,
+            "traffic": m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"],
+            "kernel": "hz::k_playout", "peak_source": f"148 SMs x 4 schedulers x {sm_mhz:.0f} MHz (SM clock sampled during the timed region)",
+            "warp_inst_per_launch": winst, "active_lanes_per_warp_inst": m["smsp__thread_inst_executed.sum"] / winst,
+            "ncu": {"duration_us": m.get("gpu__time_duration.sum", 0) / 1e3, "issue_active_pct": m.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                    "warps_active_pct": m.get("sm__warps_active.avg.pct_of_peak_sustained_active"), "source": "profiles/r02_playout_counters.json"},
+            "note": "achieved = warp instructions per launch (ncu, same sources by sha256) / CUDA-event launch time measured in this run",
+            "hbm_algorithmic": hbm}
+
+
 # --------------------------------------------------------------------------------------
 def cpu_port_run(n_games, seed, threads):
     """the oracle (C port of the reference's engine) playing n_games random playouts"""
@@ -162,6 +212,21 @@ def cpu_baseline(budget_s=12.0):
                       f"(~8.3k steps/s/core, BASELINE.md §2)"}
 
 
+def python_reference(args):
+    """The unmodified Python reference (baseline/_ref, staged by baseline/stage_ref.py) on this box's host
+    cores: SURVEY.md §8(d) "CPU baseline timing"."""
+    try:
+        from baseline import ref_timing as rt
+
+        if not rt.available():
+            from baseline import stage_ref
+
+            stage_ref.stage()              # works where /root/reference exists (the dev container)
+        return rt.measure(engine_budget_s=4.0, moves=2, sims=args.mcts_sims)
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port; the Python reference cannot
     travel to the GPU box) on all host threads, same metric/config, bounded sample per step."""
@@ -183,19 +248,29 @@ def run_reference(args):
         t_total += dt
     v = steps_total / t_total
     sample = f"{n_games} random-playout games per step on {threads} pthreads (oracle/hz_oracle.c, C port of harmonies_engine.py)"
+    # the sims/s half of the metric: the C port's tree-only rate and the Python reference's own self-play layout
+    mcts_ref = {"port": cpu_mcts_baseline(budget_s=6.0)}
+    pyref = None if args.no_python_reference else python_reference(args)
+    if pyref is not None:
+        mcts_ref["python_reference"] = pyref
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": "random playouts, 65,536 concurrent 2-player games per GPU, engine only (configs[1])",
                    "games_per_step": n_games},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "python_reference": (pyref or {}).get("engine")},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mcts": {"metric": "mcts_sims_per_sec", "unit": "sims/s",
+                 "value": ((pyref or {}).get("mcts_loggers_on") or {}).get("value") or mcts_ref["port"]["with_network_estimate"]["value"],
+                 "kind": "reference" if (pyref or {}).get("mcts_loggers_on") else "port estimate",
+                 "detail": mcts_ref},
     }))
 
 
 # --------------------------------------------------------------------------------------
-def mcts_measure(args, dev, world, rank, dist, with_collectives=True):
+def mcts_measure(args, dev, world, rank, dist, with_collectives=True, tower=None, play_games=0):
     """configs[3]: MCTS self-play with the model.py net (random-init, bf16), 100 sims/move,
     4,096 concurrent games per GPU.  One step = one move of every game = 4,096 x 100
     simulations (select -> network forward -> expand+backup, CUDA-graph replayed)."""
@@ -208,7 +283,7 @@ def mcts_measure(args, dev, world, rank, dist, with_collectives=True):
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(0)
     model = hznet.AlphaZeroNet.from_config(hznet.DEFAULT_MODEL_CONFIG).eval()
-    inf = hznet.InferenceNet(model, device=dev, dtype=torch.bfloat16)
+    inf = hznet.InferenceNet(model, device=dev, dtype=torch.bfloat16, tower=tower or args.mcts_tower)
     B, S = args.mcts_games, args.mcts_sims
     cfg = sp.SelfPlayConfig(n_slots=B, num_simulations=S, cpuct=2.0, dirichlet_alpha=0.4, dirichlet_epsilon=0.25,
                             turns_until_tau0=15, seed=77, first_game_id=rank * B, n_streams=args.mcts_streams, leaves_per_step=args.mcts_leaves,
@@ -274,21 +349,67 @@ def mcts_measure(args, dev, world, rank, dist, with_collectives=True):
                        "trajectory_gather_ms": float(tms[1]), "examples_per_rank": n_ex,
                        "bytes_per_example": g.stats.get("bytes_per_example"), "backend": "nccl"}
     sims = B * S * K * world
-    v = sims / (ms * 1e-3)
+    v_step = sims / (ms * 1e-3)
     pk, pk_src = peaks()
     flops = hznet.flops_per_position()
+    hand = inf.hand is not None
+    own_per_sim = (2 + (4 if hand else (inf.heads is not None))) if drv.graph is not None else 0   # select, expand (+ tower, head convs, heads / heads)
+    peak_step = {"value": v_step, "unit": "sims/s", "ms_per_move": ms / K, "moves": K,
+                 "what": f"{K} moves of all {B} games from ply 8 (every slot live): the step rate of the search itself"}
+    whole = None
+    if play_games > 0:
+        # configs[3] as specified: whole self-play games (trainer.py:468-509), finished games replaced in place
+        pcfg = sp.SelfPlayConfig(n_slots=B, num_simulations=S, cpuct=2.0, dirichlet_alpha=0.4, dirichlet_epsilon=0.25,
+                                 turns_until_tau0=15, seed=78, first_game_id=rank * play_games, n_streams=args.mcts_streams,
+                                 leaves_per_step=args.mcts_leaves, use_cuda_graph=not args.mcts_no_graph)
+        drv.cfg = pcfg
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l1 = hb.launch_count()
+        sampler2 = ClockSampler(dev.index if dev.index is not None else 0)
+        sampler2.start()
+        traj = drv.play(play_games)
+        torch.cuda.synchronize()
+        play_clocks = sampler2.stop()
+        st = traj.stats
+        tt = torch.tensor([st["seconds"]], dtype=torch.float64, device=dev)
+        cnt = torch.tensor([st["sims"], st["games"], len(traj), st["move_steps"]], dtype=torch.int64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        secs = float(tt.item())
+        live_sims, games, examples, move_steps = (int(x) for x in cnt.tolist())
+        whole = {"value": live_sims / secs, "unit": "sims/s", "games_per_s": games / secs, "examples_per_s": examples / secs,
+                 "games": games, "seconds": secs, "move_steps_per_gpu": move_steps // world,
+                 "slot_utilisation": live_sims / (S * B * max(1, move_steps)),
+                 "vs_peak_step": (live_sims / secs) / v_step, "clocks": play_clocks,
+                 "launches_direct": (hb.launch_count() - l1) * world,
+                 "what": f"BatchedSelfPlay.play: {play_games} complete games per GPU on {B} slots (refill in place), live simulations only; "
+                         "includes refill, trajectory bookkeeping, move sampling and the game tail"}
+        direct_launches += hb.launch_count() - l1
+    v = whole["value"] if whole else v_step
     ach = (v / world) * flops / 1e12
-    return {"metric": "mcts_sims_per_sec", "value": v, "unit": "sims/s", "ms_per_move": ms / K,
-            "config": {"workload": "MCTS self-play, model.py net 128f x 8 blocks random-init, bf16, "
-                                   f"{S} sims/move, {B} concurrent games per GPU (configs[3])",
-                       "fused_conv": inf.fused, "fused_heads": inf.heads is not None, "cuda_graph": drv.graph is not None, "streams": drv.n_groups, "leaves_per_step": args.mcts_leaves},
-            "dtype": "bf16", "collectives": collectives, "clocks": mcts_clocks,
-            # direct C-ABI launches + the two tree kernels replayed inside the CUDA graph per simulation
-            "gpu_launches_own": (direct_launches + ((2 + (inf.heads is not None)) * drv.n_groups * S * K if drv.graph is not None else 0)) * world,
-            "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
-                         "peak_source": pk_src + " (sustained cuBLAS bf16)",
-                         "note": f"{flops / 1e6:.2f} MFLOP per simulation (network forward) x sims/s per GPU"}}
+    n_steps_graph = S * K + (S * (whole["move_steps_per_gpu"] if whole else 0))
+    out = {"metric": "mcts_sims_per_sec", "value": v, "unit": "sims/s", "ms_per_move": ms / K,
+           "config": {"workload": "MCTS self-play, model.py net 128f x 8 blocks random-init, bf16, "
+                                  f"{S} sims/move, {B} concurrent games per GPU (configs[3])"
+                                  + (f", {play_games} whole games per GPU" if whole else ", fixed positions"),
+                      "tower": "hand-written sm_100a tcgen05 (csrc/hz_tower.cu)" if hand else "cuDNN",
+                      "fused_conv": inf.fused, "fused_heads": inf.heads is not None, "cuda_graph": drv.graph is not None, "streams": drv.n_groups, "leaves_per_step": args.mcts_leaves},
+           "dtype": "bf16", "collectives": collectives, "clocks": mcts_clocks, "peak_step": peak_step,
+           # direct C-ABI launches + this library's kernels replayed inside the CUDA graph per simulation step
+           "gpu_launches_own": (direct_launches + own_per_sim * drv.n_groups * n_steps_graph) * world,
+           "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
+                        "peak_source": pk_src + " (sustained cuBLAS bf16)",
+                        "peak_step_frac": (v_step / world) * flops / 1e12 / pk["bf16_tflops_sustained"],
+                        "note": f"{flops / 1e6:.2f} MFLOP per simulation (the network forward as the reference defines it, zero padding "
+                                "included) x sims/s per GPU" + ("; the hand-written tower executes 247/315 of the convolution MACs (taps that "
+                                "fall off the 5x7 board are skipped)" if hand else "")}}
+    if whole:
+        out["whole_games"] = whole
+    return out
 
 
 def cpu_mcts_baseline(budget_s=10.0):
@@ -538,21 +659,7 @@ def run_b200(args):
                              "api": "HostPlayout.run_many: K batches of 128-byte records in and out, pipelined over 3 device buffers (PCIe-bound)"},
         "gpu_launches": launches_all,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / pk["hbm_gbs"],
-                     # dram__bytes_read.sum + dram__bytes_write.sum per launch at 65,536 games, ncu --set full
-                     # (profiles/r01_playout_ncu.txt): the initial records only; results stay in L2
-                     "traffic": 8424448 if n == 65536 else None, "peak_source": pk_src + " (burst copy)",
-                     "kernel": "hz::k_playout", "note": "algorithmic 258 B/step x steps per launch / CUDA-event launch time "
-                     "(SURVEY.md 8d). frac > 1 is expected here and does NOT mean skipped work: the fused kernel keeps each "
-                     "game's state in registers for its ~62 steps, so DRAM sees 128 B per GAME (traffic) instead of 258 B per "
-                     "STEP; every final record is bit-identical to the CPU oracle's (tests/test_gpu_engine.py). The kernel is "
-                     "bound by integer-ALU issue: see issue_slots below (SURVEY.md H7) and 'unfused' for the per-step path.",
-                     # ncu --set full of this kernel at 65,536 games (profiles/r01_playout_ncu.txt)
-                     "issue_slots": {"issue_active_pct": 57.7, "alu_pipe_pct": 51.2, "ipc_active": 2.11,
-                                     "active_threads_per_warp": 26.4, "achieved_occupancy_pct": 18.4,
-                                     "latency_floor_us": 62.4, "source": "ncu r01d (profiles/r01_playout_ncu.txt); latency_floor = "
-                                     "duration of a quarter-size wave: one game is a chain of ~70 dependent steps"}},
+        "roofline": headline_roofline(n, steps_done / K, avg_launch_s, clocks, pk, pk_src),
         "wall_s": wall,
         "unfused": {"value": unfused_steps / (unfused_ms * 1e-3), "unit": UNIT, "launches": 76 * 3, "ms": unfused_ms,
                     "achieved_GBps": unfused_steps * ALGO_BYTES_PER_STEP / (unfused_ms * 1e-3) / 1e9,
@@ -560,7 +667,11 @@ def run_b200(args):
     }
     if not args.no_mcts:
         # second half of BASELINE.json's metric: MCTS sims/s (configs[3]), reported alongside
-        out["mcts"] = mcts_measure(args, dev, world, rank, dist if world > 1 else None)
+        out["mcts"] = mcts_measure(args, dev, world, rank, dist if world > 1 else None, play_games=args.mcts_play_games)
+        if args.mcts_tower == "hand":
+            # A/B on the same box in the same run: the identical search with the cuDNN tower
+            ab = mcts_measure(args, dev, world, rank, dist if world > 1 else None, with_collectives=False, tower="cudnn")
+            out["mcts"]["cudnn_tower_peak_step"] = {"value": ab["peak_step"]["value"], "unit": "sims/s", "ms_per_move": ab["ms_per_move"]}
         if args.mcts_leaves == 1:
             # the same leg with 4 simulations in flight per tree (virtual loss, north_star's tree mode;
             # not visit-for-visit identical to the reference's sequential search, hence reported aside)
@@ -569,12 +680,18 @@ def run_b200(args):
             vl_args = copy.copy(args)
             vl_args.mcts_leaves = 4
             vl = mcts_measure(vl_args, dev, world, rank, dist if world > 1 else None, with_collectives=False)
-            out["mcts"]["virtual_loss"] = {"leaves_per_step": 4, "value": vl["value"], "unit": vl["unit"],
-                                           "ms_per_move": vl["ms_per_move"], "roofline_frac": vl["roofline"]["frac"]}
+            out["mcts"]["virtual_loss"] = {"leaves_per_step": 4, "value": vl["peak_step"]["value"], "unit": vl["unit"],
+                                           "ms_per_move": vl["ms_per_move"], "roofline_frac": vl["roofline"]["peak_step_frac"],
+                                           "what": "peak step rate with 4 simulations in flight per tree"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
+        pyref = None if args.no_python_reference else python_reference(args)
+        if pyref is not None:
+            out["cpu_baseline"]["python_reference"] = pyref.get("engine", pyref)
         if "mcts" in out:
             out["mcts"]["cpu_baseline"] = cpu_mcts_baseline()
+            if pyref is not None:
+                out["mcts"]["cpu_baseline"]["python_reference"] = {k: v for k, v in pyref.items() if k != "engine"}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
