@@ -19,6 +19,9 @@ SIGNATURES = {
     "hz_init_states": (_i, [_vp, _i64, _vp, _u64, _u64, _vp]),
     "hz_legal_mask": (_i, [_vp, _i64, _vp, _vp]),
     "hz_apply": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "hz_end_turn": (_i, [_vp, _i64, _vp, _vp, _vp]),
+    "hz_replenish_piles": (_i, [_vp, _i64, _vp]),
+    "hz_draw_tiles": (_i, [_vp, _i64, _i, _vp, _vp]),
     "hz_score": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "hz_encode": (_i, [_vp, _i64, _vp, _vp, _i, _i, _vp]),
     "hz_canon_hash": (_i, [_vp, _i64, _i, _vp, _vp]),

@@ -42,6 +42,29 @@ def apply(words, action, draw=None):
     return hb.states_to_numpy(st)[0], int(status[0])
 
 
+def end_turn(words):
+    st = _to_dev(words)
+    hb.end_turn(st)
+    return hb.states_to_numpy(st)[0]
+
+
+def replenish(words):
+    st = _to_dev(words)
+    hb.replenish_piles(st)
+    return hb.states_to_numpy(st)[0]
+
+
+def draw_tiles(words, count):
+    st = _to_dev(words)
+    t = hb.draw_tiles(st, count).cpu().numpy()[0]
+    return hb.states_to_numpy(st)[0], [int(x) for x in t[: int(t[15])]]
+
+
+def score_terms(words):
+    """int[2][5]: grass, mountains, fields, buildings, water per player"""
+    return hb.score(_to_dev(words), with_terms=True)[1].cpu().numpy()[0]
+
+
 def scores(words):
     return hb.score(_to_dev(words)).cpu().numpy()[0]
 

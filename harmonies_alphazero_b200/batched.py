@@ -82,6 +82,35 @@ def apply(states, actions, draws=None, status=None):
     return status
 
 
+def end_turn(states, draws=None, status=None):
+    """In-place _end_turn_actions (harmonies_engine.py:301-329) for the player to move of every state."""
+    lib = _lib.load()
+    n = _check_states(states)
+    status = torch.empty(n, dtype=torch.uint8, device=states.device) if status is None else status
+    with torch.cuda.device(states.device):
+        _lib.check(lib.hz_end_turn(_ptr(states), n, _ptr(draws), _ptr(status), _stream(states)), "hz_end_turn")
+    return status
+
+
+def replenish_piles(states):
+    """In-place _replenish_piles (harmonies_engine.py:132-137)."""
+    lib = _lib.load()
+    n = _check_states(states)
+    with torch.cuda.device(states.device):
+        _lib.check(lib.hz_replenish_piles(_ptr(states), n, _stream(states)), "hz_replenish_piles")
+
+
+def draw_tiles(states, count):
+    """In-place _draw_tiles(count) (harmonies_engine.py:120-130), count <= 15.  Returns uint8[n,16]:
+    tile types in draw order, [:,15] = number drawn."""
+    lib = _lib.load()
+    n = _check_states(states)
+    out = torch.zeros((n, 16), dtype=torch.uint8, device=states.device)
+    with torch.cuda.device(states.device):
+        _lib.check(lib.hz_draw_tiles(_ptr(states), n, int(count), _ptr(out), _stream(states)), "hz_draw_tiles")
+    return out
+
+
 def score(states, with_terms=False):
     """int16[n, 2] scores (calculate_score_for_player, harmonies_engine.py:357-523);
     with_terms also returns int16[n, 2, 5] (grass, mountains, fields, buildings, water)."""

@@ -477,6 +477,57 @@ __device__ __forceinline__ void partial_scores(const State& s, const NbrLut* lut
     score_board(lut, board_of(s, 1), t, q, (int)threadIdx.x * 2 + 1);
     s1 = t[0] + t[1] + t[2] + t[3] + t[4];
 }
+// ---- _replenish_piles (:132-137) + _end_turn_actions (:301-329) -------------------------------------
+// Tops the piles up to five from the bag (first pile = explicit_code when use_explicit: trace replay),
+// draw k of event `devent` of stream `dkey` being rand(dkey, devent*8 + k).  Returns whether the bag
+// was empty BEFORE replenishing (:307).
+__device__ __forceinline__ bool replenish_piles(State& s, uint32_t hand, bool use_explicit, uint32_t explicit_code, uint64_t dkey,
+                                                uint32_t devent, const uint64_t* rtab, int& np_out) {
+    int np = n_piles_of(s);
+    uint64_t bag = bag_of(s);
+    bool bag_empty_before = bag_total(bag) == 0;                      // :307
+    Piles P = piles_of(s);
+    for (int k = 0; np < 5; k++) {                                    // _replenish_piles :132-137
+        uint32_t pc;
+        if (k == 0 && use_explicit) { pc = explicit_code; bag = bag_minus(bag, pc); }
+        else pc = draw_pile(bag, rand64_t(rtab, dkey, (uint64_t)devent * 8 + (uint64_t)k));
+        if (pc == 0) break;                                           // :135-136
+#pragma unroll
+        for (int j = 0; j < 5; j++) P.p[j] = (j == np) ? pc : P.p[j];
+        np++;
+    }
+    set_bag(s, bag);
+    set_piles(s, P, hand, np);   // the reference does not clear a (non-standard) leftover hand at end of turn
+    np_out = np;
+    return bag_empty_before;
+}
+// `pl` has just finished a turn; occ_after = occupancy mask of pl's board.  (The reference's
+// _end_turn_actions, also called directly by its GUI: GUI/main.py:364-365.)
+template <bool DEFER_SCORE = false, bool REL = false>
+__device__ __forceinline__ int end_turn(State& s, int pl, uint32_t occ_after, uint32_t hand, bool use_explicit, uint32_t explicit_code,
+                                        uint64_t dkey, uint32_t devent, bool bump_event, const NbrLut* lut, const uint64_t* rtab) {
+    bool player_trigger = (23 - __popc(occ_after)) <= 2;              // :304-305
+    int np;
+    bool bag_empty_before = replenish_piles(s, hand, use_explicit, explicit_code, dkey, devent, rtab, np);
+    if (bump_event) s.w[HZ_W_EVENT]++;
+    bool triggered = player_trigger || (bag_empty_before && np == 0);  // :309-311
+    bool ending = ending_of(s);
+    uint32_t m = meta(s) & 1u;                                        // keep player
+    if (triggered && !ending && pl == 0) {                            // :314-318
+        m = 1u | (HZ_PHASE_CHOOSE << 1) | (1u << 4);
+        if (REL) swap_boards(s);
+    } else if ((triggered && !ending) || ending) {                    // :319-326
+        set_meta(s, m | (HZ_PHASE_OVER << 1) | (1u << 4));            // :320,324 (winner still None)
+        if (!DEFER_SCORE) finalize_scores(s, lut);                    // :321-322,325-326
+        return HZ_MOVE_OK;
+    } else {                                                          // :327-329
+        m = (m ^ 1u) | (HZ_PHASE_CHOOSE << 1);
+        if (REL) swap_boards(s);
+    }
+    set_meta(s, m);
+    return HZ_MOVE_OK;
+}
+
 template <bool DEFER_SCORE = false, bool REL = false>
 __device__ __forceinline__ int apply_move(State& s, int a, uint32_t explicit_code, uint64_t dkey,
                                           uint32_t devent, bool bump_event, const NbrLut* lut,
@@ -536,37 +587,7 @@ __device__ __forceinline__ int apply_move(State& s, int a, uint32_t explicit_cod
     }
 
     // ---- _end_turn_actions (:301-329)
-    bool player_trigger = (23 - __popc(t.occ0 | bit)) <= 2;           // :304-305
-    bool bag_empty_before = bag_total(bag) == 0;                      // :307
-    Piles P = piles_of(s);
-    for (int k = 0; np < 5; k++) {                                    // _replenish_piles :132-137
-        uint32_t pc;
-        if (k == 0 && use_explicit) { pc = explicit_code; bag = bag_minus(bag, pc); }
-        else pc = draw_pile(bag, rand64_t(rtab, dkey, (uint64_t)devent * 8 + (uint64_t)k));
-        if (pc == 0) break;                                           // :135-136
-#pragma unroll
-        for (int j = 0; j < 5; j++) P.p[j] = (j == np) ? pc : P.p[j];
-        np++;
-    }
-    set_bag(s, bag);
-    set_piles(s, P, hand, np);   // the reference does not clear a (non-standard) leftover hand at end of turn
-    if (bump_event) s.w[HZ_W_EVENT]++;
-    bool triggered = player_trigger || (bag_empty_before && np == 0);  // :309-311
-    bool ending = ending_of(s);
-    uint32_t m = meta(s) & 1u;                                        // keep player
-    if (triggered && !ending && pl == 0) {                            // :314-318
-        m = 1u | (HZ_PHASE_CHOOSE << 1) | (1u << 4);
-        if (REL) swap_boards(s);
-    } else if ((triggered && !ending) || ending) {                    // :319-326
-        set_meta(s, m | (HZ_PHASE_OVER << 1) | (1u << 4));            // :320,324 (winner still None)
-        if (!DEFER_SCORE) finalize_scores(s, lut);                    // :321-322,325-326
-        return HZ_MOVE_OK;
-    } else {                                                          // :327-329
-        m = (m ^ 1u) | (HZ_PHASE_CHOOSE << 1);
-        if (REL) swap_boards(s);
-    }
-    set_meta(s, m);
-    return HZ_MOVE_OK;
+    return end_turn<DEFER_SCORE, REL>(s, pl, t.occ0 | bit, hand, use_explicit, explicit_code, dkey, devent, bump_event, lut, rtab);
 }
 
 // ---- canonical keys ----------------------------------------------------------------------------

@@ -49,6 +49,72 @@ __global__ void __launch_bounds__(TPB) k_apply(void* states, int64_t n, const in
     if (status) status[g] = (uint8_t)st;
 }
 
+// ---- the reference's private turn helpers, for callers that drive them directly (GUI/main.py:364-365,
+// harness code): _end_turn_actions (:301-329), _replenish_piles (:132-137), _draw_tiles (:120-130)
+__global__ void __launch_bounds__(TPB) k_end_turn(void* states, int64_t n, const uint16_t* draws, uint8_t* status) {
+    __shared__ NbrLut lut;
+    int64_t g = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    State s;
+    if (g < n) load_state(s, states, g);
+    build_nbr_lut(&lut);
+    __syncthreads();
+    if (g >= n) return;
+    uint32_t ex = draws ? (uint32_t)draws[g] : (uint32_t)HZ_NO_DRAW;
+    bool use_explicit = ex != HZ_NO_DRAW && n_piles_of(s) < 5;
+    int st = HZ_MOVE_OK;
+    if (use_explicit && !pile_available(bag_of(s), ex)) st = HZ_MOVE_BAD_DRAW;
+    else {
+        int pl = player_of(s);
+        Tops t = tops_of(board_of(s, pl));
+        st = end_turn<false, false>(s, pl, t.occ0, hand_of(s), use_explicit, ex, key_of(s), s.w[HZ_W_EVENT], true, &lut, nullptr);
+        store_state(s, states, g);
+    }
+    if (status) status[g] = (uint8_t)st;
+}
+
+__global__ void __launch_bounds__(TPB) k_replenish(void* states, int64_t n) {
+    int64_t g = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (g >= n) return;
+    State s;
+    load_state(s, states, g);
+    int np;
+    replenish_piles(s, hand_of(s), false, 0u, key_of(s), s.w[HZ_W_EVENT], nullptr, np);
+    s.w[HZ_W_EVENT]++;
+    store_state(s, states, g);
+}
+
+// draws min(count, bag total) tiles one by one, uniformly without replacement from the bag multiset
+// (random.sample over the flattened bag, :122-129), with the arithmetic of draw_pile; tiles[g][0..14] =
+// tile types in draw order, tiles[g][15] = how many were drawn.  One draw event of the state's stream.
+__global__ void __launch_bounds__(TPB) k_draw_tiles(void* states, int64_t n, int count, uint8_t* tiles) {
+    int64_t g = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (g >= n) return;
+    State s;
+    load_state(s, states, g);
+    uint64_t bag = bag_of(s), key = key_of(s);
+    int total = bag_total(bag), drawn = 0;
+    for (int grp = 0; grp < 5 && drawn < count && total > 0; grp++) {
+        uint64_t z = rand64(key, (uint64_t)s.w[HZ_W_EVENT] * 8 + (uint64_t)grp);
+        for (int j = 0; j < 3 && drawn < count && total > 0; j++) {
+            uint32_t x = (uint32_t)(z >> (21 * j)) & 0x1FFFFFu;
+            uint32_t r = (x * (uint32_t)total) >> 21;
+            int t = 0;
+            uint32_t cum = 0;
+            for (; t < 5; t++) {
+                cum += (uint32_t)(bag >> (8 * t)) & 0xFFu;
+                if (cum > r) break;
+            }
+            bag -= 1ull << (8 * t);
+            total--;
+            tiles[g * 16 + drawn++] = (uint8_t)t;
+        }
+    }
+    tiles[g * 16 + 15] = (uint8_t)drawn;
+    set_bag(s, bag);
+    s.w[HZ_W_EVENT]++;
+    store_state(s, states, g);
+}
+
 __global__ void __launch_bounds__(TPB) k_score(const void* states, int64_t n, int16_t* scores,
                                                int16_t* terms) {
     __shared__ NbrLut lut;
@@ -537,6 +603,27 @@ int hz_apply(void* states, int64_t n, const int16_t* actions, const uint16_t* dr
     if (!states || !actions || n < 0) return HZ_ERR_ARG;
     if (n == 0) return HZ_OK;
     k_apply<<<blocks_for(n, TPB), TPB, 0, (cudaStream_t)stream>>>(states, n, actions, draws, status);
+    return hz_launched(1);
+}
+
+int hz_end_turn(void* states, int64_t n, const uint16_t* draws, uint8_t* status, void* stream) {
+    if (n == 0) return HZ_OK;
+    if (!states || n < 0) return HZ_ERR_ARG;
+    k_end_turn<<<blocks_for(n, TPB), TPB, 0, (cudaStream_t)stream>>>(states, n, draws, status);
+    return hz_launched(1);
+}
+
+int hz_replenish_piles(void* states, int64_t n, void* stream) {
+    if (n == 0) return HZ_OK;
+    if (!states || n < 0) return HZ_ERR_ARG;
+    k_replenish<<<blocks_for(n, TPB), TPB, 0, (cudaStream_t)stream>>>(states, n);
+    return hz_launched(1);
+}
+
+int hz_draw_tiles(void* states, int64_t n, int count, uint8_t* tiles, void* stream) {
+    if (n == 0) return HZ_OK;
+    if (!states || !tiles || n < 0 || count < 0 || count > 15) return HZ_ERR_ARG;
+    k_draw_tiles<<<blocks_for(n, TPB), TPB, 0, (cudaStream_t)stream>>>(states, n, count, tiles);
     return hz_launched(1);
 }
 

@@ -147,6 +147,62 @@ class HarmoniesGameState:
         new._load(words)
         return new
 
+    # ---- the reference's private helpers (its GUI, harnesses and tests call them directly) -----
+    def _adopt(self, words):
+        """Mutate THIS object into the state the kernel produced (the reference's private helpers
+        work in place)."""
+        self._load(words)
+
+    def _draw_tiles(self, num_tiles):
+        """harmonies_engine.py:120-130: draws from (and decrements) the bag; returns tile names."""
+        words, tiles = _dev().draw_tiles(self._pack(), int(num_tiles))
+        f = pk.unpack_fields(words)
+        self.tile_bag = f["tile_bag"]
+        self._rng_event = f["rng_event"]
+        return [TILE_TYPES[t] for t in tiles]
+
+    def _replenish_piles(self):
+        """harmonies_engine.py:132-137."""
+        f = pk.unpack_fields(_dev().replenish(self._pack()))
+        self.tile_bag, self.available_piles, self._rng_event = f["tile_bag"], f["available_piles"], f["rng_event"]
+
+    def _get_top_tile(self, board, coord):
+        return board.get(coord, [None])[-1]                        # harmonies_engine.py:142-143
+
+    def _end_turn_actions(self):
+        """harmonies_engine.py:301-329, in place: replenish, end-of-game triggers, turn switch or
+        final scoring for the player who has just finished a turn."""
+        self._adopt(_dev().end_turn(self._pack()))
+
+    def _calculate_final_scores(self):                             # harmonies_engine.py:344-346
+        self.final_scores[0] = self.calculate_score_for_player(0)
+        self.final_scores[1] = self.calculate_score_for_player(1)
+
+    def _determine_winner(self):                                   # harmonies_engine.py:348-354
+        a, b = self.final_scores
+        self.winner = 0 if a > b else 1 if b > a else -1
+
+    def _score_term(self, board, term):
+        """One scoring term of ``board`` (any dict coord -> stack) on the GPU: the board is packed as
+        player 0 of a scratch state."""
+        words = pk.pack_fields([board, {}], {t: 0 for t in TILE_TYPES}, [], 0, [], "choose_pile", False, None, [0, 0])
+        return int(_dev().score_terms(words)[0][term])
+
+    def _score_grass(self, board, player):                         # harmonies_engine.py:369-385
+        return self._score_term(board, 0)
+
+    def _score_mountains(self, board, player):                     # :392-413
+        return self._score_term(board, 1)
+
+    def _score_fields(self, board, player):                        # :424-443
+        return self._score_term(board, 2)
+
+    def _score_buildings(self, board, player):                     # :454-469
+        return self._score_term(board, 3)
+
+    def _score_water(self, board, player):                         # :480-523
+        return self._score_term(board, 4)
+
     def is_game_over(self):
         return self.game_over and self.winner is not None          # harmonies_engine.py:332-333
 

@@ -89,15 +89,20 @@ def _fold(conv, bn):
 class InferenceNet:
     """Folded, channels-last inference copy of an AlphaZeroNet on one device."""
 
-    def __init__(self, model, device="cuda", dtype=torch.bfloat16, fused=True, fused_heads=True, tower="cudnn"):
-        """tower: "cudnn" (library convolutions) or "hand" (csrc/hz_tower.cu, the hand-written
-        sm_100a tcgen05 tower; bf16 on CUDA with 128 filters only — it raises otherwise, there is
-        no silent fallback between the two)."""
+    def __init__(self, model, device="cuda", dtype=torch.bfloat16, fused=True, fused_heads=True, tower="auto"):
+        """tower: "hand" = csrc/hz_tower.cu, the hand-written sm_100a tcgen05 tower (bf16 on CUDA
+        with 128 filters and <= 64 input planes; it raises for anything else, there is no silent
+        fallback); "cudnn" = library convolutions (other shapes / dtypes, and the A/B switch);
+        "auto" (default) = "hand" exactly when the network has the shape it supports."""
         self.device, self.dtype = torch.device(device), dtype
         self.fused = fused and self.device.type == "cuda"
         self.use_fused_heads = fused_heads
+        if tower == "auto":
+            ok = (self.device.type == "cuda" and dtype == torch.bfloat16 and model.conv.out_channels == 128
+                  and model.conv.in_channels <= 64)
+            tower = "hand" if ok else "cudnn"
         if tower not in ("cudnn", "hand"):
-            raise ValueError("tower must be 'cudnn' or 'hand'")
+            raise ValueError("tower must be 'auto', 'cudnn' or 'hand'")
         if tower == "hand" and not (self.device.type == "cuda" and dtype == torch.bfloat16):
             raise ValueError("the hand-written tower is bf16 on CUDA only")
         self.tower = tower

@@ -181,6 +181,19 @@ int hz_score(const void *states, int64_t n, int16_t *scores, int16_t *terms, voi
 int hz_encode(const void *states, int64_t n, void *board, void *glob, int dtype, int layout,
               void *stream);
 
+/* The reference's private turn helpers, for callers that drive them directly (its GUI calls
+ * _end_turn_actions itself, GUI/main.py:364-365; harnesses patch _draw_tiles):
+ * hz_end_turn       = _end_turn_actions (harmonies_engine.py:301-329) for the player to move:
+ *                     replenish, end-of-game triggers, turn switch or final scoring; draws/status
+ *                     as for hz_apply (HZ_MOVE_OK or HZ_MOVE_BAD_DRAW).
+ * hz_replenish_piles = _replenish_piles (:132-137): top the piles up to five from the bag.
+ * hz_draw_tiles     = _draw_tiles(count) (:120-130), count <= 15: tiles [n,16] uint8 = tile types
+ *                     in draw order, byte 15 = number drawn; the bag is decremented.
+ * Each call consumes one draw event of the state's stream. */
+int hz_end_turn(void *states, int64_t n, const uint16_t *draws, uint8_t *status, void *stream);
+int hz_replenish_piles(void *states, int64_t n, void *stream);
+int hz_draw_tiles(void *states, int64_t n, int count, uint8_t *tiles, void *stream);
+
 /* 64-bit key of get_canonical_tuple / __hash__ (harmonies_engine.py:81-113). */
 int hz_canon_hash(const void *states, int64_t n, int key_mode, uint64_t *hashes, void *stream);
 

@@ -233,3 +233,105 @@ def test_trainer_hook_fills_replay_buffer(eng):
     et.self_play_config = dict(et.self_play_config, eval_win_rate_threshold=2.0)
     calls.clear()
     assert not trainer_hooks.evaluate_model(et, eval_config=cfg_eval)["promoted"] and calls == []
+
+
+# ---- the reference's private helpers (harmonies_engine.py:120-143,301-354,369-523) -------------
+def test_end_turn_actions_equals_the_tail_of_apply_move(eng):
+    """apply_move of a third placement = place the tile, then _end_turn_actions (harmonies_engine.py:
+    283-292,301-329): doing the placement on the attributes and calling the private helper must give
+    the state apply_move gives (same draw stream, same event) — through turn switches, the end
+    trigger, player 1's last turn and the final scoring."""
+    random.seed(11)
+    s = eng.HarmoniesGameState()
+    checked = ended = 0
+    while not s.is_game_over():
+        moves = s.get_legal_moves()
+        mv = moves[random.randrange(len(moves))]
+        nxt = s.apply_move(mv)
+        if s.turn_phase == "place_tile_3":
+            t = s.clone()
+            tile, coord = mv
+            t.player_boards[t.current_player].setdefault(coord, []).append(tile)
+            t.tiles_in_hand.remove(tile)
+            t._end_turn_actions()
+            assert t == nxt and (t.game_over, t.winner, t.final_scores) == (nxt.game_over, nxt.winner, nxt.final_scores)
+            assert t.turn_phase == nxt.turn_phase and t.current_player == nxt.current_player
+            checked += 1
+            ended += nxt.is_game_over()
+        s = nxt
+    assert checked >= 15 and ended == 1
+
+
+def test_draw_and_replenish_helpers(eng):
+    random.seed(5)
+    s = eng.HarmoniesGameState()
+    bag0 = dict(s.tile_bag)
+    tiles = s._draw_tiles(3)
+    assert len(tiles) == 3 and all(t in eng.TILE_TYPES for t in tiles)
+    for t in eng.TILE_TYPES:
+        assert s.tile_bag[t] == bag0[t] - tiles.count(t)
+    more = s._draw_tiles(7)
+    assert len(more) == 7 and sum(s.tile_bag.values()) == 105 - 10
+    s.available_piles = s.available_piles[:2]
+    before = sum(s.tile_bag.values())
+    s._replenish_piles()
+    assert len(s.available_piles) == 5 and all(len(p) == 3 for p in s.available_piles)
+    assert sum(s.tile_bag.values()) == before - 9
+    # an empty bag gives no tiles and no piles (harmonies_engine.py:123-124,135-136)
+    e = eng.HarmoniesGameState()
+    e.tile_bag = {t: 0 for t in eng.TILE_TYPES}
+    e.available_piles = []
+    assert e._draw_tiles(3) == []
+    e._replenish_piles()
+    assert e.available_piles == []
+    # a nearly empty bag gives a partial pile (:125)
+    e.tile_bag["stone"] = 2
+    assert e._draw_tiles(3) == ["stone", "stone"] and e.tile_bag["stone"] == 0
+    assert e._get_top_tile({(0, 0): ["wood", "plant"]}, (0, 0)) == "plant" and e._get_top_tile({}, (0, 0)) is None
+
+
+def test_score_term_helpers_match_the_reference(eng):
+    """_score_grass/_mountains/_fields/_buildings/_water on boards of the reference-generated golden
+    scoring set (per-term values recorded from harmonies_engine.py:369-523)."""
+    from tests.conftest import load_golden
+
+    g = load_golden("scoring")
+    s = eng.HarmoniesGameState()
+    for i in range(0, 6000, 401):
+        f = pk.unpack_fields(g["states"][i])
+        for p in (0, 1):
+            board = f["player_boards"][p]
+            got = [s._score_grass(board, p), s._score_mountains(board, p), s._score_fields(board, p),
+                   s._score_buildings(board, p), s._score_water(board, p)]
+            assert got == g["terms"][i, p].tolist()
+    t = eng.HarmoniesGameState({**pk.unpack_fields(g["states"][7]), "rng_key": 0})
+    t._calculate_final_scores()
+    t._determine_winner()
+    assert t.final_scores == g["totals"][7].tolist()
+    assert t.winner == (0 if t.final_scores[0] > t.final_scores[1] else 1 if t.final_scores[1] > t.final_scores[0] else -1)
+
+
+def test_search_entry_point_edge_cases_follow_the_reference(eng):
+    """MCTS.py:297 (terminal leaves are not sent to the network), :420-423 (greedy choice with an
+    unvisited root takes the first root edge), :386-392 (the uniform fallback is written into an int
+    array and truncates to zero)."""
+    from harmonies_alphazero_b200 import MCTS
+
+    cfg = {"num_simulations": 1, "cpuct": 2, "dirichlet_alpha": 0.4, "dirichlet_epsilon": 0.25,
+           "turns_until_tau0": 15, "action_size": 143, "testing": True}
+    random.seed(3)
+    s = eng.HarmoniesGameState()
+    mv, pi = MCTS.get_best_action_and_pi(s.clone(), _FakeManager(), cfg, 0)
+    assert mv == s.get_legal_moves()[0] and pi.sum() == 0 and pi.dtype.kind == "i"
+    # exploratory phase with an unvisited root: random legal move (MCTS.py:425-433)
+    mv, pi = MCTS.get_best_action_and_pi(s.clone(), _FakeManager(), dict(cfg, testing=False), 0)
+    assert mv in s.get_legal_moves() and pi.sum() == 0
+    # play to the last turn: searches from there reach terminal leaves, which must not be evaluated
+    while True:
+        nxt = s.apply_move(s.get_legal_moves()[0])
+        if nxt.is_game_over():
+            break
+        s = nxt
+    mgr = _FakeManager()
+    mv, pi = MCTS.get_best_action_and_pi(s.clone(), mgr, dict(cfg, num_simulations=12), 60)
+    assert mv is not None and 1 <= mgr.calls < 12
