@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -15 | tee gpurun_out/k_tests.log
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -15 | tee gpurun_out/k_tests.log

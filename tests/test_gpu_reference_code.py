@@ -43,5 +43,5 @@ def test_reference_unit_tests_pass_on_the_drop_in(staged):
 def test_reference_trainer_runs_through_the_hooks(staged):
     rc, out, log = _run("trainer", timeout=900)
     assert rc == 0, (out, log[-3000:])
-    assert out["examples_after_iteration"] >= 6 * 40            # six complete games, one example per action
-    assert out["buffer_len_after_second_phase"] >= out["examples_after_iteration"] or out["buffer_len_after_second_phase"] == 100
+    # six complete games give > 300 examples; the test configuration's deque keeps the last 100 (config.py:160)
+    assert out["examples_after_iteration"] == 100 and out["buffer_len_after_second_phase"] == 100
