@@ -515,6 +515,157 @@ def gen_net(n=16):
     print(f"net: {sum(v.numel() for v in ref.state_dict().values())} values in the state_dict, {n} positions")
 
 
+def _reference_model(mc):
+    import importlib
+
+    rh.load_reference()
+    if rh.REF_ROOT not in sys.path:
+        sys.path.insert(0, rh.REF_ROOT)
+    model_mod = importlib.import_module("model")
+    return model_mod.AlphaZeroModel(
+        input_channels=mc["input_channels"], cnn_filters=mc["cnn_filters"], board_size=mc["board_size"],
+        action_size=mc["action_size"], global_feature_size=mc["global_feature_size"],
+        value_hidden_dim=mc["value_head_hidden_dim"], num_res_blocks=mc["num_res_blocks"])
+
+
+def _positions(n, pgs):
+    boards, globs = [], []
+    for g in range(n):
+        st = rh.new_game_stream(2000 + g)
+        for _ in range(2 + 3 * g):
+            if st.is_game_over():
+                break
+            moves = sorted(st.get_legal_moves(), key=pgs.get_action_index)
+            st = st.apply_move(moves[(5 * g + 1) % len(moves)])
+        b, gl = pgs.create_state_tensors(st)
+        boards.append(b); globs.append(gl)
+    import torch
+
+    return torch.stack(boards), torch.stack(globs)
+
+
+def gen_net_default(n=24, seed=20260):
+    """a17 / f4 at the DEFAULT size (config.py:18-29: 128 filters x 8 blocks, the network every
+    throughput number uses): the reference's own AlphaZeroModel with weights from
+    oracle/synth_weights.fill_ (numpy PCG64, so the fixture needs no 10 MB state_dict), eval mode;
+    stored: the inputs (encoded by the reference from real positions), logits, value, softmax, and
+    the tower output (what the hand-written sm_100a tower must reproduce)."""
+    import importlib
+
+    import torch
+
+    try:
+        from oracle import synth_weights
+    except ImportError:          # run as a script: oracle/ itself is on sys.path
+        import synth_weights
+
+    rh.load_reference()
+    if rh.REF_ROOT not in sys.path:
+        sys.path.insert(0, rh.REF_ROOT)
+    cfgm, pgs = importlib.import_module("config"), importlib.import_module("process_game_state")
+    mc = dict(cfgm.model_config_default)
+    ref = synth_weights.fill_(_reference_model(mc), seed).eval()
+    B, G = _positions(n, pgs)
+    with torch.no_grad():
+        logits, value = ref(B, G)
+        x = torch.relu(ref.bn(ref.conv(B)))
+        for blk in ref.residual_blocks:
+            x = blk(x)
+    np.savez_compressed(os.path.join(OUT, "net_default.npz"), seed=np.int64(seed), board=B.numpy(), glob=G.numpy(), logits=logits.numpy(),
+                        value=value.numpy().reshape(-1), probs=torch.softmax(logits, dim=1).numpy(),
+                        tower_abs_max=np.float32(x.abs().max()), tower_sample=x[:4].numpy().astype(np.float16))
+    print(f"net_default: {sum(v.numel() for v in ref.state_dict().values())} synthetic values (seed {seed}), {n} positions, "
+          f"|logits| max {float(logits.abs().max()):.3f}")
+
+
+def gen_mcts_real_priors(n_searches=16, sims=100, seed=20261):
+    """a12-a16 with REAL priors: the reference's MCTS.py searching with the reference's default-size
+    AlphaZeroModel behind the reference's ModelManager.predict (fp32 softmax, unmasked, model.py:81-110).
+    Every (priors, value) the network returned is recorded in call order; the GPU tree is then fed the
+    same table and must reproduce N, W, P, pi and the chosen move."""
+    import importlib
+
+    import torch
+
+    try:
+        from oracle import synth_weights
+    except ImportError:          # run as a script: oracle/ itself is on sys.path
+        import synth_weights
+
+    ref = rh.load_reference()
+    if rh.REF_ROOT not in sys.path:
+        sys.path.insert(0, rh.REF_ROOT)
+    cfgm = importlib.import_module("config")
+    model_mod = importlib.import_module("model")
+    import contextlib
+    import io
+
+    torch.set_num_threads(1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        mm = model_mod.ModelManager(dict(cfgm.model_config_default), dict(cfgm.training_config_default, device="cpu"))
+    synth_weights.fill_(mm.model, seed)
+    mm.model.eval()
+
+    class Recording:
+        def __init__(self):
+            self.rows = []
+
+        def predict(self, b, g):
+            p, v = mm.predict(b, g)
+            self.rows.append((np.asarray(p, dtype=np.float32).copy(), np.float32(v)))
+            return p, v
+
+    gai = ref["pgs"].get_action_index
+    nrng = np.random.default_rng(seed)
+    out = {k: [] for k in "root skey testing eps noise choice_u move_no tau0 cpuct N W P pi action n_nodes n_edges n_eval".split()}
+    table_p, table_v = [], []
+    t0 = time.time()
+    for i in range(n_searches):
+        key = pk.rand(0x7EA1, i)
+        s = rh.new_game_stream(key)
+        moves = 0
+        for _ in range([0, 1, 3, 4, 9, 17, 26, 33, 41, 47, 52, 55, 57, 58, 59, 60][i % 16]):
+            if s.is_game_over():
+                break
+            lm = s.get_legal_moves()
+            s = s.apply_move(lm[playout_pick(key, moves, len(lm))])
+            moves += 1
+        while s.is_game_over():          # never a terminal root here
+            s = rh.new_game_stream(key + 1)
+            moves = 0
+        testing = i % 3 == 1
+        cfg = {"num_simulations": sims, "cpuct": 2, "dirichlet_alpha": 0.4, "dirichlet_epsilon": 0.0 if testing else 0.25,
+               "fpu_value": 0.25, "turns_until_tau0": 15, "action_size": 143, "testing": testing}
+        noise = nrng.gamma(0.4, size=143).astype(np.float32) + np.float32(1e-6)
+        u = float(np.float32(nrng.random()))
+        skey = pk.rand(key ^ 0x5EA7C4, moves)
+        rec = Recording()
+        ev = rh.ctx.event
+        mv, pi, info = rh.run_search(s, skey, cfg, moves, noise=None if testing else noise, choice_u=u, manager=rec)
+        P = np.zeros((sims, 143), dtype=np.float32)
+        V = np.zeros(sims, dtype=np.float32)
+        for j, (p, v) in enumerate(rec.rows):
+            P[j], V[j] = p, v
+        table_p.append(P); table_v.append(V)
+        for k, val in (("root", pk.pack_state(s, rng_key=key, rng_event=ev, moves=moves)), ("skey", skey), ("testing", int(testing)),
+                       ("eps", cfg["dirichlet_epsilon"]), ("noise", noise), ("choice_u", u), ("move_no", moves), ("tau0", 15),
+                       ("cpuct", 2.0), ("N", info["N"]), ("W", info["W"]), ("P", info["P"]), ("pi", pi),
+                       ("action", -1 if mv is None else gai(mv)), ("n_nodes", info["n_nodes"]), ("n_edges", info["n_edges"]),
+                       ("n_eval", len(rec.rows))):
+            out[k].append(val)
+    np.savez_compressed(
+        os.path.join(OUT, "mcts_real.npz"), sims=np.int32(sims), seed=np.int64(seed),
+        root=np.array(out["root"], dtype=np.uint32), skey=np.array(out["skey"], dtype=np.uint64),
+        testing=np.array(out["testing"], dtype=np.uint8), eps=np.array(out["eps"], dtype=np.float64),
+        noise=np.array(out["noise"], dtype=np.float32), choice_u=np.array(out["choice_u"], dtype=np.float32),
+        move_no=np.array(out["move_no"], dtype=np.int32), tau0=np.array(out["tau0"], dtype=np.int32),
+        cpuct=np.array(out["cpuct"], dtype=np.float64), N=np.array(out["N"], dtype=np.int32), W=np.array(out["W"], dtype=np.float64),
+        P=np.array(out["P"], dtype=np.float32), pi=np.array(out["pi"], dtype=np.float64), action=np.array(out["action"], dtype=np.int16),
+        n_nodes=np.array(out["n_nodes"], dtype=np.int32), n_edges=np.array(out["n_edges"], dtype=np.int32),
+        n_eval=np.array(out["n_eval"], dtype=np.int32), table_p=np.array(table_p, dtype=np.float32), table_v=np.array(table_v, dtype=np.float32))
+    print(f"mcts_real: {n_searches} searches x {sims} sims with the reference model's fp32 softmax priors, {time.time() - t0:.1f}s")
+
+
 def gen_selfplay(n_games=3, sims=12, seed=4242):
     """f1: the reference's own ``self_play_worker`` (trainer.py:434-541), unmodified, run for
     ``n_games`` whole games.  Only its collaborators are pinned down: ModelManager is the fake
@@ -580,6 +731,10 @@ def gen_selfplay(n_games=3, sims=12, seed=4242):
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "net_default" in (sys.argv[1:] or ["net_default"]):
+        gen_net_default()
+    if "mcts_real" in (sys.argv[1:] or ["mcts_real"]):
+        gen_mcts_real_priors()
     if "net" in (sys.argv[1:] or ["net"]):
         gen_net()
     if "selfplay" in (sys.argv[1:] or ["selfplay"]):

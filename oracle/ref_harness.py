@@ -161,7 +161,7 @@ def new_game_stream(key):
     return ref["G"]()
 
 
-def run_search(state, search_key, mcts_config, move_number, noise=None, choice_u=None):
+def run_search(state, search_key, mcts_config, move_number, noise=None, choice_u=None, manager=None):
     """Reference get_best_action_and_pi (MCTS.py:272-441) with in-tree draws keyed by
     (simulation, action), the fake evaluator and injected Dirichlet noise / choice uniform.
     Returns (move, pi[143] float64, info)."""
@@ -207,7 +207,7 @@ def run_search(state, search_key, mcts_config, move_number, noise=None, choice_u
         np.random.choice = choice
     try:
         move, pi = ref["mcts"].get_best_action_and_pi(
-            state.clone(), FakeModelManager(), mcts_config, move_number
+            state.clone(), manager if manager is not None else FakeModelManager(), mcts_config, move_number
         )
     finally:
         ref["mcts"].MCTS = OrigMCTS

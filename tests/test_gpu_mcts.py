@@ -211,6 +211,48 @@ def test_fused_softmax_path(mods):
     assert torch.allclose(res[0][2], res[1][2], rtol=1e-5, atol=1e-7)
 
 
+def test_golden_searches_with_the_reference_models_priors(mods):
+    """16 searches x 100 simulations run by the reference's MCTS.py with the reference's default-size
+    AlphaZeroModel behind ModelManager.predict (real fp32 softmax priors: W sums round, priors are not
+    dyadic).  The GPU trees are fed the recorded (priors, value) table in the reference's call order
+    (terminal leaves are not evaluated, MCTS.py:297) and must reproduce N, W, P, the node / edge counts,
+    pi within 1e-6 and the chosen move."""
+    hb, tr = mods
+    g = load_golden("mcts_real")
+    sims = int(g["sims"])
+    for testing in (0, 1):
+        idx = np.nonzero(g["testing"] == testing)[0]
+        n = len(idx)
+        t = tr.BatchedMCTS(n, sims)
+        t.reset(hb.states_from_numpy(g["root"][idx]), tr.search_keys_tensor(g["skey"][idx]))
+        noise = None if testing else torch.from_numpy(np.ascontiguousarray(g["noise"][idx])).cuda()
+        eps = float(g["eps"][idx][0])
+        assert (g["eps"][idx] == eps).all()
+        table_p, table_v = torch.from_numpy(g["table_p"][idx]).cuda(), torch.from_numpy(g["table_v"][idx]).cuda()
+        used = torch.zeros(n, dtype=torch.int64, device="cuda")
+        leaf = torch.empty((n, 32), dtype=torch.int32, device="cuda")
+        rows = torch.arange(n, device="cuda")
+        for _ in range(sims):
+            t.select(float(g["cpuct"][idx][0]), leaf_states=leaf)
+            live = ((leaf[:, 22] >> 29) & 3) == 0                  # is_game_over <=> winner bits set
+            k = used.clamp_max(sims - 1)
+            t.expand_backup(table_p[rows, k].contiguous(), table_v[rows, k].contiguous(), noise=noise, eps=eps)
+            used += live.to(torch.int64)
+        t.check_status()
+        assert np.array_equal(used.cpu().numpy(), g["n_eval"][idx])          # same number of network calls
+        N, W, P, _ = (x.cpu().numpy() for x in t.root_edges())
+        assert np.array_equal(N, g["N"][idx])
+        assert np.array_equal(W, g["W"][idx])
+        assert np.array_equal(P.view(np.uint32), g["P"][idx].view(np.uint32))
+        nn, ne, _ = (x.cpu().numpy() for x in t.stats())
+        assert np.array_equal(nn, g["n_nodes"][idx]) and np.array_equal(ne, g["n_edges"][idx])
+        _, pi = (x.cpu().numpy() for x in t.root_policy())
+        assert np.abs(pi.astype(np.float64) - g["pi"][idx]).max() <= 1e-6
+        expl = ((g["testing"][idx] == 0) & (g["move_no"][idx] < g["tau0"][idx])).astype(np.uint8)
+        a = t.choose(torch.from_numpy(g["choice_u"][idx]).cuda(), torch.from_numpy(expl).cuda()).cpu().numpy()
+        assert np.array_equal(a, g["action"][idx])
+
+
 def test_arena_overflow_is_reported(mods):
     hb, tr = mods
     n = 8

@@ -198,3 +198,25 @@ def test_selfplay_worker_golden(oracle):
                 mover = (S[idx] [:, 22] >> 24) & 1
                 want = np.where(mover == 0, float(oc[0]), -float(oc[0])) if oc[0] != 0 else np.zeros(len(idx))
                 assert np.array_equal(Z[idx], want.astype(np.float32))
+
+
+def test_oracle_search_with_the_reference_models_priors(oracle):
+    """tests/golden/mcts_real.npz: the reference's MCTS.py with the reference's default-size network
+    (real fp32 softmax priors).  The C oracle, fed the recorded (priors, value) table in call order,
+    reproduces visit counts, W bit for bit, priors, node and edge counts."""
+    g = load_golden("mcts_real")
+    sims = int(g["sims"])
+    for i in range(len(g["root"])):
+        calls = [0]
+
+        def ev(w, i=i):
+            k = calls[0]
+            calls[0] += 1
+            return g["table_p"][i, k], float(g["table_v"][i, k])
+
+        noise = None if g["testing"][i] else g["noise"][i]
+        r = oracle.search(g["root"][i], g["skey"][i], sims, float(g["cpuct"][i]), noise=noise, eps=float(g["eps"][i]), eval_fn=ev)
+        assert calls[0] == int(g["n_eval"][i])
+        assert np.array_equal(r["N"], g["N"][i]) and np.array_equal(r["W"], g["W"][i])
+        assert np.array_equal(r["P"].view(np.uint32), g["P"][i].view(np.uint32))
+        assert (r["n_nodes"], r["n_edges"]) == (int(g["n_nodes"][i]), int(g["n_edges"][i]))
