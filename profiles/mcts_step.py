@@ -26,7 +26,7 @@ torch.backends.cudnn.benchmark = True
 torch.manual_seed(0)
 dev = torch.device("cuda", 0)
 model = hznet.AlphaZeroNet.from_config(hznet.DEFAULT_MODEL_CONFIG).eval()
-inf = hznet.InferenceNet(model, device=dev, dtype=torch.bfloat16)
+inf = hznet.InferenceNet(model, device=dev, dtype=torch.bfloat16, tower=os.environ.get("HZ_TOWER", "auto"))
 cfg = sp.SelfPlayConfig(n_slots=a.games, num_simulations=100, use_cuda_graph=False, seed=77)
 drv = sp.BatchedSelfPlay(inf, cfg, device=dev)
 states = hb.init_states(a.games, device=dev, seed=77)
@@ -59,20 +59,19 @@ def timed(fn, reps=20):
 
 parts = {}
 for _ in range(3):
-    parts["select_us"] = timed(lambda: g.tree.select(cfg.cpuct, g.board, g.glob, dtype=inf.dtype, channels_last=True, pad40=drv.pad40), 1)
-    x = inf._conv_relu(g.board, inf.stem40 if drv.pad40 else inf.stem, 1)
-
-    def tower():
-        global x
-        x = inf._conv_relu(g.board, inf.stem40 if drv.pad40 else inf.stem, 1)
-        for c1, c2 in inf.blocks:
-            y = inf._conv_relu(x, c1, 1)
-            x = inf._conv_relu(y, c2, 1, residual=x)
-
-    parts["tower_us"] = timed(tower, 5)
-    parts["heads_us"] = timed(lambda: inf._fused_heads(x, g.glob, (g.logits, g.value)), 5)
+    parts["select_us"] = timed(lambda: g.tree.select(cfg.cpuct, g.board, g.glob, dtype=inf.dtype, channels_last=True, pad40=drv.pad40, tiles=g.tiles), 1)
+    if g.tiles:       # hand-written tower: leaves are already in the stem's operand image
+        n = g.glob.shape[0]
+        parts["tower_us"] = timed(lambda: inf.hand.forward_tiles(g.board, n), 5)
+        parts["tower_and_heads_us"] = timed(lambda: inf.forward_tiles(g.board, g.glob, n, out=(g.logits, g.value)), 5)
+        parts["heads_us"] = parts["tower_and_heads_us"] - parts["tower_us"]
+    else:
+        x = inf.tower_out(g.board)
+        parts["tower_us"] = timed(lambda: inf.tower_out(g.board), 5)
+        parts["heads_us"] = timed(lambda: inf._fused_heads(x, g.glob, (g.logits, g.value)), 5)
     parts["expand_us"] = timed(lambda: g.tree.expand_backup(g.logits, g.value, is_logits=True, noise=g.noise, eps=cfg.dirichlet_epsilon), 1)
-parts["step_sum_us"] = sum(v for k, v in parts.items())
+parts["step_sum_us"] = parts["select_us"] + parts["tower_us"] + parts["heads_us"] + parts["expand_us"]
+parts["tower"] = "hand" if g.tiles else "cudnn"
 import json  # noqa: E402
 
 print(json.dumps(parts))
