@@ -50,7 +50,8 @@ SIGNATURES = {
     "hz_tower_set_trace": (_i, [_vp]),
     "hz_tower_to_tiles": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
     "hz_tower_from_tiles": (_i, [_vp, _vp, _i64, _vp]),
-    "hz_tower_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "hz_tower_sched_bytes": (C.c_size_t, [_i64, _i]),
+    "hz_tower_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "hz_tower_conv3x3": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
 }
 

@@ -57,7 +57,8 @@ constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;   // barriers + alignment slack
 
 // barrier indices
 constexpr int B_WFULL = 0, B_WEMPTY = NSTAGE, B_AFULL = 2 * NSTAGE, B_AEMPTY = 2 * NSTAGE + 2, B_TFULL = 2 * NSTAGE + 4,
-              B_TEMPTY = 2 * NSTAGE + 4 + NUNIT, B_DONE = 2 * NSTAGE + 4 + 2 * NUNIT, B_YDONE = B_DONE + 1, N_BARS = B_YDONE + 8;
+              B_TEMPTY = 2 * NSTAGE + 4 + NUNIT, B_DONE = 2 * NSTAGE + 4 + 2 * NUNIT, B_QFULL = B_DONE + 1, B_QEMPTY = B_QFULL + 2,
+              N_BARS = B_QEMPTY + 2;
 
 // tap = ky*3 + kx (dy = ky-1, dx = kx-1).  Within a dy group the dx = 0 tap comes first: the first
 // MMA into a row accumulator overwrites it and must cover all 112 columns.
@@ -70,7 +71,8 @@ __device__ __forceinline__ int unit_of(int r) { return r == 4 ? 0 : r; }
 __device__ __forceinline__ int use_of(int r, int it) { return r == 0 ? 2 * it : r == 4 ? 2 * it + 1 : it; }
 
 constexpr int MAX_LAYERS = 20;   // stem + 8 residual blocks = 17
-constexpr int MAX_SLOTS = 8;     // tiles per CTA the fused (multi-layer) launch supports
+constexpr int N_CONSUMERS = 11;  // roles that read the work-item queue: weight producer, activation producer, MMA warp, 8 epilogue warps
+constexpr unsigned FLAG_DONE = 8; // a tile's layer output is complete when its 8 epilogue warps have signalled
 
 struct Layer {
     const uint8_t* w;      // weight tiles [9][nkh][128][128 B]
@@ -78,12 +80,19 @@ struct Layer {
     int in_buf, res_buf, out_buf;   // indices into Params::buf; res_buf < 0: no residual
     int nkh, kmajor, relu; // input channel halves; input image T16K (stem) or T16
 };
-// One launch runs layers[0..n_layers) for every tile the CTA owns.  Boards are independent, so a CTA
-// needs no other CTA's output: layer l+1 of a tile only waits for the CTA's own epilogue of layer l.
+// One launch runs layers[0..n_layers) for all tiles.  Work item i = (layer i / n_tiles, tile i % n_tiles);
+// boards are independent, so item (l, t) depends on item (l-1, t) only.  With `sched` the CTAs draw items
+// from a global counter in index order (dynamic: 17 x 256 items over 148 CTAs balance to within one item,
+// where a static tile-to-CTA map leaves 40 CTAs idle half the time at 256 tiles) and a tile's completion
+// is published through sched[1 + item] (8 epilogue warps -> FLAG_DONE).  Deadlock-free: items are handed
+// out in increasing order and every CTA works through its items in order, so the smallest unfinished
+// item always has its dependency finished and its owner working on it; all CTAs are co-resident (grid <=
+// SM count, one CTA per SM).  Without `sched` (single layer): static map, no dependencies.
 struct Params {
     uint8_t* buf[4];       // activation tile buffers (T16; a kmajor layer's input buffer is T16K with one half)
     Layer layers[MAX_LAYERS];
     int n_layers, n_tiles;
+    unsigned int* sched;   // [0] = next work item, [1 + l*n_tiles + t] = completion count of (l, t); zeroed before the launch
     int dbg;               // profiling only (hz_tower_set_debug): 1 skip MMAs, 2 skip epilogue memory traffic, 4 skip weight copies, 8 skip activation copies
     unsigned int* fault;
     unsigned long long* trace;   // profiling only (hz_tower_set_trace): SM-clock timestamps of CTA 0's roles
@@ -220,20 +229,42 @@ struct IssueCtx {
     int nstage;                  // running stage count (trace index)
 };
 
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// spin until item `dep`'s output is complete (bounded like the mbarrier waits)
+__device__ __forceinline__ void wait_item_done(const unsigned int* sched, int dep, unsigned int* fault, unsigned int code) {
+    const unsigned int* f = sched + 1 + dep;
+    for (uint32_t it = 0; ld_acquire_gpu(f) < FLAG_DONE; ++it) {
+        __nanosleep(64);
+        if (it > (1u << 22)) {
+            if (fault) { atomicExch(fault, code); __threadfence_system(); }
+            __trap();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ Params P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sX = smem_u32(sm + OFF_X), sW = smem_u32(sm + OFF_W), sBar = smem_u32(sm + OFF_BAR);
     uint32_t* tmem_slot = (uint32_t*)(sm + OFF_BAR + N_BARS * 8);
+    volatile int* qitem = (volatile int*)(sm + OFF_BAR + N_BARS * 8 + 16);   // work-item queue, 2 entries
     auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = P.n_layers * P.n_tiles;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; i++) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
         for (int i = 0; i < 2; i++) { mbar_init(bar(B_AFULL + i), 1); mbar_init(bar(B_AEMPTY + i), 1); }
         for (int i = 0; i < NUNIT; i++) { mbar_init(bar(B_TFULL + i), 1); mbar_init(bar(B_TEMPTY + i), 8); }
         mbar_init(bar(B_DONE), 1);
-        for (int i = 0; i < MAX_SLOTS; i++) mbar_init(bar(B_YDONE + i), 8);
+        for (int i = 0; i < 2; i++) { mbar_init(bar(B_QFULL + i), 1); mbar_init(bar(B_QEMPTY + i), N_CONSUMERS); }
         mbar_init_fence();
     }
     if (warp == 3) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -243,15 +274,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
     const uint32_t tbase = *tmem_slot;
     if (warp == 0) HZ_TRACE(0);
 
-    // every role walks the same sequence of work items: for layer, for this CTA's tiles (slot = 0, 1, ..)
-    if (warp == 0 && lane == 0) {
+    // every role walks the CTA's work items in the order the scheduler (warp 3) publishes them; -1 ends the walk.
+    // NEXT_ITEM: whole-warp roles call it converged; single-lane roles call it from their one lane.
+#define HZ_NEXT_ITEM(k, item, whole_warp)                                                      \
+    do {                                                                                       \
+        mbar_wait(bar(B_QFULL + ((k) & 1)), ((uint32_t)(k) >> 1) & 1u, P.fault, 0x900 + warp); \
+        item = qitem[(k) & 1];                                                                 \
+        if (whole_warp) __syncwarp();                                                          \
+        if (!(whole_warp) || lane == 0) mbar_arrive(bar(B_QEMPTY + ((k) & 1)));                \
+        (k)++;                                                                                 \
+    } while (0)
+
+    if (warp == 3) {
+        // ---- scheduler ----
+        if (lane == 0) {
+            const int per_cta = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // static map: tiles blockIdx.x + j*gridDim.x
+            for (int k = 0;; k++) {
+                int item;
+                if (P.sched) {
+                    item = (int)atomicAdd(P.sched, 1u);
+                    if (item >= n_items) item = -1;
+                } else {
+                    item = k < per_cta * P.n_layers ? (k / per_cta) * P.n_tiles + (int)blockIdx.x + (k % per_cta) * (int)gridDim.x : -1;
+                }
+                mbar_wait(bar(B_QEMPTY + (k & 1)), (((uint32_t)k >> 1) & 1u) ^ 1u, P.fault, 0xA00);
+                qitem[k & 1] = item;
+                mbar_arrive(bar(B_QFULL + (k & 1)));      // release: the consumers' waits acquire the slot
+                if (item < 0) break;
+            }
+        }
+    } else if (warp == 0) {
         // ---- weight producer: the tap stream of every pass of every item, through the ring ----
-        uint32_t stage = 0, ph = 0;
-        int ns = 0;
-        for (int l = 0; l < P.n_layers; l++) {
-            const uint8_t* w = P.layers[l].w;
-            const int nkh = P.layers[l].nkh;
-            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x)
+        if (lane == 0) {
+            uint32_t stage = 0, ph = 0;
+            int ns = 0, k = 0;
+            for (;;) {
+                int item;
+                HZ_NEXT_ITEM(k, item, false);
+                if (item < 0) break;
+                const Layer& L = P.layers[item / P.n_tiles];
+                const int nkh = L.nkh;
                 for (int pass = 0; pass < 2; pass++)
                     for (int kh = 0; kh < nkh; kh++)
                         for (int ti = 0; ti < 9; ti++, ns++) {
@@ -261,21 +323,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                             if (P.dbg & 4) mbar_arrive(bar(B_WFULL + stage));
                             else {
                                 mbar_expect_tx(bar(B_WFULL + stage), W_BYTES);
-                                bulk_g2s(sW + stage * W_BYTES, w + (size_t)(tap * nkh + kh) * W_BYTES, W_BYTES, bar(B_WFULL + stage));
+                                bulk_g2s(sW + stage * W_BYTES, L.w + (size_t)(tap * nkh + kh) * W_BYTES, W_BYTES, bar(B_WFULL + stage));
                             }
                             if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
                         }
+            }
         }
-    } else if (warp == 2 && lane == 0) {
+    } else if (warp == 2) {
         // ---- activation producer: one channel half of a tile per buffer ----
-        uint32_t cnt0 = 0, cnt1 = 0;       // uses of each half buffer so far (barrier phase)
-        int na = 0;
-        for (int l = 0; l < P.n_layers; l++) {
-            const Layer& L = P.layers[l];
-            int slot = 0;
-            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, slot++) {
-                // the tile's input is the CTA's own output of the previous layer: wait for that epilogue
-                if (l > 0) mbar_wait(bar(B_YDONE + slot), (uint32_t)(l - 1) & 1u, P.fault, 0x800 + slot);
+        if (lane == 0) {
+            uint32_t cnt0 = 0, cnt1 = 0;       // uses of each half buffer so far (barrier phase)
+            int na = 0, k = 0;
+            for (;;) {
+                int item;
+                HZ_NEXT_ITEM(k, item, false);
+                if (item < 0) break;
+                const int l = item / P.n_tiles, tile = item - l * P.n_tiles;
+                const Layer& L = P.layers[l];
+                if (l > 0) {
+                    // the tile's input is the previous layer's output, possibly written by another CTA through the
+                    // generic proxy: acquire its completion flag, then order the async-proxy reads behind it
+                    wait_item_done(P.sched, item - P.n_tiles, P.fault, 0x800);
+                    fence_proxy_async();
+                }
                 for (int kh = 0; kh < L.nkh; kh++, na++) {
                     mbar_wait(bar(B_AEMPTY + kh), ((kh ? cnt1 : cnt0) & 1u) ^ 1u, P.fault, 0x200 + kh);
                     if (kh) cnt1++; else cnt0++;
@@ -292,23 +362,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
         // ---- MMA issuer: the whole warp runs the loop, one elected lane issues ----
         IssueCtx c{sBar, sW, sX, tbase, 0u, 0u, P.fault, P.dbg, (blockIdx.x == 0 && lane == 0) ? P.trace : nullptr, 0};
         uint32_t cnt0 = 0, cnt1 = 0;
-        int wi = 0;                        // work item counter (phase of the accumulator units)
-        for (int l = 0; l < P.n_layers; l++) {
-            const int nkh = P.layers[l].nkh;
-            const bool kmajor = P.layers[l].kmajor != 0;
-            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, wi++) {
-                for (int kh = 0; kh < nkh; kh++) {
-                    mbar_wait(bar(B_AFULL + kh), (kh ? cnt1 : cnt0) & 1u, P.fault, 0x300 + kh);
-                    if (kmajor) StageLoop<true, 0, 0>::run(c, kh, wi, kh == nkh - 1);
-                    else StageLoop<false, 0, 0>::run(c, kh, wi, kh == nkh - 1);
-                }
-                for (int kh = 0; kh < nkh; kh++) {
-                    if (kmajor) StageLoop<true, 1, 0>::run(c, kh, wi, kh == nkh - 1);
-                    else StageLoop<false, 1, 0>::run(c, kh, wi, kh == nkh - 1);
-                    if (elect_one()) umma_commit(bar(B_AEMPTY + kh));   // the tile's channel half is no longer read
-                    __syncwarp();
-                    if (kh) cnt1++; else cnt0++;
-                }
+        int wi = 0, k = 0;                 // wi: work items done (phase of the accumulator units)
+        for (;; wi++) {
+            int item;
+            HZ_NEXT_ITEM(k, item, true);
+            if (item < 0) break;
+            const Layer& L = P.layers[item / P.n_tiles];
+            const int nkh = L.nkh;
+            const bool kmajor = L.kmajor != 0;
+            for (int kh = 0; kh < nkh; kh++) {
+                mbar_wait(bar(B_AFULL + kh), (kh ? cnt1 : cnt0) & 1u, P.fault, 0x300 + kh);
+                if (kmajor) StageLoop<true, 0, 0>::run(c, kh, wi, kh == nkh - 1);
+                else StageLoop<false, 0, 0>::run(c, kh, wi, kh == nkh - 1);
+            }
+            for (int kh = 0; kh < nkh; kh++) {
+                if (kmajor) StageLoop<true, 1, 0>::run(c, kh, wi, kh == nkh - 1);
+                else StageLoop<false, 1, 0>::run(c, kh, wi, kh == nkh - 1);
+                if (elect_one()) umma_commit(bar(B_AEMPTY + kh));   // the tile's channel half is no longer read
+                __syncwarp();
+                if (kh) cnt1++; else cnt0++;
             }
         }
         if (elect_one()) umma_commit(bar(B_DONE));
@@ -325,86 +397,90 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
         const int x0 = half ? 4 : 0;
         const uint32_t chan_off = (uint32_t)(c >> 3) * KG_BYTES + (uint32_t)(c & 7) * 16u;
         const bool mem = !(P.dbg & 2);
-        int wi = 0, nrow = 0;
-        for (int l = 0; l < P.n_layers; l++) {
+        int nrow = 0, k = 0;
+        for (int wi = 0;; wi++) {
+            int item;
+            HZ_NEXT_ITEM(k, item, true);
+            if (item < 0) break;
+            const int l = item / P.n_tiles, tile = item - l * P.n_tiles;
             const Layer& L = P.layers[l];
             const float bias = L.bias[c];
             const uint8_t* resb = (L.res_buf >= 0 && mem) ? P.buf[L.res_buf] : nullptr;
             uint8_t* yb = P.buf[L.out_buf];
             const bool relu = L.relu != 0;
-            int slot = 0;
-            for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, wi++, slot++) {
-                const size_t tile_off = (size_t)tile * 2 * KH_BYTES + chan_off;
-                for (int ri = 0; ri < BROWS; ri++, nrow++) {
-                    const int r = EPI_ORDER[ri], unit = unit_of(r);
-                    const size_t row_off = tile_off + (size_t)(r * BCOLS + x0) * (G * 16);
-                    // the residual of this warp's cells is requested before the accumulator is waited for
-                    // (this thread wrote those bytes itself two layers ago: program order makes them visible)
-                    uint4 rv[8];
+            // the residual (the block input, two layers back) may have been written by another CTA: observing the
+            // previous layer's completion flag makes the whole chain of this tile's earlier outputs visible
+            if (l > 0 && lane == 0) wait_item_done(P.sched, item - P.n_tiles, P.fault, 0x810);
+            __syncwarp();
+            const size_t tile_off = (size_t)tile * 2 * KH_BYTES + chan_off;
+            for (int ri = 0; ri < BROWS; ri++, nrow++) {
+                const int r = EPI_ORDER[ri], unit = unit_of(r);
+                const size_t row_off = tile_off + (size_t)(r * BCOLS + x0) * (G * 16);
+                // the residual of this warp's cells is requested before the accumulator is waited for
+                uint4 rv[8];
+                if (resb) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (j < 3 || !half) {
+                            const uint8_t* rp = resb + row_off + (size_t)j * (G * 16);
+                            rv[2 * j] = *reinterpret_cast<const uint4*>(rp);
+                            rv[2 * j + 1] = *reinterpret_cast<const uint4*>(rp + 128);
+                        }
+                }
+                if (warp == 4) HZ_TRACE(600 + 4 * nrow);
+                mbar_wait(bar(B_TFULL + unit), use_of(r, wi) & 1, P.fault, 0x700 + unit);
+                tc_fence_after();
+                if (warp == 4) HZ_TRACE(600 + 4 * nrow + 1);
+                uint32_t v[4][16];
+                const uint32_t ta = tbase + ((uint32_t)(q * 32) << 16) + unit * UNIT_COLS + x0 * G;
+                tmem_ld16(ta, v[0]);
+                tmem_ld16(ta + G, v[1]);
+                tmem_ld16(ta + 2 * G, v[2]);
+                if (!half) tmem_ld16(ta + 3 * G, v[3]);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(B_TEMPTY + unit));      // the accumulator may be overwritten from here on
+                if (warp == 4) HZ_TRACE(600 + 4 * nrow + 2);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (j == 3 && half) break;
+                    float o[16];
+#pragma unroll
+                    for (int b = 0; b < G; b++) o[b] = __uint_as_float(v[j][b]) + bias;
                     if (resb) {
+                        const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rv[2 * j]);
 #pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            if (j < 3 || !half) {
-                                const uint8_t* rp = resb + row_off + (size_t)j * (G * 16);
-                                rv[2 * j] = *reinterpret_cast<const uint4*>(rp);
-                                rv[2 * j + 1] = *reinterpret_cast<const uint4*>(rp + 128);
-                            }
-                    }
-                    if (warp == 4) HZ_TRACE(600 + 4 * nrow);
-                    mbar_wait(bar(B_TFULL + unit), use_of(r, wi) & 1, P.fault, 0x700 + unit);
-                    tc_fence_after();
-                    if (warp == 4) HZ_TRACE(600 + 4 * nrow + 1);
-                    uint32_t v[4][16];
-                    const uint32_t ta = tbase + ((uint32_t)(q * 32) << 16) + unit * UNIT_COLS + x0 * G;
-                    tmem_ld16(ta, v[0]);
-                    tmem_ld16(ta + G, v[1]);
-                    tmem_ld16(ta + 2 * G, v[2]);
-                    if (!half) tmem_ld16(ta + 3 * G, v[3]);
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(B_TEMPTY + unit));      // the accumulator may be overwritten from here on
-                    if (warp == 4) HZ_TRACE(600 + 4 * nrow + 2);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        if (j == 3 && half) break;
-                        float o[16];
-#pragma unroll
-                        for (int b = 0; b < G; b++) o[b] = __uint_as_float(v[j][b]) + bias;
-                        if (resb) {
-                            const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rv[2 * j]);
-#pragma unroll
-                            for (int e = 0; e < 8; e++) {
-                                o[2 * e] += __uint_as_float(rw[e] << 16);
-                                o[2 * e + 1] += __uint_as_float(rw[e] & 0xFFFF0000u);
-                            }
+                        for (int e = 0; e < 8; e++) {
+                            o[2 * e] += __uint_as_float(rw[e] << 16);
+                            o[2 * e + 1] += __uint_as_float(rw[e] & 0xFFFF0000u);
                         }
-                        uint8_t* yp = yb + row_off + (size_t)j * (G * 16);
-                        if (!mem) { if (o[0] + o[5] + o[10] + o[15] == 12345.678f) *reinterpret_cast<float*>(yp) = o[3]; continue; }
-                        uint32_t pk[8];
-                        if (relu) {
-#pragma unroll
-                            for (int e = 0; e < 8; e++) pk[e] = pack_bf16x2_relu(o[2 * e], o[2 * e + 1]);
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 8; e++) pk[e] = pack_bf16x2(o[2 * e], o[2 * e + 1]);
-                        }
-                        *reinterpret_cast<uint4*>(yp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        *reinterpret_cast<uint4*>(yp + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     }
-                    if (warp == 4) HZ_TRACE(600 + 4 * nrow + 3);
+                    uint8_t* yp = yb + row_off + (size_t)j * (G * 16);
+                    if (!mem) { if (o[0] + o[5] + o[10] + o[15] == 12345.678f) *reinterpret_cast<float*>(yp) = o[3]; continue; }
+                    uint32_t pk[8];
+                    if (relu) {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) pk[e] = pack_bf16x2_relu(o[2 * e], o[2 * e + 1]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) pk[e] = pack_bf16x2(o[2 * e], o[2 * e + 1]);
+                    }
+                    *reinterpret_cast<uint4*>(yp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(yp + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 }
-                if (l + 1 < P.n_layers) {
-                    // hand the tile's output to the activation producer of the next layer: the stores go
-                    // through the generic proxy, the bulk copy reads through the async proxy
-                    __threadfence();
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(B_YDONE + slot));
-                }
+                if (warp == 4) HZ_TRACE(600 + 4 * nrow + 3);
+            }
+            if (P.sched && l + 1 < P.n_layers) {
+                // publish the tile's output: generic-proxy stores -> visible at gpu scope and to async-proxy readers
+                __threadfence();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) red_release_gpu_add(P.sched + 1 + item, 1u);
             }
         }
     }
+#undef HZ_NEXT_ITEM
     tc_fence_before();
     __syncthreads();
     if (warp == 0) HZ_TRACE(1);
@@ -553,6 +629,7 @@ int hz_tower_conv3x3(const void* x_tiles, int in_channel_halves, int in_kmajor, 
     P.layers[0] = Layer{(const uint8_t*)w_tiles, bias, 0, residual_tiles ? 1 : -1, 2, in_channel_halves, in_kmajor, relu};
     P.n_layers = 1;
     P.n_tiles = (int)(n_boards / G);
+    P.sched = nullptr;
     P.fault = fault;
     P.dbg = g_debug;
     P.trace = g_trace;
@@ -560,13 +637,19 @@ int hz_tower_conv3x3(const void* x_tiles, int in_channel_halves, int in_kmajor, 
     return hz_launched(1);
 }
 
+size_t hz_tower_sched_bytes(int64_t n_boards, int n_blocks) {
+    if (n_boards <= 0 || n_blocks < 0) return 0;
+    int64_t tiles = (n_boards + hz::tower::G - 1) / hz::tower::G;
+    return sizeof(unsigned int) * (size_t)(1 + (1 + 2 * n_blocks) * tiles);
+}
+
 int hz_tower_forward(const void* x0_tiles, const void* const* w_tiles, const float* const* biases, int n_blocks, void* buf_a,
-                     void* buf_b, void* buf_c, void** out_tiles, int64_t n_boards, unsigned int* fault, void* stream) {
+                     void* buf_b, void* buf_c, void* sched, void** out_tiles, int64_t n_boards, unsigned int* fault, void* stream) {
     using namespace hz::tower;
-    if (!x0_tiles || !w_tiles || !biases || !buf_a || !buf_b || !buf_c || n_boards <= 0 || (n_boards % G) || n_blocks < 0 ||
+    if (!x0_tiles || !w_tiles || !biases || !buf_a || !buf_b || !buf_c || !sched || n_boards <= 0 || (n_boards % G) || n_blocks < 0 ||
         1 + 2 * n_blocks > MAX_LAYERS)
         return HZ_ERR_ARG;
-    if (((uintptr_t)x0_tiles | (uintptr_t)buf_a | (uintptr_t)buf_b | (uintptr_t)buf_c) & 15) return HZ_ERR_ARG;
+    if (((uintptr_t)x0_tiles | (uintptr_t)buf_a | (uintptr_t)buf_b | (uintptr_t)buf_c | (uintptr_t)sched) & 15) return HZ_ERR_ARG;
     int st = ensure_attr();
     if (st != HZ_OK) return st;
     Params P{};
@@ -589,25 +672,15 @@ int hz_tower_forward(const void* x0_tiles, const void* const* w_tiles, const flo
     }
     P.n_layers = n;
     P.n_tiles = (int)(n_boards / G);
+    P.sched = (unsigned int*)sched;
     P.fault = fault;
     P.dbg = g_debug;
     P.trace = g_trace;
     if (out_tiles) *out_tiles = P.buf[cur];
-    const int grid = grid_for(P.n_tiles);
-    if ((P.n_tiles + grid - 1) / grid <= MAX_SLOTS) {
-        k_tower<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(P);
-        return hz_launched(1);
-    }
-    // more tiles per CTA than the fused launch tracks: one launch per layer (stream order is the dependency)
-    for (int l = 0; l < n; l++) {
-        Params Q = P;
-        Q.layers[0] = P.layers[l];
-        Q.n_layers = 1;
-        k_tower<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(Q);
-        int r = hz_launched(1);
-        if (r != HZ_OK) return r;
-    }
-    return HZ_OK;
+    cudaError_t e = cudaMemsetAsync(sched, 0, hz_tower_sched_bytes(n_boards, n_blocks), (cudaStream_t)stream);
+    if (e != cudaSuccess) return hz_record_launch(0, e);
+    k_tower<<<grid_for(P.n_tiles), NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    return hz_launched(1);
 }
 
 }  // extern "C"

@@ -76,6 +76,7 @@ class HandTower:
             tiles = n_pad // G
             mk = lambda halves: torch.zeros(tiles * halves * KH_BYTES, dtype=torch.uint8, device=self.device)  # noqa: E731
             b = self._bufs[n_pad] = dict(x0=mk(1), a=mk(2), b=mk(2), c=mk(2),
+                                         sched=torch.zeros(self.lib.hz_tower_sched_bytes(n_pad, len(self.blocks)), dtype=torch.uint8, device=self.device),
                                          out=torch.zeros((n_pad, 35, 128), dtype=torch.bfloat16, device=self.device))
         return b
 
@@ -116,7 +117,7 @@ class HandTower:
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.hz_tower_forward(
                     x0.data_ptr(), self._w_ptrs, self._b_ptrs, len(self.blocks), x.data_ptr(), y.data_ptr(), z.data_ptr(),
-                    ct.byref(res), n_pad, self.fault, self._stream()), "hz_tower_forward")
+                    buf["sched"].data_ptr(), ct.byref(res), n_pad, self.fault, self._stream()), "hz_tower_forward")
             return res.value
         self.conv(x0, 1, self.stem, None, x, n_pad, kmajor=True)
         for c1, c2 in self.blocks:

@@ -365,12 +365,16 @@ int hz_tower_conv3x3(const void *x_tiles, int in_channel_halves, int in_kmajor, 
  * n_blocks residual blocks (layers 1 + 2i: conv+bn+relu, 2 + 2i: conv+bn, + block input, relu).
  * w_tiles / biases: HOST arrays of 1 + 2*n_blocks DEVICE pointers (weight tiles as above, fp32
  * bias[128]).  buf_a/b/c: three T16 scratch buffers of hz_tower_tile_bytes(n_boards, 2) bytes;
- * *out_tiles receives the one that holds the result (buf_a or buf_c).  Boards are independent,
- * so each CTA carries its own tiles through all layers with no grid-wide synchronisation: layer
- * l+1 of a tile starts as soon as the CTA's own epilogue of layer l has stored it. */
+ * *out_tiles receives the one that holds the result (buf_a or buf_c).  sched: device scratch of
+ * hz_tower_sched_bytes() bytes (zeroed by the call on `stream`).
+ * Boards are independent, so work item (layer l, tile t) depends on (l-1, t) only: the CTAs draw
+ * the (1 + 2*n_blocks) * n_boards/16 items from a global counter in order and publish each
+ * tile's completion through `sched` — no grid-wide synchronisation, and the load balances to
+ * within one item per CTA whatever the tile count. */
+size_t hz_tower_sched_bytes(int64_t n_boards, int n_blocks);
 int hz_tower_forward(const void *x0_tiles, const void *const *w_tiles, const float *const *biases,
-                     int n_blocks, void *buf_a, void *buf_b, void *buf_c, void **out_tiles,
-                     int64_t n_boards, unsigned int *fault, void *stream);
+                     int n_blocks, void *buf_a, void *buf_b, void *buf_c, void *sched,
+                     void **out_tiles, int64_t n_boards, unsigned int *fault, void *stream);
 
 #define HZ_PLAYOUT_SALT 0xA5A5F00DC0FFEE11ull
 #define HZ_SEARCH_SALT  0x5EA2C47EE5A17B00ull

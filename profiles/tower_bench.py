@@ -131,6 +131,15 @@ def main():
         with torch.cuda.graph(gt):
             net.tower_out(board)
         out[name + "_tower_graph"] = timeit(gt.replay, a.iters)
+    # attribution of the fused all-layers launch (eager; results are garbage with a switch on)
+    x0 = hand.hand.x0_buffer(B)
+    hand.hand.to_tiles(board, 40, True, x0)
+    fa = {}
+    for flags, name in ((0, "full"), (4, "no_weight_copies"), (8, "no_act_copies"), (2, "no_epilogue_mem"), (12, "no_copies"), (14, "mma_only"), (1, "no_mma")):
+        ht.lib.hz_tower_set_debug(flags)
+        fa[name] = timeit(lambda: hand.hand.forward_tiles(x0, B), a.iters)["us_min"]
+    ht.lib.hz_tower_set_debug(0)
+    out["hand_tower_fused_attribution_us"] = fa
     lh, vh = hand(board, glob)
     ll, vl = lib(board, glob)
     out["max_logit_diff_hand_vs_cudnn"] = float((lh - ll).abs().max())
