@@ -31,8 +31,9 @@
 //     complete and drained before pass 1 starts; pass 1 runs dy = -1, 0, +1, so row 4 (no dy = +1)
 //     is drained before the next tile's row 0 needs the unit.  The epilogue of one row therefore
 //     always overlaps the MMAs of the others.
-//   * warp roles: 0 = weight producer, 1 = MMA issuer, 2 = activation producer, 3 = TMEM
-//     allocator, 4..11 = epilogue (bias + residual + ReLU + bf16, thread = output channel).
+//   * warp roles: 0 = weight producer, 1 and 12 = MMA issuers (alternating weight stages), 2 =
+//     activation producer, 3 = TMEM allocator + work scheduler, 4..11 = epilogue (bias + residual +
+//     ReLU + bf16, thread = output channel).
 #include "hz_common.cuh"
 #include "hz_sm100.cuh"
 
@@ -49,7 +50,7 @@ constexpr int ROW_BYTES = BCOLS * G * 128;     // 14,336: one board row of one c
 constexpr int W_BYTES = 128 * 128;             // 16,384: [128 out][64 in] bf16
 constexpr int NSTAGE = 5;
 constexpr int NUNIT = 4, UNIT_COLS = 128;
-constexpr int NTHREADS = 384;                  // 4 control warps + 8 epilogue warps
+constexpr int NTHREADS = 416;                  // 4 control warps + 8 epilogue warps + the second MMA issuer
 constexpr int OFF_X = 0;
 constexpr int OFF_W = 2 * KH_BYTES;
 constexpr int OFF_BAR = OFF_W + NSTAGE * W_BYTES;
@@ -71,7 +72,7 @@ __device__ __forceinline__ int unit_of(int r) { return r == 4 ? 0 : r; }
 __device__ __forceinline__ int use_of(int r, int it) { return r == 0 ? 2 * it : r == 4 ? 2 * it + 1 : it; }
 
 constexpr int MAX_LAYERS = 20;   // stem + 8 residual blocks = 17
-constexpr int N_CONSUMERS = 11;  // roles that read the work-item queue: weight producer, activation producer, MMA warp, 8 epilogue warps
+constexpr int N_CONSUMERS = 12;  // roles that read the work-item queue: weight producer, activation producer, 2 MMA warps, 8 epilogue warps
 constexpr unsigned FLAG_DONE = 8; // a tile's layer output is complete when its 8 epilogue warps have signalled
 
 struct Layer {
@@ -81,30 +82,37 @@ struct Layer {
     int nkh, kmajor, relu; // input channel halves; input image T16K (stem) or T16
 };
 // One launch runs layers[0..n_layers) for all tiles.  Work item i = (layer i / n_tiles, tile i % n_tiles);
-// boards are independent, so item (l, t) depends on item (l-1, t) only.  With `sched` the CTAs draw items
-// from a global counter in index order (dynamic: 17 x 256 items over 148 CTAs balance to within one item,
-// where a static tile-to-CTA map leaves 40 CTAs idle half the time at 256 tiles) and a tile's completion
-// is published through sched[1 + item] (8 epilogue warps -> FLAG_DONE).  Deadlock-free: items are handed
-// out in increasing order and every CTA works through its items in order, so the smallest unfinished
-// item always has its dependency finished and its owner working on it; all CTAs are co-resident (grid <=
-// SM count, one CTA per SM).  Without `sched` (single layer): static map, no dependencies.
+// boards are independent, so item (l, t) depends on item (l-1, t) only.  With `sched` the CTAs take items
+// from a global READY QUEUE: it starts with the stem items, and the last of the 8 epilogue warps to finish
+// item (l, t) appends (l+1, t).  An item is therefore handed out only when its input is complete (no
+// dependency stalls, and its tile can be prefetched while the previous item is still in flight), and the
+// load balances to within one item per CTA (a static tile-to-CTA map leaves 40 of 148 CTAs idle half the
+// time at 256 tiles).  Every queue slot below n_items is filled exactly once, so a scheduler that drew
+// slot s only ever waits for the s-th completion, which some running CTA is producing: no deadlock (all
+// CTAs are co-resident: grid <= SM count, one CTA per SM).  Without `sched` (single layer): static map.
 struct Params {
     uint8_t* buf[4];       // activation tile buffers (T16; a kmajor layer's input buffer is T16K with one half)
     Layer layers[MAX_LAYERS];
     int n_layers, n_tiles;
-    unsigned int* sched;   // [0] = next work item, [1 + l*n_tiles + t] = completion count of (l, t); zeroed before the launch
-    int dbg;               // profiling only (hz_tower_set_debug): 1 skip MMAs, 2 skip epilogue memory traffic, 4 skip weight copies, 8 skip activation copies
+    unsigned int* sched;   // ready queue (see hz_tower_forward): [0] head, [1] tail, [2 + item] completion count, [2 + n_items + slot] queue
+    int dbg;               // profiling only (hz_tower_set_debug): 1 skip MMAs, 2 skip epilogue memory traffic, 4 skip weight copies, 8 skip activation copies, 32 single MMA issuer
     unsigned int* fault;
     unsigned long long* trace;   // profiling only (hz_tower_set_trace): SM-clock timestamps of CTA 0's roles
 };
-// trace slots (CTA 0 only): [0] start, [1] end; MMA warp per weight stage i: [16+3i] before the wait on the
-// stage, [+1] after it, [+2] after the MMAs and commits were issued; weight producer [400+i] when it issues
-// stage i; epilogue warp 4 per row j: [600+4j] before the accumulator wait, [+1] after, [+2] after the TMEM
-// loads, [+3] after the stores; activation producer [700+j] when it issues half j.
+// trace slots (CTA 0 only, 4096 uint64): [0] start, [1] end (SM clock), [2] start, [3] end (globaltimer, ns);
+// MMA warp per weight stage i < 600: [16+3i] before the wait on the stage, [+1] after it, [+2] after the MMAs
+// and commits were issued; weight producer [2000+i] when it issues stage i; epilogue warp 4 per row j < 200:
+// [2700+4j] before the accumulator wait, [+1] after, [+2] after the TMEM loads, [+3] after the stores;
+// activation producer [3600+j] when it issues half j.
 #define HZ_TRACE(slot)                                                                  \
     do {                                                                                \
-        if (P.trace && blockIdx.x == 0 && lane == 0 && (slot) < 1024) P.trace[slot] = clock64(); \
+        if (P.trace && blockIdx.x == 0 && lane == 0 && (slot) < 4096) P.trace[slot] = clock64(); \
     } while (0)
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // B operand, MN-major without swizzle: core matrices of [8 channels][8 positions]; LBO = stride
 // between 8-channel groups (K direction), SBO = stride between 8-position groups (N direction)
@@ -160,7 +168,7 @@ constexpr uint32_t DESC_LO_T16 = (uint32_t)(KG_BYTES >> 4) << 16;             //
 __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
 // the MMAs of one weight stage (tap, channel half): 4 k-steps x the rows of the pass the tap touches
-template <bool KMAJOR, int PASS, int TI>
+template <bool KMAJOR, int PASS, int TI, int K0, int K1>
 __device__ __forceinline__ void issue_stage(uint32_t a_lo, uint32_t b_lo, uint32_t tbase, uint32_t acc_first) {
     constexpr int tap = tap_at(PASS, TI), dy = tap / 3 - 1, dx = tap % 3 - 1;
     constexpr int r0 = PASS ? 3 : 0, r1 = PASS ? 5 : 3;
@@ -168,7 +176,7 @@ __device__ __forceinline__ void issue_stage(uint32_t a_lo, uint32_t b_lo, uint32
     // rows of the pass this tap touches: [ra, rb) (always a contiguous range)
     constexpr int ra = (r0 + dy < 0) ? r0 + 1 : r0, rb = (r1 - 1 + dy >= BROWS) ? r1 - 1 : r1;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = K0; k < K1; k++) {
         const uint64_t da = desc64(a_lo + (uint32_t)(k * 2), DESC_HI_SW128);
 #pragma unroll
         for (int r = ra; r < rb; r++) {
@@ -187,34 +195,50 @@ __device__ __forceinline__ void issue_stage(uint32_t a_lo, uint32_t b_lo, uint32
     }
 }
 
+// Two issuer warps (warp 1: even stages, warp 12: odd stages of the CTA's running stage count) take turns:
+// the MMA queue of the tensor pipe is shallow, so with ONE issuer the pipe drains during every barrier wait,
+// commit and loop step between stages (about a third of the time).  With two, warp B waits for the weights of
+// stage s+1 while warp A's MMAs of stage s execute, and starts issuing the moment A hands over (named barrier;
+// the hand-over comes after A's last MMA of the stage, so the A-operand collector groups never interleave).
+// tcgen05 operations of one CTA execute in issue order, so accumulation order and the commits' coverage are
+// those of the single-issuer sequence.
+__device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
 template <bool KMAJOR, int PASS, int TI>
 struct StageLoop {
-    // runs stages TI..8 of a pass for one channel half
+    // runs stages TI..8 of a pass for one channel half; each stage is issued by the warp whose parity matches
     template <class Ctx>
     static __device__ __forceinline__ void run(Ctx& c, int kh, int it, bool last_kh) {
         constexpr int tap = tap_at(PASS, TI);
         constexpr int r0 = PASS ? 3 : 0, r1 = PASS ? 5 : 3;
-        if (c.trace && c.nstage < 120) c.trace[16 + 3 * c.nstage] = clock64();
-        mbar_wait(c.bar0 + 8u * (B_WFULL + c.stage), c.ph, c.fault, 0x400 + c.stage);
-        if (TI == 0 && kh == 0) {       // first touch of the pass's accumulators for this tile: previous tenants must be drained
+        const bool mine = !c.dual || ((c.nstage & 1) == c.parity);
+        if (mine) {
+            if (c.trace && c.nstage < 600) c.trace[16 + 3 * c.nstage] = clock64();
+            mbar_wait(c.bar0 + 8u * (B_WFULL + c.stage), c.ph, c.fault, 0x400 + c.stage);
+            if (TI == 0 && kh == 0) {   // first touch of the pass's accumulators for this tile: previous tenants must be drained
 #pragma unroll
-            for (int r = r0; r < r1; r++) mbar_wait(c.bar0 + 8u * (B_TEMPTY + unit_of(r)), (use_of(r, it) & 1) ^ 1, c.fault, 0x500 + r);
-        }
-        tc_fence_after();
-        if (c.trace && c.nstage < 120) c.trace[16 + 3 * c.nstage + 1] = clock64();
-        if (elect_one()) {
-            const uint32_t a_lo = DESC_LO_SW128 | ((c.sW + c.stage * W_BYTES) >> 4);
-            const uint32_t b_lo = (KMAJOR ? DESC_LO_SW128 : DESC_LO_T16) | ((c.sX + (uint32_t)kh * KH_BYTES) >> 4);
-            if (!(c.dbg & 1)) issue_stage<KMAJOR, PASS, TI>(a_lo, b_lo, c.tbase, kh == 0 ? 0u : 1u);
-            umma_commit(c.bar0 + 8u * (B_WEMPTY + c.stage));      // frees the weight stage when these MMAs have read it
-            if (last_kh) {
-#pragma unroll
-                for (int r = r0; r < r1; r++)
-                    if (tap == last_tap_of(r)) umma_commit(c.bar0 + 8u * (B_TFULL + unit_of(r)));
+                for (int r = r0; r < r1; r++) mbar_wait(c.bar0 + 8u * (B_TEMPTY + unit_of(r)), (use_of(r, it) & 1) ^ 1, c.fault, 0x500 + r);
             }
+            if (c.dual && c.nstage > 0) named_bar_sync(c.parity ? 1 : 2);   // the other issuer has issued stage nstage-1
+            tc_fence_after();
+            if (c.trace && c.nstage < 600) c.trace[16 + 3 * c.nstage + 1] = clock64();
+            if (elect_one()) {
+                const uint32_t a_lo = DESC_LO_SW128 | ((c.sW + c.stage * W_BYTES) >> 4);
+                const uint32_t b_lo = (KMAJOR ? DESC_LO_SW128 : DESC_LO_T16) | ((c.sX + (uint32_t)kh * KH_BYTES) >> 4);
+                if (!(c.dbg & 1)) issue_stage<KMAJOR, PASS, TI, 0, 4>(a_lo, b_lo, c.tbase, kh == 0 ? 0u : 1u);
+                umma_commit(c.bar0 + 8u * (B_WEMPTY + c.stage));      // frees the weight stage when these MMAs have read it
+                if (last_kh) {
+#pragma unroll
+                    for (int r = r0; r < r1; r++)
+                        if (tap == last_tap_of(r)) umma_commit(c.bar0 + 8u * (B_TFULL + unit_of(r)));
+                }
+                if (PASS == 1 && TI == 8) umma_commit(c.bar0 + 8u * (B_AEMPTY + kh));   // the tile's channel half is no longer read
+            }
+            __syncwarp();
+            if (c.dual) named_bar_arrive(c.parity ? 2 : 1);
+            if (c.trace && c.nstage < 600) c.trace[16 + 3 * c.nstage + 2] = clock64();
         }
-        __syncwarp();
-        if (c.trace && c.nstage < 120) c.trace[16 + 3 * c.nstage + 2] = clock64();
         c.nstage++;
         if (++c.stage == NSTAGE) { c.stage = 0; c.ph ^= 1; }
         if constexpr (TI < 8) StageLoop<KMAJOR, PASS, TI + 1>::run(c, kh, it, last_kh);
@@ -226,7 +250,9 @@ struct IssueCtx {
     unsigned int* fault;
     int dbg;
     unsigned long long* trace;   // null unless CTA 0 is being traced
-    int nstage;                  // running stage count (trace index)
+    int nstage;                  // running stage count of the CTA (trace index; parity = issuing warp)
+    int parity;                  // this warp issues the stages with nstage % 2 == parity
+    bool dual;                   // two issuer warps (false: this warp issues everything)
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
@@ -234,19 +260,28 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, unsigned int v) {
+    unsigned int old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
 }
-// spin until item `dep`'s output is complete (bounded like the mbarrier waits)
-__device__ __forceinline__ void wait_item_done(const unsigned int* sched, int dep, unsigned int* fault, unsigned int code) {
-    const unsigned int* f = sched + 1 + dep;
-    for (uint32_t it = 0; ld_acquire_gpu(f) < FLAG_DONE; ++it) {
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// take the next ready item: slot = head++; the slot is filled (item + 1) by the CTA that completes the item's input
+__device__ __forceinline__ int dequeue_item(unsigned int* sched, int n_items, unsigned int* fault) {
+    const unsigned int slot = atomicAdd(sched, 1u);
+    if (slot >= (unsigned int)n_items) return -1;
+    const unsigned int* q = sched + 2 + n_items + slot;
+    unsigned int v;
+    for (uint32_t it = 0; (v = ld_acquire_gpu(q)) == 0u; ++it) {
         __nanosleep(64);
         if (it > (1u << 22)) {
-            if (fault) { atomicExch(fault, code); __threadfence_system(); }
+            if (fault) { atomicExch(fault, 0xB00u); __threadfence_system(); }
             __trap();
         }
     }
+    return (int)v - 1;
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ Params P) {
@@ -263,8 +298,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
         for (int i = 0; i < NSTAGE; i++) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
         for (int i = 0; i < 2; i++) { mbar_init(bar(B_AFULL + i), 1); mbar_init(bar(B_AEMPTY + i), 1); }
         for (int i = 0; i < NUNIT; i++) { mbar_init(bar(B_TFULL + i), 1); mbar_init(bar(B_TEMPTY + i), 8); }
-        mbar_init(bar(B_DONE), 1);
-        for (int i = 0; i < 2; i++) { mbar_init(bar(B_QFULL + i), 1); mbar_init(bar(B_QEMPTY + i), N_CONSUMERS); }
+        mbar_init(bar(B_DONE), (P.dbg & 32) ? 1 : 2);
+        for (int i = 0; i < 2; i++) { mbar_init(bar(B_QFULL + i), 1); mbar_init(bar(B_QEMPTY + i), (P.dbg & 32) ? N_CONSUMERS - 1 : N_CONSUMERS); }
         mbar_init_fence();
     }
     if (warp == 3) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -273,6 +308,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
     tc_fence_after();
     const uint32_t tbase = *tmem_slot;
     if (warp == 0) HZ_TRACE(0);
+    if (warp == 0 && P.trace && blockIdx.x == 0 && lane == 0) P.trace[2] = globaltimer_ns();
 
     // every role walks the CTA's work items in the order the scheduler (warp 3) publishes them; -1 ends the walk.
     // NEXT_ITEM: whole-warp roles call it converged; single-lane roles call it from their one lane.
@@ -292,8 +328,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
             for (int k = 0;; k++) {
                 int item;
                 if (P.sched) {
-                    item = (int)atomicAdd(P.sched, 1u);
-                    if (item >= n_items) item = -1;
+                    item = dequeue_item(P.sched, n_items, P.fault);
                 } else {
                     item = k < per_cta * P.n_layers ? (k / per_cta) * P.n_tiles + (int)blockIdx.x + (k % per_cta) * (int)gridDim.x : -1;
                 }
@@ -319,7 +354,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                         for (int ti = 0; ti < 9; ti++, ns++) {
                             int tap = TAP_ORDER[pass][ti];
                             mbar_wait(bar(B_WEMPTY + stage), ph ^ 1, P.fault, 0x100 + stage);
-                            HZ_TRACE(400 + ns);
+                            if (ns < 600) HZ_TRACE(2000 + ns);
                             if (P.dbg & 4) mbar_arrive(bar(B_WFULL + stage));
                             else {
                                 mbar_expect_tx(bar(B_WFULL + stage), W_BYTES);
@@ -340,16 +375,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 if (item < 0) break;
                 const int l = item / P.n_tiles, tile = item - l * P.n_tiles;
                 const Layer& L = P.layers[l];
-                if (l > 0) {
-                    // the tile's input is the previous layer's output, possibly written by another CTA through the
-                    // generic proxy: acquire its completion flag, then order the async-proxy reads behind it
-                    wait_item_done(P.sched, item - P.n_tiles, P.fault, 0x800);
-                    fence_proxy_async();
-                }
+                // the tile's input is the previous layer's output, possibly written by another CTA through the generic
+                // proxy; the ready queue (acquired by the scheduler, handed over through the item barrier) makes it
+                // visible to this thread, the proxy fence orders the async-proxy reads behind that
+                if (l > 0) fence_proxy_async();
                 for (int kh = 0; kh < L.nkh; kh++, na++) {
                     mbar_wait(bar(B_AEMPTY + kh), ((kh ? cnt1 : cnt0) & 1u) ^ 1u, P.fault, 0x200 + kh);
                     if (kh) cnt1++; else cnt0++;
-                    HZ_TRACE(700 + na);
+                    if (na < 400) HZ_TRACE(3600 + na);
                     if (P.dbg & 8) { mbar_arrive(bar(B_AFULL + kh)); continue; }
                     mbar_expect_tx(bar(B_AFULL + kh), KH_BYTES);
                     const uint8_t* src = P.buf[L.in_buf] + ((size_t)tile * L.nkh + kh) * KH_BYTES;
@@ -358,35 +391,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 }
             }
         }
-    } else if (warp == 1) {
-        // ---- MMA issuer: the whole warp runs the loop, one elected lane issues ----
-        IssueCtx c{sBar, sW, sX, tbase, 0u, 0u, P.fault, P.dbg, (blockIdx.x == 0 && lane == 0) ? P.trace : nullptr, 0};
-        uint32_t cnt0 = 0, cnt1 = 0;
-        int wi = 0, k = 0;                 // wi: work items done (phase of the accumulator units)
-        for (;; wi++) {
-            int item;
-            HZ_NEXT_ITEM(k, item, true);
-            if (item < 0) break;
-            const Layer& L = P.layers[item / P.n_tiles];
-            const int nkh = L.nkh;
-            const bool kmajor = L.kmajor != 0;
-            for (int kh = 0; kh < nkh; kh++) {
-                mbar_wait(bar(B_AFULL + kh), (kh ? cnt1 : cnt0) & 1u, P.fault, 0x300 + kh);
-                if (kmajor) StageLoop<true, 0, 0>::run(c, kh, wi, kh == nkh - 1);
-                else StageLoop<false, 0, 0>::run(c, kh, wi, kh == nkh - 1);
+    } else if (warp == 1 || warp == 12) {
+        // ---- MMA issuers: the whole warp runs the loop, one elected lane issues its stages ----
+        const bool dual = !(P.dbg & 32);
+        if (warp == 12 && !dual) {
+            // single-issuer mode (profiling A/B): nothing to do
+        } else {
+            IssueCtx c{sBar, sW, sX, tbase, 0u, 0u, P.fault, P.dbg, (blockIdx.x == 0 && lane == 0) ? P.trace : nullptr, 0, warp == 12 ? 1 : 0, dual};
+            uint32_t cnt0 = 0, cnt1 = 0;
+            int wi = 0, k = 0;                 // wi: work items done (phase of the accumulator units)
+            for (;; wi++) {
+                int item;
+                HZ_NEXT_ITEM(k, item, true);
+                if (item < 0) break;
+                const Layer& L = P.layers[item / P.n_tiles];
+                const int nkh = L.nkh;
+                const bool kmajor = L.kmajor != 0;
+                for (int kh = 0; kh < nkh; kh++) {
+                    mbar_wait(bar(B_AFULL + kh), (kh ? cnt1 : cnt0) & 1u, P.fault, 0x300 + kh);   // both issuers observe the tile half
+                    if (kh) cnt1++; else cnt0++;
+                    if (kmajor) StageLoop<true, 0, 0>::run(c, kh, wi, kh == nkh - 1);
+                    else StageLoop<false, 0, 0>::run(c, kh, wi, kh == nkh - 1);
+                }
+                for (int kh = 0; kh < nkh; kh++) {
+                    if (kmajor) StageLoop<true, 1, 0>::run(c, kh, wi, kh == nkh - 1);
+                    else StageLoop<false, 1, 0>::run(c, kh, wi, kh == nkh - 1);
+                }
             }
-            for (int kh = 0; kh < nkh; kh++) {
-                if (kmajor) StageLoop<true, 1, 0>::run(c, kh, wi, kh == nkh - 1);
-                else StageLoop<false, 1, 0>::run(c, kh, wi, kh == nkh - 1);
-                if (elect_one()) umma_commit(bar(B_AEMPTY + kh));   // the tile's channel half is no longer read
-                __syncwarp();
-                if (kh) cnt1++; else cnt0++;
-            }
+            // the last hand-over has no taker yet: the warp whose turn would be next consumes it
+            if (dual && c.nstage > 0 && (c.nstage & 1) == c.parity) named_bar_sync(c.parity ? 1 : 2);
+            if (elect_one()) umma_commit(bar(B_DONE));
+            __syncwarp();
+            mbar_wait(bar(B_DONE), 0, P.fault, 0x600);
         }
-        if (elect_one()) umma_commit(bar(B_DONE));
-        __syncwarp();
-        mbar_wait(bar(B_DONE), 0, P.fault, 0x600);
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 12) {
         // ---- epilogue: 8 warps.  thread = output channel c (TMEM lane); warps 4-7 take cells x = 0..3
         // of a board row, warps 8-11 cells x = 4..6.  One TMEM load = the 16 boards of a cell = 2 x 16
         // contiguous bytes of channel c's row in the T16 image (vector stores, vector residual loads).
@@ -408,10 +446,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
             const uint8_t* resb = (L.res_buf >= 0 && mem) ? P.buf[L.res_buf] : nullptr;
             uint8_t* yb = P.buf[L.out_buf];
             const bool relu = L.relu != 0;
-            // the residual (the block input, two layers back) may have been written by another CTA: observing the
-            // previous layer's completion flag makes the whole chain of this tile's earlier outputs visible
-            if (l > 0 && lane == 0) wait_item_done(P.sched, item - P.n_tiles, P.fault, 0x810);
-            __syncwarp();
+            // (the residual — the block input, two layers back, possibly written by another CTA — is visible: every hand-over
+            // of this tile went through a gpu-scope release/acquire of the ready queue and this CTA's item barrier)
             const size_t tile_off = (size_t)tile * 2 * KH_BYTES + chan_off;
             for (int ri = 0; ri < BROWS; ri++, nrow++) {
                 const int r = EPI_ORDER[ri], unit = unit_of(r);
@@ -427,10 +463,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                             rv[2 * j + 1] = *reinterpret_cast<const uint4*>(rp + 128);
                         }
                 }
-                if (warp == 4) HZ_TRACE(600 + 4 * nrow);
+                if (warp == 4 && nrow < 200) HZ_TRACE(2700 + 4 * nrow);
                 mbar_wait(bar(B_TFULL + unit), use_of(r, wi) & 1, P.fault, 0x700 + unit);
                 tc_fence_after();
-                if (warp == 4) HZ_TRACE(600 + 4 * nrow + 1);
+                if (warp == 4 && nrow < 200) HZ_TRACE(2700 + 4 * nrow + 1);
                 uint32_t v[4][16];
                 const uint32_t ta = tbase + ((uint32_t)(q * 32) << 16) + unit * UNIT_COLS + x0 * G;
                 tmem_ld16(ta, v[0]);
@@ -441,7 +477,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(B_TEMPTY + unit));      // the accumulator may be overwritten from here on
-                if (warp == 4) HZ_TRACE(600 + 4 * nrow + 2);
+                if (warp == 4 && nrow < 200) HZ_TRACE(2700 + 4 * nrow + 2);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     if (j == 3 && half) break;
@@ -469,14 +505,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                     *reinterpret_cast<uint4*>(yp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     *reinterpret_cast<uint4*>(yp + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 }
-                if (warp == 4) HZ_TRACE(600 + 4 * nrow + 3);
+                if (warp == 4 && nrow < 200) HZ_TRACE(2700 + 4 * nrow + 3);
             }
             if (P.sched && l + 1 < P.n_layers) {
                 // publish the tile's output: generic-proxy stores -> visible at gpu scope and to async-proxy readers
                 __threadfence();
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) red_release_gpu_add(P.sched + 1 + item, 1u);
+                if (lane == 0 && atom_add_acq_rel_gpu(P.sched + 2 + item, 1u) == FLAG_DONE - 1) {
+                    // last of the 8 epilogue warps: the tile's next layer becomes ready
+                    const unsigned int slot = atomicAdd(P.sched + 1, 1u);
+                    st_release_gpu(P.sched + 2 + n_items + slot, (unsigned int)(item + P.n_tiles) + 1u);
+                }
             }
         }
     }
@@ -484,7 +524,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
     tc_fence_before();
     __syncthreads();
     if (warp == 0) HZ_TRACE(1);
+    if (warp == 0 && P.trace && blockIdx.x == 0 && lane == 0) P.trace[3] = globaltimer_ns();
     if (warp == 3) tmem_dealloc(tbase, 512);
+}
+
+// ready queue before the launch: head 0, tail n_tiles, no completions, the stem items in slots 0..n_tiles-1
+__global__ void k_sched_init(unsigned int* sched, int n_tiles, int n_items) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 + 2 * n_items; i += gridDim.x * blockDim.x) {
+        unsigned int v = 0u;
+        if (i == 1) v = (unsigned int)n_tiles;
+        else if (i >= 2 + n_items && i < 2 + n_items + n_tiles) v = (unsigned int)(i - (2 + n_items)) + 1u;
+        sched[i] = v;
+    }
 }
 
 // ---- layout conversion (interop with NHWC tensors: tests, the heads kernel) -----------------------
@@ -587,8 +638,8 @@ int hz_tower_set_debug(int flags) {
     return HZ_OK;
 }
 
-int hz_tower_set_trace(unsigned long long* device_buffer_1024) {
-    hz::tower::g_trace = device_buffer_1024;
+int hz_tower_set_trace(unsigned long long* device_buffer_4096) {
+    hz::tower::g_trace = device_buffer_4096;
     return HZ_OK;
 }
 
@@ -640,7 +691,7 @@ int hz_tower_conv3x3(const void* x_tiles, int in_channel_halves, int in_kmajor, 
 size_t hz_tower_sched_bytes(int64_t n_boards, int n_blocks) {
     if (n_boards <= 0 || n_blocks < 0) return 0;
     int64_t tiles = (n_boards + hz::tower::G - 1) / hz::tower::G;
-    return sizeof(unsigned int) * (size_t)(1 + (1 + 2 * n_blocks) * tiles);
+    return sizeof(unsigned int) * (size_t)(2 + 2 * (1 + 2 * n_blocks) * tiles);
 }
 
 int hz_tower_forward(const void* x0_tiles, const void* const* w_tiles, const float* const* biases, int n_blocks, void* buf_a,
@@ -677,10 +728,10 @@ int hz_tower_forward(const void* x0_tiles, const void* const* w_tiles, const flo
     P.dbg = g_debug;
     P.trace = g_trace;
     if (out_tiles) *out_tiles = P.buf[cur];
-    cudaError_t e = cudaMemsetAsync(sched, 0, hz_tower_sched_bytes(n_boards, n_blocks), (cudaStream_t)stream);
-    if (e != cudaSuccess) return hz_record_launch(0, e);
+    const int n_items = P.n_layers * P.n_tiles;
+    k_sched_init<<<(2 + 2 * n_items + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P.sched, P.n_tiles, n_items);
     k_tower<<<grid_for(P.n_tiles), NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(P);
-    return hz_launched(1);
+    return hz_launched(2);
 }
 
 }  // extern "C"

@@ -338,12 +338,13 @@ size_t hz_tower_tile_bytes(int64_t n_boards, int channel_halves);
 int hz_tower_set_max_ctas(int max_ctas);
 /* Profiling switches of hz_tower_conv3x3 (0 = normal operation; results are WRONG otherwise):
  * 1 skip the MMAs, 2 skip the epilogue's memory traffic, 4 skip the weight copies, 8 skip the
- * activation copies.  Used by profiles/tower_bench.py to attribute the kernel's time. */
+ * activation copies; 32 = one MMA issuer warp instead of two (results stay right: A/B switch).
+ * Used by profiles/tower_bench.py to attribute the kernel's time. */
 int hz_tower_set_debug(int flags);
-/* Profiling: a device buffer of 1024 uint64 (or NULL to switch off) into which CTA 0 of every
+/* Profiling: a device buffer of 4096 uint64 (or NULL to switch off) into which CTA 0 of every
  * following hz_tower_conv3x3 launch writes SM-clock timestamps of its producer / MMA / epilogue
  * roles (slot map in csrc/hz_tower.cu). */
-int hz_tower_set_trace(unsigned long long *device_buffer_1024);
+int hz_tower_set_trace(unsigned long long *device_buffer_4096);
 
 /* NHWC bf16 [n,35,channels] -> tiles.  kmajor != 0: T16K (channels % 8 == 0, <= 64; missing
  * channels zero); kmajor == 0: T16 (channels must be 128).  Boards that pad n up to a multiple
@@ -366,11 +367,12 @@ int hz_tower_conv3x3(const void *x_tiles, int in_channel_halves, int in_kmajor, 
  * w_tiles / biases: HOST arrays of 1 + 2*n_blocks DEVICE pointers (weight tiles as above, fp32
  * bias[128]).  buf_a/b/c: three T16 scratch buffers of hz_tower_tile_bytes(n_boards, 2) bytes;
  * *out_tiles receives the one that holds the result (buf_a or buf_c).  sched: device scratch of
- * hz_tower_sched_bytes() bytes (zeroed by the call on `stream`).
- * Boards are independent, so work item (layer l, tile t) depends on (l-1, t) only: the CTAs draw
- * the (1 + 2*n_blocks) * n_boards/16 items from a global counter in order and publish each
- * tile's completion through `sched` — no grid-wide synchronisation, and the load balances to
- * within one item per CTA whatever the tile count. */
+ * hz_tower_sched_bytes() bytes (initialised by the call on `stream`).
+ * Boards are independent, so work item (layer l, tile t) depends on (l-1, t) only: the CTAs take
+ * the (1 + 2*n_blocks) * n_boards/16 items from a ready queue in `sched` that starts with the
+ * stem items and to which the completion of (l, t) appends (l+1, t) — no grid-wide
+ * synchronisation, no dependency stalls, and the load balances to within one item per CTA
+ * whatever the tile count. */
 size_t hz_tower_sched_bytes(int64_t n_boards, int n_blocks);
 int hz_tower_forward(const void *x0_tiles, const void *const *w_tiles, const float *const *biases,
                      int n_blocks, void *buf_a, void *buf_b, void *buf_c, void *sched,

@@ -74,27 +74,36 @@ def main():
         attr[name] = timeit(lambda: ht.conv(buf["a"], 2, c2, buf["b"], buf["c"], n_pad), a.iters)["us_min"]
     ht.lib.hz_tower_set_debug(0)
     out["hand_conv_attribution_us"] = attr
-    # role timeline of CTA 0 (SM clocks): where does a tile's time go?
-    tr = torch.zeros(1024, dtype=torch.int64, device="cuda")
-    ht.lib.hz_tower_set_trace(tr.data_ptr())
-    ht.conv(buf["a"], 2, c2, buf["b"], buf["c"], n_pad)
-    torch.cuda.synchronize()
-    ht.lib.hz_tower_set_trace(None)
-    t = tr.cpu().numpy().astype("int64")
-    t0 = int(t[0])
-    rel = lambda v: int(v - t0) if v else None  # noqa: E731
-    stages = [(rel(t[16 + 3 * i]), rel(t[16 + 3 * i + 1]), rel(t[16 + 3 * i + 2])) for i in range(72) if t[16 + 3 * i]]
-    out["trace"] = {
-        "total_cycles": rel(t[1]),
-        "mma_stage(before_wait,after_wait,after_issue)": stages,
-        "weight_issue": [rel(t[400 + i]) for i in range(72) if t[400 + i]],
-        "act_issue": [rel(t[700 + i]) for i in range(4) if t[700 + i]],
-        "epilogue_rows(before_wait,after_wait,after_tmem_ld,after_stores)": [tuple(rel(t[600 + 4 * j + k]) for k in range(4)) for j in range(10) if t[600 + 4 * j]],
-    }
-    waits = [b - a for a, b, _ in stages]
-    issues = [c - b for _, b, c in stages]
-    out["trace_summary"] = {"mma_wait_cycles_total": sum(waits), "mma_issue_cycles_total": sum(issues),
-                            "mma_wait_max": max(waits) if waits else None}
+    # role timeline of CTA 0 (SM clocks) for the fused all-layers launch
+    def trace_run(fn, n_stage=600, n_rows=200):
+        tr = torch.zeros(4096, dtype=torch.int64, device="cuda")
+        ht.lib.hz_tower_set_trace(tr.data_ptr())
+        fn()
+        torch.cuda.synchronize()
+        ht.lib.hz_tower_set_trace(None)
+        t = tr.cpu().numpy().astype("int64")
+        t0 = int(t[0])
+        rel = lambda v: int(v - t0) if v else None  # noqa: E731
+        stages = [(rel(t[16 + 3 * i]), rel(t[16 + 3 * i + 1]), rel(t[16 + 3 * i + 2])) for i in range(n_stage) if t[16 + 3 * i + 2]]
+        rows = [tuple(rel(t[2700 + 4 * j + k]) for k in range(4)) for j in range(n_rows) if t[2700 + 4 * j + 3]]
+        waits = [b - a for a, b, _ in stages]
+        issues = [c - b for _, b, c in stages]
+        cyc, ns = rel(t[1]), int(t[3] - t[2])
+        return {"total_cycles": cyc, "total_ns": ns, "sm_ghz": cyc / ns if ns else None, "n_stages": len(stages),
+                "mma_wait_cycles_total": sum(waits), "mma_issue_cycles_total": sum(issues), "mma_wait_max": max(waits) if waits else None,
+                "stage_period_avg": (stages[-1][2] - stages[0][0]) / len(stages) if stages else None,
+                "stages(before_wait,after_wait,after_issue)": stages, "weight_issue": [rel(t[2000 + i]) for i in range(n_stage) if t[2000 + i]],
+                "act_issue": [rel(t[3600 + i]) for i in range(64) if t[3600 + i]],
+                "epilogue_rows(before_wait,after_wait,after_tmem_ld,after_stores)": rows,
+                "epilogue_wait_total": sum(r[1] - r[0] for r in rows), "epilogue_work_total": sum(r[3] - r[1] for r in rows)}
+
+    x0t = hand.hand.x0_buffer(B)
+    hand.hand.to_tiles(board, 40, True, x0t)
+    out["trace_fused"] = trace_run(lambda: hand.hand.forward_tiles(x0t, B))
+    ht.lib.hz_tower_set_debug(14)
+    out["trace_fused_mma_only"] = trace_run(lambda: hand.hand.forward_tiles(x0t, B))
+    ht.lib.hz_tower_set_debug(0)
+    out["trace_summary"] = {k: {kk: vv for kk, vv in out[k].items() if not isinstance(vv, list)} for k in ("trace_fused", "trace_fused_mma_only")}
     hand.tower_out(board)
     x = lib.tower_out(board)
     r = timeit(lambda: lib._conv_relu(x, lib.blocks[0][1], 1, residual=x), a.iters, flush)
@@ -135,7 +144,7 @@ def main():
     x0 = hand.hand.x0_buffer(B)
     hand.hand.to_tiles(board, 40, True, x0)
     fa = {}
-    for flags, name in ((0, "full"), (4, "no_weight_copies"), (8, "no_act_copies"), (2, "no_epilogue_mem"), (12, "no_copies"), (14, "mma_only"), (1, "no_mma")):
+    for flags, name in ((0, "full"), (4, "no_weight_copies"), (8, "no_act_copies"), (2, "no_epilogue_mem"), (12, "no_copies"), (14, "mma_only"), (1, "no_mma"), (32, "single_issuer")):
         ht.lib.hz_tower_set_debug(flags)
         fa[name] = timeit(lambda: hand.hand.forward_tiles(x0, B), a.iters)["us_min"]
     ht.lib.hz_tower_set_debug(0)
