@@ -142,6 +142,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
 #define HZ_TOWER_COLLECTOR 1
 #endif
 
+
 // ---- MMA issue, fully unrolled -------------------------------------------------------------------
 // One thread issues ~312 MMAs of ~50 tensor-core cycles each per tile, so the issue path has to be
 // a handful of instructions per MMA: the whole warp runs the (warp-uniform) control flow, taps /
@@ -220,13 +221,21 @@ struct StageLoop {
 #pragma unroll
                 for (int r = r0; r < r1; r++) mbar_wait(c.bar0 + 8u * (B_TEMPTY + unit_of(r)), (use_of(r, it) & 1) ^ 1, c.fault, 0x500 + r);
             }
-            if (c.dual && c.nstage > 0) named_bar_sync(c.parity ? 1 : 2);   // the other issuer has issued stage nstage-1
+            // everything the first MMA needs is computed before the hand-over is awaited
+            const bool lead = elect_one();
+            const uint32_t a_lo = DESC_LO_SW128 | ((c.sW + c.stage * W_BYTES) >> 4);
+            const uint32_t b_lo = (KMAJOR ? DESC_LO_SW128 : DESC_LO_T16) | ((c.sX + (uint32_t)kh * KH_BYTES) >> 4);
+            const uint32_t acc0 = kh == 0 ? 0u : 1u;
+            if (c.dual && c.nstage > 0) named_bar_sync(c.parity ? 1 : 2);   // the other issuer has handed over
             tc_fence_after();
             if (c.trace && c.nstage < 600) c.trace[16 + 3 * c.nstage + 1] = clock64();
-            if (elect_one()) {
-                const uint32_t a_lo = DESC_LO_SW128 | ((c.sW + c.stage * W_BYTES) >> 4);
-                const uint32_t b_lo = (KMAJOR ? DESC_LO_SW128 : DESC_LO_T16) | ((c.sX + (uint32_t)kh * KH_BYTES) >> 4);
-                if (!(c.dbg & 1)) issue_stage<KMAJOR, PASS, TI, 0, 4>(a_lo, b_lo, c.tbase, kh == 0 ? 0u : 1u);
+            // (handing over BEFORE the last k-step, with that step issued without collector hints, was measured: the
+            // interleaved MMAs corrupt the other issuer's collector group — results differ — so the hand-over stays behind
+            // the last MMA; the commits, which only track this thread's own MMAs, come after it)
+            if (lead && !(c.dbg & 1)) issue_stage<KMAJOR, PASS, TI, 0, 4>(a_lo, b_lo, c.tbase, acc0);
+            __syncwarp();
+            if (c.dual) named_bar_arrive(c.parity ? 2 : 1);
+            if (lead) {
                 umma_commit(c.bar0 + 8u * (B_WEMPTY + c.stage));      // frees the weight stage when these MMAs have read it
                 if (last_kh) {
 #pragma unroll
@@ -236,7 +245,6 @@ struct StageLoop {
                 if (PASS == 1 && TI == 8) umma_commit(c.bar0 + 8u * (B_AEMPTY + kh));   // the tile's channel half is no longer read
             }
             __syncwarp();
-            if (c.dual) named_bar_arrive(c.parity ? 2 : 1);
             if (c.trace && c.nstage < 600) c.trace[16 + 3 * c.nstage + 2] = clock64();
         }
         c.nstage++;

@@ -13,7 +13,7 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo, uint32
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
 }
 
-template <int MODE>   // 0: plain, 1: collector fill/use/lastuse in groups of 3, 2: groups of 3 with the same A but no hints
+template <int MODE>   // 0: a different A per MMA, 1: collector fill/use/lastuse in groups of 3, 2: groups of 3 with the same A, no hints
 __global__ void __launch_bounds__(128, 1) rate(int N, int bmn, long long* out) {
     extern __shared__ uint8_t raw[];
     uint8_t* sm = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
@@ -29,27 +29,39 @@ __global__ void __launch_bounds__(128, 1) rate(int N, int bmn, long long* out) {
     __syncthreads();
     tc_fence_after();
     uint32_t tb = slot;
-    if (threadIdx.x == 0) {
-        uint32_t idesc = idesc_bf16_f32(128, N) | (bmn ? (1u << 16) : 0u);
-        uint32_t sA = smem_u32(sm), sB = smem_u32(sm + 64 * 1024);
+    if (warp == 0) {
+        const uint32_t idesc = idesc_bf16_f32(128, N) | (bmn ? (1u << 16) : 0u);
+        const uint32_t sA = smem_u32(sm), sB = smem_u32(sm + 64 * 1024);
+        const uint32_t a_lo = (1u << 16) | (sA >> 4);
+        const uint32_t a_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t b_lo = bmn ? (((8960u >> 4) << 16) | (sB >> 4)) : ((1u << 16) | (sB >> 4));
+        const uint32_t b_hi = bmn ? ((128u >> 4) | (1u << 14)) : a_hi;
+        const uint32_t ncol = N > 128 ? 256u : 128u;              // accumulator slots of this width
         long long t0 = clock64();
-        for (int it = 0; it < 512; it++) {
-            int grp = it / 3, r = it % 3;
-            uint32_t aoff = (MODE == 0 ? (it & 15) : (grp & 15)) * 4096 + (it & 3) * 0;   // a different 128x16 weight slice per MMA / per group
-            uint64_t da = smem_desc_sw128(sA + (aoff & 0xFFFF));
-            uint32_t boff = (uint32_t)((it % 5) * 7 * 16) * (bmn ? 16 : 128);
-            uint64_t db = bmn ? desc_mn(sB + boff, 8960, 128) : smem_desc_sw128(sB + boff);
-            uint32_t d = tb + (it & 3) * 128;
-            if (MODE == 1) {
-                if (r == 0) umma_bf16_coll<COLL_FILL>(d, da, db, idesc, 1);
-                else if (r == 1) umma_bf16_coll<COLL_USE>(d, da, db, idesc, 1);
-                else umma_bf16_coll<COLL_LASTUSE>(d, da, db, idesc, 1);
-            } else umma_bf16(d, da, db, idesc, 1);
+        uint32_t pred;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+        if (pred) {
+#pragma unroll 1
+            for (int it = 0; it < 32; it++) {
+#pragma unroll
+                for (int j = 0; j < 12; j++) {       // 4 "k-steps" x 3 "rows", like one weight stage of the tower
+                    const int kk = j / 3, r = j % 3;
+                    const uint64_t da = ((uint64_t)a_hi << 32) | (a_lo + (uint32_t)((MODE == 0 ? j : kk) * 256));   // 4 KB apart
+                    const uint64_t db = ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)(r * (bmn ? 112 : 896)));
+                    const uint32_t d = tb + (uint32_t)(r * ncol) % 512u;
+                    if (MODE == 1) {
+                        if (r == 0) umma_bf16_coll<COLL_FILL>(d, da, db, idesc, 1);
+                        else if (r == 1) umma_bf16_coll<COLL_USE>(d, da, db, idesc, 1);
+                        else umma_bf16_coll<COLL_LASTUSE>(d, da, db, idesc, 1);
+                    } else umma_bf16(d, da, db, idesc, 1);
+                }
+            }
+            umma_commit(smem_u32(&bar));
         }
-        umma_commit(smem_u32(&bar));
+        __syncwarp();
         mbar_wait(smem_u32(&bar), 0, nullptr, 0);
         long long t1 = clock64();
-        if (blockIdx.x == 0) out[0] = t1 - t0;
+        if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = t1 - t0;
     }
     tc_fence_before();
     __syncthreads();
@@ -63,7 +75,7 @@ int main() {
     cudaFuncSetAttribute(rate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(rate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(rate<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    int Ns[] = {64, 96, 112, 128, 192, 224, 256};
+    int Ns[] = {32, 64, 80, 96, 112, 128, 160, 192, 208, 224, 240, 256};
     for (int bmn = 0; bmn < 2; bmn++)
         for (int N : Ns)
             for (int mode = 0; mode < 3; mode++) {
@@ -77,7 +89,7 @@ int main() {
                     if (h < best) best = h;
                 }
                 printf("B %s N=%3d %-28s: %6.1f cycles/MMA (tensor floor N/2 = %d)\n", bmn ? "MN-major/none " : "K-major/SW128 ", N,
-                       mode == 0 ? "A re-read per MMA" : mode == 1 ? "A collector (groups of 3)" : "same A x3, no hints", best / 512.0, N / 2);
+                       mode == 0 ? "A re-read per MMA" : mode == 1 ? "A collector (groups of 3)" : "same A x3, no hints", best / 384.0, N / 2);
             }
     return 0;
 }
