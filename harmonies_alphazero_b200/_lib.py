@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libharmonies_b200.so")
+# HZ_LIB_PATH selects another build of the same sources (profiles/run_bounds.sh: the -DHZ_DEBUG_BOUNDS library)
+LIB_PATH = os.environ.get("HZ_LIB_PATH") or os.path.join(HERE, "libharmonies_b200.so")
 
 # every symbol include/harmonies_b200.h declares: name -> (restype, argtypes)
 _vp, _i64, _u64, _i, _f, _d = C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_float, C.c_double

@@ -324,6 +324,36 @@ class HostPlayout:
                 raise TypeError(f"inputs {in_dtype}{list(in_shape)}, outputs int32{list(out_shape)}")
 
     def _pipeline(self, ins, outs, depth, dev_in, dev_out, launch):
+        """The pipelined stream of batches.  A caller that streams through the SAME pinned buffers again
+        and again (the normal case: a ring of host buffers) gets the whole pipeline — every copy, kernel
+        and cross-stream dependency — replayed as ONE CUDA graph from the third call on (first call
+        eager, second call captured): the host then issues one launch per call instead of ~10 API calls
+        per batch, which is what keeps the end-to-end rate up when 8 ranks share one host's cores."""
+        key = (id(launch.__code__), depth, tuple(a.data_ptr() for a in ins), tuple(b.data_ptr() for b in outs),
+               tuple(t.data_ptr() for t in dev_in[:depth]))
+        graphs = self.__dict__.setdefault("_graphs", {})
+        g = graphs.get(key)
+        if g is not None and g is not False:
+            g.replay()
+            torch.cuda.current_stream(self.device).synchronize()
+            return outs
+        if g is False and self.use_graphs:          # second call with these buffers: capture
+            torch.cuda.synchronize(self.device)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                self._pipeline_body(ins, outs, depth, dev_in, dev_out, launch)
+            graphs[key] = gr
+            gr.replay()
+            torch.cuda.current_stream(self.device).synchronize()
+            return outs
+        graphs[key] = False
+        self._pipeline_body(ins, outs, depth, dev_in, dev_out, launch)
+        torch.cuda.current_stream(self.device).synchronize()
+        return outs
+
+    use_graphs = True
+
+    def _pipeline_body(self, ins, outs, depth, dev_in, dev_out, launch):
         if not hasattr(self, "copy_in"):
             self.copy_in, self.copy_out = torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)
         main = torch.cuda.current_stream(self.device)
@@ -354,7 +384,6 @@ class HostPlayout:
                 drained[slot].record(self.copy_out)
         main.wait_stream(self.copy_out)
         main.wait_stream(self.copy_in)
-        main.synchronize()
         return outs
 
 

@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "../../include/harmonies_b200.h"
+#include "hz_common.cuh"   // HZ_BOUND
 
 namespace hz {
 
@@ -276,6 +277,8 @@ template <int CAP, int OWNERS>
 __device__ __forceinline__ bool water_push(WaterQueue<CAP, OWNERS>* q, uint32_t comp, int owner) {
     int slot = atomicAdd(&q->count, 1);
     if (slot >= CAP) return false;                                    // full: the caller scores it in place
+    HZ_BOUND(slot, CAP, 401);
+    HZ_BOUND(owner, OWNERS, 402);
     q->comp[slot] = comp;
     q->owner[slot] = (uint16_t)owner;
     return true;

@@ -385,31 +385,39 @@ __global__ void __launch_bounds__(FTPB, 1) k_heads_p(const __nv_bfloat16* __rest
 }
 
 // ---- 1x1 head convolutions on the tower's T16 tiles (include/harmonies_b200.h) --------------------
-// One block per 16-board tile.  Thread = (8 consecutive positions, one quarter of the channels): a
-// 16-byte load is 8 positions of one channel, so the loads are coalesced without any transpose; the
-// four channel quarters meet in shared memory.  fp32 weights, fp32 accumulation.
-constexpr int HCT = 320;
+// One block per 16-board tile.  Thread = (8 consecutive positions, one eighth of the channels): a
+// 16-byte load is 8 positions of one channel, so the loads need no transpose; a thread issues its 16
+// loads back to back (the kernel is a 37 MB read: latency, not arithmetic), and the eight channel
+// groups of a position group sit in adjacent lanes and meet by shuffles.  fp32 weights and sums.
+constexpr int HCT = 576;                  // 70 position groups x 8 channel groups = 560 working threads
 __global__ void __launch_bounds__(HCT) k_head_conv_t16(const uint8_t* __restrict__ tiles, int64_t n, const float* __restrict__ w_conv,
                                                        const float* __restrict__ b_conv, float* __restrict__ hc) {
     __shared__ float s_w[3 * 128];
-    __shared__ float s_part[4][3][560];
     const int t = threadIdx.x;
     for (int i = t; i < 3 * 128; i += HCT) s_w[i] = w_conv[i];
-    __syncthreads();
     const int64_t tile = blockIdx.x;
     const uint8_t* base = tiles + tile * (size_t)(2 * 71680);
-    if (t < 280) {
-        const int pg = t % 70, cq = t / 70;
-        float acc[3][8];
+    const int cq = t & 7, pg = t >> 3;
+    const bool live = pg < 70;
+    uint4 q[16];
+    if (live) {
 #pragma unroll
-        for (int j = 0; j < 3; j++)
+        for (int ci = 0; ci < 16; ci++) {
+            const int c = cq * 16 + ci;
+            q[ci] = *reinterpret_cast<const uint4*>(base + (size_t)(c >> 3) * 8960 + pg * 128 + (c & 7) * 16);
+        }
+    }
+    __syncthreads();
+    float acc[3][8];
 #pragma unroll
-            for (int e = 0; e < 8; e++) acc[j][e] = 0.0f;
-#pragma unroll 8
-        for (int ci = 0; ci < 32; ci++) {
-            const int c = cq * 32 + ci;
-            const uint4 q = *reinterpret_cast<const uint4*>(base + (size_t)(c >> 3) * 8960 + pg * 128 + (c & 7) * 16);
-            const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc[j][e] = 0.0f;
+    if (live) {
+#pragma unroll
+        for (int ci = 0; ci < 16; ci++) {
+            const int c = cq * 16 + ci;
+            const uint32_t qw[4] = {q[ci].x, q[ci].y, q[ci].z, q[ci].w};
             const float w0 = s_w[c], w1 = s_w[128 + c], w2 = s_w[256 + c];
 #pragma unroll
             for (int h = 0; h < 4; h++) {
@@ -419,19 +427,26 @@ __global__ void __launch_bounds__(HCT) k_head_conv_t16(const uint8_t* __restrict
                 acc[2][2 * h] = fmaf(w2, lo, acc[2][2 * h]); acc[2][2 * h + 1] = fmaf(w2, hi, acc[2][2 * h + 1]);
             }
         }
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-#pragma unroll
-            for (int e = 0; e < 8; e++) s_part[cq][j][pg * 8 + e] = acc[j][e];
     }
-    __syncthreads();
-    for (int i = t; i < 3 * 560; i += HCT) {
-        const int j = i / 560, p = i - 560 * j;
-        const int cell = p >> 4;
-        const int64_t board = tile * 16 + (p & 15);
-        if (board < n) {
-            float v = ((s_part[0][j][p] + s_part[1][j][p]) + (s_part[2][j][p] + s_part[3][j][p])) + b_conv[j];
-            hc[board * (3 * CELLS) + j * CELLS + cell] = fmaxf(v, 0.0f);
+    // the 8 channel groups of a position group are lanes 8k..8k+7: butterfly over the low 3 lane bits
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            float v = acc[j][e];
+            v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+            v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+            v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+            acc[j][e] = v;
+        }
+    if (live && cq < 3) {                 // lane cq writes output channel cq of its 8 positions
+        const int cell = pg >> 1;
+        const float bias = b_conv[cq];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int64_t board = tile * 16 + (pg & 1) * 8 + e;
+            const float v = (cq == 0 ? acc[0][e] : cq == 1 ? acc[1][e] : acc[2][e]) + bias;
+            if (board < n) hc[board * (3 * CELLS) + cq * CELLS + cell] = fmaxf(v, 0.0f);
         }
     }
 }

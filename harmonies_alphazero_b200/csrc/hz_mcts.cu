@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(TTPB) k_tree_select(hz_tree T, float cpuct, ui
                 int k = lane + 32 * r;
                 bool on = k < ne;
                 if (32 * r >= ne) { N[r] = 0; W[r] = 0.0; P[r] = 0.0f; C[r] = 0u; CI[r] = 0u; continue; }   // warp-uniform
+                if (on) HZ_BOUND(e0 + k, T.max_edges, 101);
                 N[r] = on ? v.edge_N[e0 + k] : 0;
                 W[r] = on ? v.edge_W[e0 + k] : 0.0;
                 P[r] = on ? v.edge_P[e0 + k] : 0.0f;
@@ -255,6 +256,8 @@ __global__ void __launch_bounds__(TTPB) k_tree_select(hz_tree T, float cpuct, ui
             if (best_k < 0) break;                                       // :125-133
             uint32_t e = e0 + (uint32_t)best_k;
             if (depth > T.max_sims) { if (lane == 0) T.status[t] |= 4; break; }
+            HZ_BOUND(depth, T.max_sims + 1, 102);
+            HZ_BOUND(e, T.max_edges, 103);
             if (lane == 0) {
                 path[depth] = e;
                 if (K > 1) v.edge_V[e] += 1;
@@ -263,6 +266,7 @@ __global__ void __launch_bounds__(TTPB) k_tree_select(hz_tree T, float cpuct, ui
             int br = best_k >> 5;                                        // warp-uniform
             uint32_t wc = br == 0 ? C[0] : br == 1 ? C[1] : C[2], wi = br == 0 ? CI[0] : br == 1 ? CI[1] : CI[2];
             node = (int)__shfl_sync(FULL, wc, best_k & 31);              // :145-146
+            HZ_BOUND(node, T.max_nodes, 104);
             uint32_t ci = __shfl_sync(FULL, wi, best_k & 31);
             if (ci == 0) {                                               // not known to be expanded: ask the node
                 ne = (int)(v.node_info[node] & 0xFFu);
@@ -301,11 +305,14 @@ __global__ void __launch_bounds__(TTPB) k_tree_select(hz_tree T, float cpuct, ui
 __device__ __forceinline__ int table_find(const hz_tree& T, const TreeView& v, uint64_t h, const uint32_t* key) {
     uint32_t mask = (uint32_t)T.table_size - 1u;
     uint32_t slot = (uint32_t)h & mask;
-    while (true) {
+    for (uint32_t probes = 0;; probes++) {
+        HZ_BOUND(slot, T.table_size, 201);
+        HZ_BOUND(probes, T.table_size, 202);      // an open-addressing table of 2x the nodes never fills
         uint32_t e = v.table[slot];
         uint64_t eh = v.table_hash[slot];     // independent of e: both loads are in flight together
         if (e == 0) return -1;
         int idx = (int)e - 1;
+        HZ_BOUND(idx, T.max_nodes, 203);
         if (eh == h) {
             if (!HZ_TREE_FULL_COMPARE) return idx;
             State o;
@@ -323,7 +330,11 @@ __device__ __forceinline__ int table_find(const hz_tree& T, const TreeView& v, u
 __device__ __forceinline__ void table_insert(const hz_tree& T, const TreeView& v, uint64_t h, int idx) {
     uint32_t mask = (uint32_t)T.table_size - 1u;
     uint32_t slot = (uint32_t)h & mask;
-    while (atomicCAS(&v.table[slot], 0u, (uint32_t)idx + 1u) != 0u) slot = (slot + 1) & mask;
+    HZ_BOUND(idx, T.max_nodes, 204);
+    for (uint32_t probes = 0; atomicCAS(&v.table[slot], 0u, (uint32_t)idx + 1u) != 0u; probes++) {
+        HZ_BOUND(probes, T.table_size, 205);
+        slot = (slot + 1) & mask;
+    }
     v.table_hash[slot] = h;     // read by later rounds only (after the __syncwarp that ends this one)
 }
 
@@ -346,6 +357,7 @@ __global__ void __launch_bounds__(TTPB, HZ_EXPAND_MIN_BLOCKS) k_tree_expand_back
     for (int j = 0; j < K; j++) {
     const size_t row = (size_t)t * K + j;
     int leaf = T.leaf[row], sim = sim0 + j;
+    HZ_BOUND(leaf, T.max_nodes, 306);
     // Everything that depends only on (tree, row, leaf) is requested up front, so that the logits,
     // the tree counters and the statistics of the path edges (back_fill does not depend on the
     // expansion) travel while the leaf state does: the kernel is a chain of dependent round trips.
@@ -445,6 +457,7 @@ __global__ void __launch_bounds__(TTPB, HZ_EXPAND_MIN_BLOCKS) k_tree_expand_back
             int id = found;
             if (is_new) {
                 id = n_nodes + __popc(new_mask & ((1u << lane) - 1u));
+                HZ_BOUND(id, T.max_nodes, 301);
                 store_state(cs, v.node_state, id);                   // Node(next_state), :203-204
                 v.node_hash[id] = h;
                 v.node_edge0[id] = 0;
@@ -458,6 +471,8 @@ __global__ void __launch_bounds__(TTPB, HZ_EXPAND_MIN_BLOCKS) k_tree_expand_back
             unsigned valid_mask = __ballot_sync(FULL, valid);
             if (valid) {                                             // Edge(...), :212-215
                 int e = e0 + n_new_edges + __popc(valid_mask & ((1u << lane) - 1u));
+                HZ_BOUND(e, T.max_edges, 302);
+                HZ_BOUND(a, HZ_ACTION_SIZE, 303);
                 float p = prow[a];
                 if (is_logits) p = expf(p - mx) * inv_sum;
                 if (mix) {
@@ -494,7 +509,9 @@ __global__ void __launch_bounds__(TTPB, HZ_EXPAND_MIN_BLOCKS) k_tree_expand_back
         if (K > 1) v.edge_V[pe] -= 1;                                // the in-flight visit has landed
     }
     for (int d = lane + 32; d < depth; d += 32) {
+        HZ_BOUND(d, T.max_sims + 1, 304);
         uint32_t e = path[d];
+        HZ_BOUND(e, T.max_edges, 305);
         int mover = v.edge_am[e] >> 8;
         double dir = mover == leaf_player ? 1.0 : -1.0;
         v.edge_N[e] += 1;

@@ -275,6 +275,16 @@ def test_host_buffer_api_equals_device_path(hb):
     assert acc == many_steps
     with pytest.raises(ValueError):
         api.run_keys_many(batches, outs[:3])
+    # the same buffer ring again with NEW contents: the second call captures the pipeline as a CUDA graph,
+    # the third replays it; results must follow the new keys every time
+    for rep in range(3):
+        for kb in batches:
+            kb.copy_(torch.from_numpy(rng.integers(-2**63, 2**63 - 1, size=n, dtype=np.int64)))
+        api.run_keys_many(batches, outs, depth=3)
+        for kb, ob in zip(batches, outs):
+            api.run_keys(kb, one)
+            assert torch.equal(one, ob), rep
+    assert any(g not in (None, False) for g in api._graphs.values())
     # full-record stream
     recs = [hb.init_states(n, seed=500 + k).cpu().pin_memory() for k in range(5)]
     routs = [torch.empty((n, 32), dtype=torch.int32).pin_memory() for _ in range(5)]
