@@ -35,6 +35,7 @@ SIGNATURES = {
     "hz_tree_create": (_i, [C.POINTER(_vp), _vp, C.c_size_t, _i, _i, _i, _i, _i]),
     "hz_tree_destroy": (_i, [_vp]),
     "hz_tree_reset": (_i, [_vp, _vp, _vp, _vp]),
+    "hz_tree_set_active": (_i, [_vp, _vp]),
     "hz_tree_select": (_i, [_vp, _f, _vp, _vp, _vp, _i, _i, _vp]),
     "hz_tree_expand_backup": (_i, [_vp, _vp, _vp, _i, _vp, _d, _vp]),
     "hz_tree_fake_eval": (_i, [_vp, _vp, _vp, _vp]),
@@ -45,6 +46,8 @@ SIGNATURES = {
     "hz_net_heads": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "hz_net_head_conv_t16": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "hz_net_heads_fc": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
+    "hz_net_head_conv_t16_active": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "hz_net_heads_fc_active": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "hz_tower_tile_bytes": (C.c_size_t, [_i64, _i]),
     "hz_tower_set_max_ctas": (_i, [_i]),
     "hz_tower_set_debug": (_i, [_i]),
@@ -53,6 +56,7 @@ SIGNATURES = {
     "hz_tower_from_tiles": (_i, [_vp, _vp, _i64, _vp]),
     "hz_tower_sched_bytes": (C.c_size_t, [_i64, _i]),
     "hz_tower_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "hz_tower_forward_active": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "hz_tower_conv3x3": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
 }
 
@@ -79,7 +83,7 @@ def load(path=None):
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype, fn.argtypes = res, args
-    if lib.hz_abi_version() != 4:
+    if lib.hz_abi_version() != 5:
         raise HarmoniesLibraryError("ABI version mismatch")
     if path is None:
         _lib = lib

@@ -219,8 +219,10 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 lo, __nv_bfloat16 hi
 // relu(conv + bias) as policy ch0 [35 cells], policy ch1 [35], value ch0 [35]; phase 1 is then a copy.
 __global__ void __launch_bounds__(FTPB, 1) k_heads_p(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ glob,
                                                      int64_t n, HeadParams P, float* __restrict__ logits,
-                                                     float* __restrict__ value, const float* __restrict__ hc) {
+                                                     float* __restrict__ value, const float* __restrict__ hc,
+                                                     const int* __restrict__ n_active) {
     extern __shared__ __align__(16) float smem[];
+    if (n_active) n = min(n, (int64_t)max(*n_active, 0));   // only the active prefix of the rows (hz_tree_set_active)
     float* s_wp = smem;                      // [112][143] (+ slack)
     float* s_wv = s_wp + WPN;                // [77][256]
     float* s_pin = s_wv + 77 * FH;           // [FG][112]
@@ -385,38 +387,41 @@ __global__ void __launch_bounds__(FTPB, 1) k_heads_p(const __nv_bfloat16* __rest
 }
 
 // ---- 1x1 head convolutions on the tower's T16 tiles (include/harmonies_b200.h) --------------------
-// One block per 16-board tile.  Thread = (8 consecutive positions, one eighth of the channels): a
-// 16-byte load is 8 positions of one channel, so the loads need no transpose; a thread issues its 16
-// loads back to back (the kernel is a 37 MB read: latency, not arithmetic), and the eight channel
-// groups of a position group sit in adjacent lanes and meet by shuffles.  fp32 weights and sums.
-constexpr int HCT = 576;                  // 70 position groups x 8 channel groups = 560 working threads
-__global__ void __launch_bounds__(HCT) k_head_conv_t16(const uint8_t* __restrict__ tiles, int64_t n, const float* __restrict__ w_conv,
-                                                       const float* __restrict__ b_conv, float* __restrict__ hc) {
+// One block per 16-board tile, all 256 tiles of a 4,096-leaf step resident at once (two blocks per SM).
+// Thread = (8 consecutive positions, one quarter of the channels): a 16-byte load is 8 positions of one
+// channel, so the loads need no transpose; a thread keeps 16 of them in flight (the kernel is a 37 MB
+// read: latency, not arithmetic); the four channel quarters of a position group are adjacent lanes and
+// meet by two shuffles.  fp32 weights and sums.
+constexpr int HCT = 288;                  // 70 position groups x 4 channel quarters = 280 working threads
+__global__ void __launch_bounds__(HCT, 2) k_head_conv_t16(const uint8_t* __restrict__ tiles, int64_t n, const float* __restrict__ w_conv,
+                                                          const float* __restrict__ b_conv, float* __restrict__ hc,
+                                                          const int* __restrict__ n_active) {
     __shared__ float s_w[3 * 128];
     const int t = threadIdx.x;
+    if (n_active) n = min(n, (int64_t)max(*n_active, 0));
+    if ((int64_t)blockIdx.x * 16 >= n) return;
     for (int i = t; i < 3 * 128; i += HCT) s_w[i] = w_conv[i];
+    __syncthreads();
     const int64_t tile = blockIdx.x;
     const uint8_t* base = tiles + tile * (size_t)(2 * 71680);
-    const int cq = t & 7, pg = t >> 3;
-    const bool live = pg < 70;
-    uint4 q[16];
-    if (live) {
-#pragma unroll
-        for (int ci = 0; ci < 16; ci++) {
-            const int c = cq * 16 + ci;
-            q[ci] = *reinterpret_cast<const uint4*>(base + (size_t)(c >> 3) * 8960 + pg * 128 + (c & 7) * 16);
-        }
-    }
-    __syncthreads();
+    const int cq = t & 3, pg = min(t >> 2, 69);       // threads 280..287 shadow the last group (they never store)
+    const bool live = t < 280;
     float acc[3][8];
 #pragma unroll
     for (int j = 0; j < 3; j++)
 #pragma unroll
         for (int e = 0; e < 8; e++) acc[j][e] = 0.0f;
-    if (live) {
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        uint4 q[16];
 #pragma unroll
         for (int ci = 0; ci < 16; ci++) {
-            const int c = cq * 16 + ci;
+            const int c = cq * 32 + half * 16 + ci;
+            q[ci] = *reinterpret_cast<const uint4*>(base + (size_t)(c >> 3) * 8960 + pg * 128 + (c & 7) * 16);
+        }
+#pragma unroll
+        for (int ci = 0; ci < 16; ci++) {
+            const int c = cq * 32 + half * 16 + ci;
             const uint32_t qw[4] = {q[ci].x, q[ci].y, q[ci].z, q[ci].w};
             const float w0 = s_w[c], w1 = s_w[128 + c], w2 = s_w[256 + c];
 #pragma unroll
@@ -428,7 +433,7 @@ __global__ void __launch_bounds__(HCT) k_head_conv_t16(const uint8_t* __restrict
             }
         }
     }
-    // the 8 channel groups of a position group are lanes 8k..8k+7: butterfly over the low 3 lane bits
+    // the 4 channel quarters of a position group are lanes 4k..4k+3
 #pragma unroll
     for (int j = 0; j < 3; j++)
 #pragma unroll
@@ -436,7 +441,6 @@ __global__ void __launch_bounds__(HCT) k_head_conv_t16(const uint8_t* __restrict
             float v = acc[j][e];
             v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
             v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
-            v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
             acc[j][e] = v;
         }
     if (live && cq < 3) {                 // lane cq writes output channel cq of its 8 positions
@@ -455,17 +459,29 @@ __global__ void __launch_bounds__(HCT) k_head_conv_t16(const uint8_t* __restrict
 
 extern "C" int hz_net_head_conv_t16(const void* x_tiles, int64_t n, const float* w_conv, const float* b_conv, float* head_conv,
                                     void* stream) {
+    return hz_net_head_conv_t16_active(x_tiles, n, nullptr, w_conv, b_conv, head_conv, stream);
+}
+
+extern "C" int hz_net_head_conv_t16_active(const void* x_tiles, int64_t n, const int32_t* n_active, const float* w_conv,
+                                           const float* b_conv, float* head_conv, void* stream) {
     if (n == 0) return HZ_OK;
-    if (!x_tiles || !w_conv || !b_conv || !head_conv || n < 0 || ((uintptr_t)x_tiles & 15)) return HZ_ERR_ARG;
+    if (!x_tiles || !w_conv || !b_conv || !head_conv || n < 0 || ((uintptr_t)x_tiles & 15) || ((uintptr_t)n_active & 3)) return HZ_ERR_ARG;
     int64_t tiles = (n + 15) / 16;
-    hz::k_head_conv_t16<<<(unsigned)tiles, hz::HCT, 0, (cudaStream_t)stream>>>((const uint8_t*)x_tiles, n, w_conv, b_conv, head_conv);
+    hz::k_head_conv_t16<<<(unsigned)tiles, hz::HCT, 0, (cudaStream_t)stream>>>((const uint8_t*)x_tiles, n, w_conv, b_conv, head_conv, n_active);
     return hz_launched(1);
 }
 
 extern "C" int hz_net_heads_fc(const float* head_conv, const void* glob, int64_t n, int H, const float* w_pol_t, const float* b_pol,
                                const float* w_v1_t, const float* b_v1, const float* w_v2, float b_v2, float* logits, float* value,
                                void* stream) {
+    return hz_net_heads_fc_active(head_conv, glob, n, nullptr, H, w_pol_t, b_pol, w_v1_t, b_v1, w_v2, b_v2, logits, value, stream);
+}
+
+extern "C" int hz_net_heads_fc_active(const float* head_conv, const void* glob, int64_t n, const int32_t* n_active, int H,
+                                      const float* w_pol_t, const float* b_pol, const float* w_v1_t, const float* b_v1,
+                                      const float* w_v2, float b_v2, float* logits, float* value, void* stream) {
     if (n == 0) return HZ_OK;
+    if ((uintptr_t)n_active & 3) return HZ_ERR_ARG;
     if (!head_conv || !glob || !w_pol_t || !b_pol || !w_v1_t || !b_v1 || !w_v2 || !logits || !value || n < 0) return HZ_ERR_ARG;
     if (H != hz::FH || (((uintptr_t)w_v1_t | (uintptr_t)w_pol_t) & 15)) return HZ_ERR_ARG;
     hz::HeadParams P{nullptr, nullptr, w_pol_t, b_pol, w_v1_t, b_v1, w_v2, b_v2, hz::FC, H};
@@ -479,7 +495,7 @@ extern "C" int hz_net_heads_fc(const float* head_conv, const void* glob, int64_t
     }
     int64_t fgroups = (n + hz::FG - 1) / hz::FG;
     int fgrid = (int)(fgroups < 148 ? fgroups : 148);
-    hz::k_heads_p<<<fgrid, hz::FTPB, hz::FSMEM, (cudaStream_t)stream>>>(nullptr, (const __nv_bfloat16*)glob, n, P, logits, value, head_conv);
+    hz::k_heads_p<<<fgrid, hz::FTPB, hz::FSMEM, (cudaStream_t)stream>>>(nullptr, (const __nv_bfloat16*)glob, n, P, logits, value, head_conv, n_active);
     return hz_launched(1);
 }
 
@@ -505,7 +521,7 @@ extern "C" int hz_net_heads(const void* x, const void* glob, int64_t n, int C, i
         int64_t fgroups = (n + hz::FG - 1) / hz::FG;
         int fgrid = (int)(fgroups < 148 ? fgroups : 148);
         hz::k_heads_p<<<fgrid, hz::FTPB, hz::FSMEM, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)glob,
-                                                                            n, P, logits, value, nullptr);
+                                                                            n, P, logits, value, nullptr, nullptr);
         return hz_launched(1);
     }
     size_t smem = sizeof(float) * (size_t)(3 * C + hz::HP * hz::PIN + hz::HP * 80 + hz::HP * 8);

@@ -43,6 +43,7 @@ struct hz_tree {
     uint8_t* status;
     uint64_t* search_key;
     size_t table_bytes;
+    const int32_t* n_active;   // device word (nullable): only trees 0..*n_active-1 take part in reset / select / evaluate / expand
 };
 
 namespace hz {
@@ -50,6 +51,13 @@ namespace hz {
 constexpr int WPB = 4;            // warps (trees) per block
 constexpr int TTPB = WPB * 32;
 constexpr unsigned FULL = 0xFFFFFFFFu;
+
+// trees beyond the active prefix (hz_tree_set_active) are skipped by the per-simulation kernels
+__device__ __forceinline__ int active_trees(const hz_tree& T) {
+    if (!T.n_active) return T.n_trees;
+    int n = *T.n_active;
+    return n < 0 ? 0 : n < T.n_trees ? n : T.n_trees;
+}
 
 struct TreeView {                 // device copy of the handle with per-tree offsets applied
     uint4* node_state; uint64_t* node_hash; uint32_t* node_edge0; uint32_t* node_info;
@@ -83,7 +91,7 @@ __device__ __forceinline__ void state_from_words(State& s, const uint32_t* sm) {
 // ---- reset: Node(root) + MCTS(root) (MCTS.py:288-289, 43-61) -----------------------------------
 __global__ void __launch_bounds__(TTPB) k_tree_reset(hz_tree T, const uint4* roots, const uint64_t* keys) {
     int t = blockIdx.x * TTPB + threadIdx.x;
-    if (t >= T.n_trees) return;
+    if (t >= active_trees(T)) return;
     TreeView v = view_of(T, t);
     State s;
     load_state(s, roots, t);
@@ -195,7 +203,7 @@ __global__ void __launch_bounds__(TTPB) k_tree_select(hz_tree T, float cpuct, ui
     }
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t = blockIdx.x * WPB + warp;
-    if (t >= T.n_trees) return;
+    if (t >= active_trees(T)) return;
     TreeView v = view_of(T, t);
     const int K = T.leaves;
     // K descents per tree and step.  K == 1 is the reference's move_to_leaf.  For K > 1 every
@@ -350,7 +358,7 @@ __global__ void __launch_bounds__(TTPB, HZ_EXPAND_MIN_BLOCKS) k_tree_expand_back
     const NbrLut* lut = global_nbr_lut();
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t = blockIdx.x * WPB + warp;
-    if (t >= T.n_trees) return;
+    if (t >= active_trees(T)) return;
     TreeView v = view_of(T, t);
     const int K = T.leaves, sim0 = T.sim[t];
     // the K leaves of this step are processed in order j = 0..K-1 (K == 1: the reference)
@@ -528,7 +536,7 @@ __global__ void __launch_bounds__(TTPB) k_tree_fake_eval(hz_tree T, float* polic
     __shared__ uint32_t sm_words[WPB][32];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t = blockIdx.x * WPB + warp;
-    if (t >= T.n_trees) return;
+    if (t >= active_trees(T)) return;
     TreeView v = view_of(T, t);
     for (int j = 0; j < T.leaves; j++) {
         size_t row = (size_t)t * T.leaves + j;
@@ -683,12 +691,19 @@ int hz_tree_create(hz_tree** out, void* workspace, size_t workspace_bytes, int n
     t->edge_V = (int32_t*)(b + L.off[18]);
     t->table_hash = (uint64_t*)(b + L.off[19]); t->edge_cinfo = (uint32_t*)(b + L.off[20]);
     t->table_bytes = (size_t)n_trees * L.table_size * 4;
+    t->n_active = nullptr;
     *out = t;
     return HZ_OK;
 }
 
 int hz_tree_destroy(hz_tree* t) {
     delete t;
+    return HZ_OK;
+}
+
+int hz_tree_set_active(hz_tree* t, const int32_t* n_active) {
+    if (!t || ((uintptr_t)n_active & 3)) return HZ_ERR_ARG;
+    t->n_active = n_active;
     return HZ_OK;
 }
 

@@ -98,7 +98,14 @@ struct Params {
     int dbg;               // profiling only (hz_tower_set_debug): 1 skip MMAs, 2 skip epilogue memory traffic, 4 skip weight copies, 8 skip activation copies, 32 single MMA issuer
     unsigned int* fault;
     unsigned long long* trace;   // profiling only (hz_tower_set_trace): SM-clock timestamps of CTA 0's roles
+    const int* n_active;         // device word (nullable): only the tiles that hold boards 0..*n_active-1 are computed
 };
+// tiles to compute: all of them, or those of the active board prefix (every thread of the grid reads the same word)
+__device__ __forceinline__ int tiles_of(const int* n_active, int n_tiles) {
+    if (!n_active) return n_tiles;
+    const int n = (*n_active + G - 1) / G;
+    return n < 0 ? 0 : n < n_tiles ? n : n_tiles;
+}
 // trace slots (CTA 0 only, 4096 uint64): [0] start, [1] end (SM clock), [2] start, [3] end (globaltimer, ns);
 // MMA warp per weight stage i < 600: [16+3i] before the wait on the stage, [+1] after it, [+2] after the MMAs
 // and commits were issued; weight producer [2000+i] when it issues stage i; epilogue warp 4 per row j < 200:
@@ -300,7 +307,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
     volatile int* qitem = (volatile int*)(sm + OFF_BAR + N_BARS * 8 + 16);   // work-item queue, 2 entries
     auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_items = P.n_layers * P.n_tiles;
+    const int n_tiles = tiles_of(P.n_active, P.n_tiles);
+    const int n_items = P.n_layers * n_tiles;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; i++) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
@@ -332,13 +340,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
     if (warp == 3) {
         // ---- scheduler ----
         if (lane == 0) {
-            const int per_cta = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // static map: tiles blockIdx.x + j*gridDim.x
+            const int per_cta = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // static map: tiles blockIdx.x + j*gridDim.x
             for (int k = 0;; k++) {
                 int item;
                 if (P.sched) {
                     item = dequeue_item(P.sched, n_items, P.fault);
                 } else {
-                    item = k < per_cta * P.n_layers ? (k / per_cta) * P.n_tiles + (int)blockIdx.x + (k % per_cta) * (int)gridDim.x : -1;
+                    item = k < per_cta * P.n_layers ? (k / per_cta) * n_tiles + (int)blockIdx.x + (k % per_cta) * (int)gridDim.x : -1;
                 }
                 mbar_wait(bar(B_QEMPTY + (k & 1)), (((uint32_t)k >> 1) & 1u) ^ 1u, P.fault, 0xA00);
                 qitem[k & 1] = item;
@@ -355,7 +363,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 int item;
                 HZ_NEXT_ITEM(k, item, false);
                 if (item < 0) break;
-                const Layer& L = P.layers[item / P.n_tiles];
+                const Layer& L = P.layers[item / n_tiles];
                 const int nkh = L.nkh;
                 for (int pass = 0; pass < 2; pass++)
                     for (int kh = 0; kh < nkh; kh++)
@@ -381,7 +389,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 int item;
                 HZ_NEXT_ITEM(k, item, false);
                 if (item < 0) break;
-                const int l = item / P.n_tiles, tile = item - l * P.n_tiles;
+                const int l = item / n_tiles, tile = item - l * n_tiles;
                 const Layer& L = P.layers[l];
                 // the tile's input is the previous layer's output, possibly written by another CTA through the generic
                 // proxy; the ready queue (acquired by the scheduler, handed over through the item barrier) makes it
@@ -412,7 +420,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 int item;
                 HZ_NEXT_ITEM(k, item, true);
                 if (item < 0) break;
-                const Layer& L = P.layers[item / P.n_tiles];
+                const Layer& L = P.layers[item / n_tiles];
                 const int nkh = L.nkh;
                 const bool kmajor = L.kmajor != 0;
                 for (int kh = 0; kh < nkh; kh++) {
@@ -448,7 +456,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
             int item;
             HZ_NEXT_ITEM(k, item, true);
             if (item < 0) break;
-            const int l = item / P.n_tiles, tile = item - l * P.n_tiles;
+            const int l = item / n_tiles, tile = item - l * n_tiles;
             const Layer& L = P.layers[l];
             const float bias = L.bias[c];
             const uint8_t* resb = (L.res_buf >= 0 && mem) ? P.buf[L.res_buf] : nullptr;
@@ -523,7 +531,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 if (lane == 0 && atom_add_acq_rel_gpu(P.sched + 2 + item, 1u) == FLAG_DONE - 1) {
                     // last of the 8 epilogue warps: the tile's next layer becomes ready
                     const unsigned int slot = atomicAdd(P.sched + 1, 1u);
-                    st_release_gpu(P.sched + 2 + n_items + slot, (unsigned int)(item + P.n_tiles) + 1u);
+                    st_release_gpu(P.sched + 2 + n_items + slot, (unsigned int)(item + n_tiles) + 1u);
                 }
             }
         }
@@ -537,7 +545,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
 }
 
 // ready queue before the launch: head 0, tail n_tiles, no completions, the stem items in slots 0..n_tiles-1
-__global__ void k_sched_init(unsigned int* sched, int n_tiles, int n_items) {
+__global__ void k_sched_init(unsigned int* sched, int n_tiles_max, int n_layers, const int* n_active) {
+    const int n_tiles = tiles_of(n_active, n_tiles_max), n_items = n_layers * n_tiles;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 + 2 * n_items; i += gridDim.x * blockDim.x) {
         unsigned int v = 0u;
         if (i == 1) v = (unsigned int)n_tiles;
@@ -704,7 +713,14 @@ size_t hz_tower_sched_bytes(int64_t n_boards, int n_blocks) {
 
 int hz_tower_forward(const void* x0_tiles, const void* const* w_tiles, const float* const* biases, int n_blocks, void* buf_a,
                      void* buf_b, void* buf_c, void* sched, void** out_tiles, int64_t n_boards, unsigned int* fault, void* stream) {
+    return hz_tower_forward_active(x0_tiles, w_tiles, biases, n_blocks, buf_a, buf_b, buf_c, sched, out_tiles, n_boards, nullptr, fault, stream);
+}
+
+int hz_tower_forward_active(const void* x0_tiles, const void* const* w_tiles, const float* const* biases, int n_blocks, void* buf_a,
+                            void* buf_b, void* buf_c, void* sched, void** out_tiles, int64_t n_boards, const int32_t* n_active,
+                            unsigned int* fault, void* stream) {
     using namespace hz::tower;
+    if ((uintptr_t)n_active & 3) return HZ_ERR_ARG;
     if (!x0_tiles || !w_tiles || !biases || !buf_a || !buf_b || !buf_c || !sched || n_boards <= 0 || (n_boards % G) || n_blocks < 0 ||
         1 + 2 * n_blocks > MAX_LAYERS)
         return HZ_ERR_ARG;
@@ -735,9 +751,10 @@ int hz_tower_forward(const void* x0_tiles, const void* const* w_tiles, const flo
     P.fault = fault;
     P.dbg = g_debug;
     P.trace = g_trace;
+    P.n_active = n_active;
     if (out_tiles) *out_tiles = P.buf[cur];
     const int n_items = P.n_layers * P.n_tiles;
-    k_sched_init<<<(2 + 2 * n_items + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P.sched, P.n_tiles, n_items);
+    k_sched_init<<<(2 + 2 * n_items + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P.sched, P.n_tiles, P.n_layers, n_active);
     k_tower<<<grid_for(P.n_tiles), NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(P);
     return hz_launched(2);
 }

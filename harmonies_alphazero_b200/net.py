@@ -221,10 +221,11 @@ class InferenceNet:
                 torch.zeros((rows, 143), dtype=torch.float32, device=dev), torch.zeros(rows, dtype=torch.float32, device=dev))
 
     @torch.no_grad()
-    def forward_tiles(self, x0, glob, n, out=None):
+    def forward_tiles(self, x0, glob, n, out=None, n_active=None):
         """Leaves already in the T16K image (hz_tree_select, HZ_LAYOUT_T16K): hand-written tower, the
         1x1 head convolutions straight from its T16 output, then the FC heads.  No layout-conversion
-        kernels on this path."""
+        kernels on this path.  n_active: int32 device tensor (one element): only rows 0..n_active-1
+        are evaluated (read on the device, so a captured graph follows it)."""
         from . import _lib
 
         if not self.wants_tiles:
@@ -236,15 +237,17 @@ class InferenceNet:
         hc = self._hc.get(n)
         if hc is None:
             hc = self._hc[n] = torch.zeros((n, 105), dtype=torch.float32, device=self.device)
-        x_ptr = self.hand.forward_tiles(x0, n)
+        x_ptr = self.hand.forward_tiles(x0, n, n_active=n_active)
         lib = _lib.load()
         glob = glob.contiguous()
+        na = None if n_active is None else n_active.data_ptr()
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream(self.device).cuda_stream
-            _lib.check(lib.hz_net_head_conv_t16(x_ptr, n, h["w_conv"].data_ptr(), h["b_conv"].data_ptr(), hc.data_ptr(), st), "hz_net_head_conv_t16")
-            _lib.check(lib.hz_net_heads_fc(hc.data_ptr(), glob.data_ptr(), n, h["H"], h["w_pol_t"].data_ptr(), h["b_pol"].data_ptr(),
-                                           h["w_v1_t"].data_ptr(), h["b_v1"].data_ptr(), h["w_v2"].data_ptr(), h["b_v2"],
-                                           logits.data_ptr(), value.data_ptr(), st), "hz_net_heads_fc")
+            _lib.check(lib.hz_net_head_conv_t16_active(x_ptr, n, na, h["w_conv"].data_ptr(), h["b_conv"].data_ptr(), hc.data_ptr(), st),
+                       "hz_net_head_conv_t16")
+            _lib.check(lib.hz_net_heads_fc_active(hc.data_ptr(), glob.data_ptr(), n, na, h["H"], h["w_pol_t"].data_ptr(), h["b_pol"].data_ptr(),
+                                                  h["w_v1_t"].data_ptr(), h["b_v1"].data_ptr(), h["w_v2"].data_ptr(), h["b_v2"],
+                                                  logits.data_ptr(), value.data_ptr(), st), "hz_net_heads_fc")
         return logits, value
 
     @torch.no_grad()

@@ -42,6 +42,7 @@ class SelfPlayConfig:
     n_streams: int = 1             # >1: split the slots into groups on separate streams (overlap tree kernels with convs)
     max_nodes: int = 0             # per-tree node arena; 0 = worst case 1 + 69*sims
     max_moves: int = 200           # hard cap per game (structural maximum is 160 actions)
+    compact_live: bool = True      # play(): keep the live games in a dense slot prefix and search only those (the game tail costs what it uses)
 
     @classmethod
     def from_mcts_config(cls, mcts_config, **kw):
@@ -145,6 +146,15 @@ class _Group:
         self.alpha = None if cfg.testing else torch.full((n, 143), cfg.dirichlet_alpha, dtype=torch.float32, device=dev)
         self.graph = None
         self.stream = torch.cuda.Stream(device=dev) if owner.n_groups > 1 else None
+        # [active trees, active leaf rows]: read on the device by the tree kernels and the hand-written network path,
+        # so the captured graph follows it (hz_tree_set_active)
+        self.n_active = torch.tensor([n, rows], dtype=torch.int32, device=dev)
+        self.tree.set_active(self.n_active[0:1])
+
+    def set_active(self, n_trees):
+        K = self.tree.leaves
+        self.n_active[0:1].fill_(int(n_trees))
+        self.n_active[1:2].fill_(int(n_trees) * K)
 
     def sim_step(self):
         """one simulation for every tree of the group: select -> network -> expand+backup"""
@@ -153,7 +163,7 @@ class _Group:
         if getattr(o.net, "tree_eval", False):
             t.fake_eval(self.logits, self.value)       # priors, not logits
         elif self.tiles:
-            o.net.forward_tiles(self.board, self.glob, self.glob.shape[0], out=(self.logits, self.value))
+            o.net.forward_tiles(self.board, self.glob, self.glob.shape[0], out=(self.logits, self.value), n_active=self.n_active[1:2])
         elif o._net_takes_out:        # InferenceNet writes straight into the static buffers
             o.net(self.board, self.glob, out=(self.logits, self.value))
         else:
@@ -270,9 +280,11 @@ class BatchedSelfPlay:
         finished = torch.zeros(num_games, dtype=torch.bool, device=dev)
         chunks, bad_status = [], torch.zeros((), dtype=torch.uint8, device=dev)
         live_sims = 0
+        compact = cfg.compact_live and self.n_groups == 1
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         step = 0
+        searched_slots = 0
         while True:
             over, oc = hb.outcome(states)
             done = over.bool() & live
@@ -292,6 +304,14 @@ class BatchedSelfPlay:
             n_live = int(live.sum().item())
             if n_live == 0:
                 break
+            if compact:
+                if n_done and n_live < B:
+                    # live games first (stable): nothing is keyed by the slot index, the draws and the search
+                    # streams depend on the game's own key only
+                    order = torch.argsort((~live).to(torch.int8), stable=True)
+                    states, game_id, live = states[order].contiguous(), game_id[order], live[order]
+                self.groups[0].set_active(n_live)
+            searched_slots += n_live if compact else B
             move_no = states[:, 27].clone()
             if int(move_no[live].max().item()) >= cfg.max_moves:
                 raise RuntimeError("a game exceeded max_moves without ending")
@@ -319,6 +339,8 @@ class BatchedSelfPlay:
                 self.check_status()
             if progress:
                 progress(step, int(finished.sum().item()), num_games)
+        for g in self.groups:
+            g.set_active(g.hi - g.lo)
         self.check_status()
         if int(bad_status.item()) != 0:
             raise RuntimeError(f"engine rejected a searched move (status {int(bad_status.item())})")
@@ -336,5 +358,6 @@ class BatchedSelfPlay:
             G = torch.empty(0, dtype=torch.int64, device=dev); M = torch.empty(0, dtype=torch.int32, device=dev)
             z = torch.empty(0, dtype=torch.float32, device=dev)
         stats = {"sims": live_sims, "seconds": secs, "sims_per_s": live_sims / secs if secs > 0 else 0.0,
-                 "games": int(finished.sum().item()), "examples": int(S.shape[0]), "move_steps": step}
+                 "games": int(finished.sum().item()), "examples": int(S.shape[0]), "move_steps": step,
+                 "searched_slots": searched_slots}
         return Trajectories(S, V, z, G + cfg.first_game_id, M, stats)

@@ -106,19 +106,23 @@ class HandTower:
         return torch.zeros(n_pad // G * KH_BYTES, dtype=torch.uint8, device=self.device)
 
     @torch.no_grad()
-    def forward_tiles(self, x0, n):
+    def forward_tiles(self, x0, n, n_active=None):
         """x0: T16K tiles of n boards.  Returns the address of the T16 tiles holding the tower output
-        (one of this object's scratch buffers: valid until the next call with the same n)."""
+        (one of this object's scratch buffers: valid until the next call with the same n).
+        n_active: int32 device tensor (one element) = boards to compute, read on the device."""
         n_pad = (n + G - 1) // G * G
         buf = self._buffers(n_pad)
         x, y, z = buf["a"], buf["b"], buf["c"]
         if self.fused_layers:
             res = ct.c_void_p()
             with torch.cuda.device(self.device):
-                _lib.check(self.lib.hz_tower_forward(
+                _lib.check(self.lib.hz_tower_forward_active(
                     x0.data_ptr(), self._w_ptrs, self._b_ptrs, len(self.blocks), x.data_ptr(), y.data_ptr(), z.data_ptr(),
-                    buf["sched"].data_ptr(), ct.byref(res), n_pad, self.fault, self._stream()), "hz_tower_forward")
+                    buf["sched"].data_ptr(), ct.byref(res), n_pad, None if n_active is None else n_active.data_ptr(),
+                    self.fault, self._stream()), "hz_tower_forward")
             return res.value
+        if n_active is not None:
+            raise ValueError("n_active needs the fused all-layers launch")
         self.conv(x0, 1, self.stem, None, x, n_pad, kmajor=True)
         for c1, c2 in self.blocks:
             self.conv(x, 2, c1, None, y, n_pad)

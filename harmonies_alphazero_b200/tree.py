@@ -44,6 +44,15 @@ class BatchedMCTS:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def set_active(self, n_active):
+        """n_active: int32 device tensor with one element (kept alive by this object) or None.  Only trees
+        0..n_active-1 take part in the following reset / select / expand_backup calls; the value may be
+        changed between calls (``n_active.fill_(k)``), also between replays of a captured graph."""
+        if n_active is not None:
+            assert n_active.dtype == torch.int32 and n_active.numel() >= 1 and n_active.device == self.workspace.device
+        self._n_active = n_active
+        _lib.check(self.lib.hz_tree_set_active(self.handle, _ptr(n_active)), "hz_tree_set_active")
+
     def reset(self, root_states, search_keys=None):
         """New search per tree (no tree reuse, MCTS.py:288-289).  search_keys int64[n] or None
         (derived per (game, move) from the root's own rng key and move counter)."""

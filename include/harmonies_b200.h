@@ -69,7 +69,7 @@
 extern "C" {
 #endif
 
-#define HZ_ABI_VERSION      4
+#define HZ_ABI_VERSION      5
 #define HZ_STATE_WORDS      32
 #define HZ_STATE_BYTES      128
 #define HZ_NUM_HEXES        23
@@ -254,6 +254,16 @@ int hz_tree_destroy(hz_tree *t);
 int hz_tree_reset(hz_tree *t, const void *root_states, const uint64_t *search_keys,
                   void *stream);
 
+/* Active prefix (whole-game drivers whose games end at different times): n_active is a DEVICE
+ * int32 (or NULL = all trees) read by every following hz_tree_reset / hz_tree_select /
+ * hz_tree_fake_eval / hz_tree_expand_backup launch: only trees 0..*n_active-1 take part, the
+ * others are skipped (their node and edge arrays keep the last search; hz_tree_reset still clears
+ * every tree's hash index).  The word may change between launches (also between
+ * replays of a captured CUDA graph); with the *_active network entry points below the evaluation
+ * of a step then costs only the live rows.  The reference has no counterpart (one process per
+ * game, trainer.py:104-107). */
+int hz_tree_set_active(hz_tree *t, const int32_t *n_active);
+
 /* move_to_leaf (MCTS.py:63-149) for every tree, then create_state_tensors of the leaf
  * (MCTS.py:299) into board/glob (see hz_encode).  cpuct is applied as fp32(cpuct)*P in fp32
  * then promoted to fp64, the reference's numpy>=2 arithmetic (MCTS.py:107-112).
@@ -318,6 +328,15 @@ int hz_net_head_conv_t16(const void *x_tiles, int64_t n, const float *w_conv, co
 int hz_net_heads_fc(const float *head_conv, const void *glob, int64_t n, int H, const float *w_pol_t,
                     const float *b_pol, const float *w_v1_t, const float *b_v1, const float *w_v2,
                     float b_v2, float *logits, float *value, void *stream);
+/* The same with the row count taken from the device: rows min(n, *n_active) are evaluated
+ * (n_active NULL = n; see hz_tree_set_active). */
+int hz_net_head_conv_t16_active(const void *x_tiles, int64_t n, const int32_t *n_active,
+                                const float *w_conv, const float *b_conv, float *head_conv,
+                                void *stream);
+int hz_net_heads_fc_active(const float *head_conv, const void *glob, int64_t n,
+                           const int32_t *n_active, int H, const float *w_pol_t, const float *b_pol,
+                           const float *w_v1_t, const float *b_v1, const float *w_v2, float b_v2,
+                           float *logits, float *value, void *stream);
 
 /* ---- residual tower (model.py:325-339, ResidualBlock.forward model.py:380-392) -----------
  * Hand-written sm_100a 3x3 convolution (tcgen05.mma, accumulators in tensor memory, operands
@@ -377,6 +396,14 @@ size_t hz_tower_sched_bytes(int64_t n_boards, int n_blocks);
 int hz_tower_forward(const void *x0_tiles, const void *const *w_tiles, const float *const *biases,
                      int n_blocks, void *buf_a, void *buf_b, void *buf_c, void *sched,
                      void **out_tiles, int64_t n_boards, unsigned int *fault, void *stream);
+
+/* hz_tower_forward over the tiles that hold boards 0..min(n_boards, *n_active)-1 only (n_active: a
+ * DEVICE int32, NULL = all; see hz_tree_set_active).  The launch geometry and every address are
+ * those of n_boards, so one captured CUDA graph serves every active count. */
+int hz_tower_forward_active(const void *x0_tiles, const void *const *w_tiles,
+                            const float *const *biases, int n_blocks, void *buf_a, void *buf_b,
+                            void *buf_c, void *sched, void **out_tiles, int64_t n_boards,
+                            const int32_t *n_active, unsigned int *fault, void *stream);
 
 #define HZ_PLAYOUT_SALT 0xA5A5F00DC0FFEE11ull
 #define HZ_SEARCH_SALT  0x5EA2C47EE5A17B00ull

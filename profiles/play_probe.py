@@ -19,13 +19,14 @@ ap.add_argument("--sims", type=int, default=100)
 ap.add_argument("--profile", action="store_true")
 ap.add_argument("--slots", type=int, default=4096)
 ap.add_argument("--leaves", type=int, default=1)
+ap.add_argument("--no-compact", action="store_true")
 a = ap.parse_args()
 torch.backends.cudnn.benchmark = True
 torch.manual_seed(0)
 dev = torch.device("cuda", 0)
 model = hznet.AlphaZeroNet.from_config(hznet.DEFAULT_MODEL_CONFIG).eval()
 inf = hznet.InferenceNet(model, device=dev, dtype=torch.bfloat16)
-cfg = sp.SelfPlayConfig(n_slots=a.slots, num_simulations=a.sims, seed=1, leaves_per_step=a.leaves)
+cfg = sp.SelfPlayConfig(n_slots=a.slots, num_simulations=a.sims, seed=1, leaves_per_step=a.leaves, compact_live=not a.no_compact)
 drv = sp.BatchedSelfPlay(inf, cfg, device=dev)
 drv.play(min(64, a.slots))
 evs = []
@@ -52,6 +53,7 @@ gaps = [evs[i][1].elapsed_time(evs[i + 1][0]) for i in range(len(evs) - 1)]
 print(json.dumps({"gap_ms_mean": sum(gaps) / max(1, len(gaps)), "gap_ms_sorted_tail": [round(g, 2) for g in sorted(gaps)[-8:]],
                   "gap_ms_median": sorted(gaps)[len(gaps) // 2] if gaps else None}))
 st = traj.stats
+print(json.dumps({"search_ms_every_8th_step": [round(m, 2) for m in ms[::8]]}))
 print(json.dumps({"steps": len(ms), "loop_s": st["seconds"], "search_s": sum(ms) / 1e3,
                   "outside_search_ms_per_step": (st["seconds"] - sum(ms) / 1e3) / len(ms) * 1e3,
                   "search_ms_per_step": sum(ms) / len(ms), "slot_utilisation": st["examples"] / (len(ms) * a.slots), "stats": st}))

@@ -41,7 +41,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     # the Python binding declares a signature for each of them, and nothing else
     assert sorted(_lib.SIGNATURES) == syms
     loaded = _lib.load()
-    assert loaded.hz_abi_version() == 4
+    assert loaded.hz_abi_version() == 5
     assert loaded.hz_status_string(-4).decode().startswith("workspace")
     assert loaded.hz_launch_count() == 0
     assert loaded.hz_tree_workspace_bytes(4096, 100, 0, 1) > 4096 * 6901 * 128

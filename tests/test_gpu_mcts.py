@@ -291,3 +291,29 @@ def test_terminal_root(mods):
     visits, pi = t.root_policy()
     assert (visits == 0).all() and (pi == 0).all()
     assert (t.choose() == -1).all()   # MCTS.py:439: (None, pi)
+
+
+def test_active_prefix_leaves_other_trees_untouched(mods):
+    """hz_tree_set_active: trees beyond the device-side count keep their previous search bit for bit,
+    the active ones search exactly as without the switch."""
+    hb, tree = mods[0], mods[-1]
+    st = hb.init_states(64, seed=21)
+    hb.playout(st, max_steps=9)
+    a = tree.BatchedMCTS(64, 32)
+    b = tree.BatchedMCTS(64, 32)
+    a.reset(st); a.run_synthetic(20, 2.0)
+    b.reset(st); b.run_synthetic(20, 2.0)
+    st2 = st.clone()
+    hb.playout(st2, max_steps=3)
+    na = torch.tensor([24], dtype=torch.int32, device="cuda")
+    b.set_active(na)
+    b.reset(st2); b.run_synthetic(32, 2.0)
+    c = tree.BatchedMCTS(64, 32)
+    c.reset(st2); c.run_synthetic(32, 2.0)
+    Nb, Wb, Pb, _ = b.root_edges(); Na, Wa, Pa, _ = a.root_edges(); Nc, Wc, Pc, _ = c.root_edges()
+    assert torch.equal(Nb[:24], Nc[:24]) and torch.equal(Wb[:24], Wc[:24]) and torch.equal(Pb[:24], Pc[:24])
+    assert torch.equal(Nb[24:], Na[24:]) and torch.equal(Wb[24:], Wa[24:])
+    b.set_active(None)
+    b.reset(st2); b.run_synthetic(32, 2.0)
+    Nb, Wb, _, _ = b.root_edges()
+    assert torch.equal(Nb, Nc) and torch.equal(Wb, Wc)

@@ -291,3 +291,51 @@ def test_self_play_runs_on_the_hand_written_tower(tw):
     v = traj.visits.to(torch.int64).sum(dim=1)
     assert int(v.max()) == 11 and int(v.min()) >= 0          # sum N = sims - 1 (MCTS.py:355-381)
     assert set(traj.z.unique().tolist()) <= {-1.0, 0.0, 1.0}
+
+
+def test_active_prefix_of_the_tile_path(tw):
+    """hz_tower_forward_active / hz_net_*_active: with a device-side row count the evaluated prefix is
+    bit-identical to the full evaluation and the rows beyond the last active tile are left untouched."""
+    from harmonies_alphazero_b200 import net as hnet
+
+    torch.manual_seed(4)
+    model = hnet.AlphaZeroNet.from_config(hnet.DEFAULT_MODEL_CONFIG).eval()
+    hand = hnet.InferenceNet(model, device="cuda", tower="hand")
+    B = 200
+    g = torch.Generator().manual_seed(11)
+    b40 = torch.zeros((B, 40, 5, 7), dtype=torch.bfloat16, device="cuda").contiguous(memory_format=torch.channels_last)
+    b40[:, :38] = (torch.rand((B, 38, 5, 7), generator=g) < 0.2).to(torch.bfloat16).cuda()
+    glob = torch.rand((B, 42), generator=g).to(torch.bfloat16).cuda()
+    x0 = hand.hand.x0_buffer(B)
+    hand.hand.to_tiles(b40, 40, True, x0)
+    l_full, v_full = hand.forward_tiles(x0, glob, B)
+    l_full, v_full = l_full.clone(), v_full.clone()
+    na = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for k in (200, 131, 16, 1, 0):
+        na.fill_(k)
+        out = (torch.full((B, 143), -7.0, device="cuda"), torch.full((B,), -7.0, device="cuda"))
+        hand.forward_tiles(x0, glob, B, out=out, n_active=na)
+        torch.cuda.synchronize()
+        assert torch.equal(out[0][:k], l_full[:k]) and torch.equal(out[1][:k], v_full[:k])
+        assert bool((out[0][k:] == -7.0).all()) and bool((out[1][k:] == -7.0).all())
+
+
+def test_self_play_with_live_prefix_compaction_equals_plain(tw):
+    """SelfPlayConfig.compact_live: whole games on the hand-written tower with the live games kept in a
+    dense prefix (device-side active counts under the captured graph) give exactly the trajectories of
+    the plain loop — every row's evaluation is independent of where it sits in the batch."""
+    from harmonies_alphazero_b200 import net as hnet
+    from harmonies_alphazero_b200 import selfplay as sp
+
+    torch.manual_seed(0)
+    model = hnet.AlphaZeroNet.from_config(hnet.DEFAULT_MODEL_CONFIG).eval()
+    hand = hnet.InferenceNet(model, device="cuda", tower="hand")
+    out = []
+    for compact in (False, True):
+        cfg = sp.SelfPlayConfig(n_slots=40, num_simulations=8, seed=5, testing=True, compact_live=compact)
+        t = sp.BatchedSelfPlay(hand, cfg).play(56)
+        assert t.stats["games"] == 56
+        order = torch.argsort(t.game_id * 1000 + t.move_no.to(torch.int64))
+        out.append((t.states[order].cpu(), t.visits[order].cpu(), t.z[order].cpu(), t.stats["searched_slots"], t.stats["move_steps"]))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+    assert out[1][3] < out[0][3] and out[1][3] == len(out[1][0])      # compacted: exactly one searched slot per example
