@@ -363,6 +363,10 @@ def mcts_measure(args, dev, world, rank, dist, with_collectives=True, tower=None
                                  turns_until_tau0=15, seed=78, first_game_id=rank * play_games, n_streams=args.mcts_streams,
                                  leaves_per_step=args.mcts_leaves, use_cuda_graph=not args.mcts_no_graph)
         drv.cfg = pcfg
+        # warm-up of the whole-game loop itself: a tiny driver plays more games than it has slots, so every torch kernel of the
+        # refill / compaction / bookkeeping path is loaded before the timed region (first uses cost up to 100 ms each)
+        wcfg = sp.SelfPlayConfig(n_slots=32, num_simulations=4, seed=5, n_streams=args.mcts_streams, use_cuda_graph=not args.mcts_no_graph)
+        sp.BatchedSelfPlay(inf, wcfg, device=dev).play(80)
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
@@ -386,7 +390,9 @@ def mcts_measure(args, dev, world, rank, dist, with_collectives=True, tower=None
                  "vs_peak_step": (live_sims / secs) / v_step, "clocks": play_clocks,
                  "launches_direct": (hb.launch_count() - l1) * world,
                  "what": f"BatchedSelfPlay.play: {play_games} complete games per GPU on {B} slots (refill in place), live simulations only; "
-                         "includes refill, trajectory bookkeeping, move sampling and the game tail"}
+                         "includes refill, trajectory bookkeeping, move sampling and the game tail; live games are kept in a dense slot prefix "
+                         "and only those are searched (SelfPlayConfig.compact_live)",
+                 "searched_slot_steps": int(st.get("searched_slots", 0))}
         direct_launches += hb.launch_count() - l1
     v = whole["value"] if whole else v_step
     ach = (v / world) * flops / 1e12

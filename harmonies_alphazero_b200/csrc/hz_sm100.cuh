@@ -38,16 +38,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 #ifndef HZ_MBAR_SPIN_LIMIT
 #define HZ_MBAR_SPIN_LIMIT (1u << 24)
 #endif
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* fault, unsigned int code) {
-    for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
-        if (it > HZ_MBAR_SPIN_LIMIT) {
-            if (fault) {
-                atomicExch(fault, code);
-                __threadfence_system();
-            }
-            __trap();
-        }
+// (the time-out path is one out-of-line function: inlined at every wait it made the tower's issue loop several times
+// larger than the instruction cache)
+__device__ __noinline__ void mbar_timeout(unsigned int* fault, unsigned int code) {
+    if (fault) {
+        atomicExch(fault, code);
+        __threadfence_system();
     }
+    __trap();
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, unsigned int* fault, unsigned int code) {
+    for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
+        if (it > HZ_MBAR_SPIN_LIMIT) mbar_timeout(fault, code);
+    }
+}
+// inline: one try; the spin loop is shared code (a waiter that has to spin is not in a hurry)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* fault, unsigned int code) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, fault, code);
 }
 
 // ---- proxies / fences ------------------------------------------------------------------------

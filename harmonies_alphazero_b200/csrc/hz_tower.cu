@@ -111,10 +111,23 @@ __device__ __forceinline__ int tiles_of(const int* n_active, int n_tiles) {
 // and commits were issued; weight producer [2000+i] when it issues stage i; epilogue warp 4 per row j < 200:
 // [2700+4j] before the accumulator wait, [+1] after, [+2] after the TMEM loads, [+3] after the stores;
 // activation producer [3600+j] when it issues half j.
+// compiled in with -DHZ_TOWER_TRACE=1 only (profiles/tower_trace.py): the time stamps cost instruction-cache space
+#ifndef HZ_TOWER_TRACE
+#define HZ_TOWER_TRACE 0
+#endif
+#if HZ_TOWER_TRACE
 #define HZ_TRACE(slot)                                                                  \
     do {                                                                                \
         if (P.trace && blockIdx.x == 0 && lane == 0 && (slot) < 4096) P.trace[slot] = clock64(); \
     } while (0)
+#define HZ_CTRACE(slot)                                                                 \
+    do {                                                                                \
+        if (c.trace && c.nstage < 600) c.trace[slot] = clock64();                       \
+    } while (0)
+#else
+#define HZ_TRACE(slot) do { } while (0)
+#define HZ_CTRACE(slot) do { } while (0)
+#endif
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -145,6 +158,23 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
 }
 
 // A-operand collector hints (csrc/hz_sm100.cuh): compile-time A/B switch, -DHZ_TOWER_COLLECTOR=0 to disable
+#ifndef HZ_TOWER_KUNROLL
+#define HZ_TOWER_KUNROLL 0      // 1: unroll the k-steps of a stage as well (A/B switch)
+#endif
+#if HZ_TOWER_KUNROLL
+#define HZ_TOWER_K_PRAGMA _Pragma("unroll")
+#else
+#define HZ_TOWER_K_PRAGMA _Pragma("unroll 1")
+#endif
+// stages per issuer turn in pass 0 / pass 1 (see StageLoop).  Measured (tower of 4,096 boards): 1/1 394 us, 1/2 406,
+// 1/3 412, 2/2 416, 3/3 420: what the second issuer buys is a warp that already waits for the NEXT stage's weights,
+// and longer turns give that up
+#ifndef HZ_TOWER_TURN_P0
+#define HZ_TOWER_TURN_P0 1
+#endif
+#ifndef HZ_TOWER_TURN_P1
+#define HZ_TOWER_TURN_P1 1
+#endif
 #ifndef HZ_TOWER_COLLECTOR
 #define HZ_TOWER_COLLECTOR 1
 #endif
@@ -183,7 +213,12 @@ __device__ __forceinline__ void issue_stage(uint32_t a_lo, uint32_t b_lo, uint32
     constexpr uint32_t idesc = idesc_bf16_f32(128, dx ? 96 : 112) | (KMAJOR ? 0u : (1u << 16));
     // rows of the pass this tap touches: [ra, rb) (always a contiguous range)
     constexpr int ra = (r0 + dy < 0) ? r0 + 1 : r0, rb = (r1 - 1 + dy >= BROWS) ? r1 - 1 : r1;
-#pragma unroll
+    // the k loop is NOT unrolled: with it unrolled the issue code of a residual layer is 41 KB, more than the instruction
+    // cache keeps beside the epilogue, and every change of pass stalled both issuers on instruction fetch (role timeline,
+    // profiles/tower_trace.py: 2-14 thousand cycles at the first stage of pass 1 of every work item; tower 435 -> 400 us).
+    // Taps and rows stay compile-time: run-time loops over them were measured slower (450-470 us; the set-up between the
+    // hand-over and the first MMA is what the tensor pipe waits for)
+    HZ_TOWER_K_PRAGMA
     for (int k = K0; k < K1; k++) {
         const uint64_t da = desc64(a_lo + (uint32_t)(k * 2), DESC_HI_SW128);
 #pragma unroll
@@ -220,9 +255,14 @@ struct StageLoop {
     static __device__ __forceinline__ void run(Ctx& c, int kh, int it, bool last_kh) {
         constexpr int tap = tap_at(PASS, TI);
         constexpr int r0 = PASS ? 3 : 0, r1 = PASS ? 5 : 3;
-        const bool mine = !c.dual || ((c.nstage & 1) == c.parity);
+        // a TURN = the consecutive stages one issuer runs between two hand-overs (HZ_TOWER_TURN_P0 / _P1 stages of the pass,
+        // counted across its channel halves; the pass's last stage always ends a turn)
+        constexpr int T = PASS ? HZ_TOWER_TURN_P1 : HZ_TOWER_TURN_P0;
+        const int idx = kh * 9 + TI;
+        const bool first_in_turn = T == 1 || idx % T == 0, last_in_turn = T == 1 || idx % T == T - 1 || (last_kh && TI == 8);
+        const bool mine = !c.dual || ((c.nturn & 1) == c.parity);
         if (mine) {
-            if (c.trace && c.nstage < 600) c.trace[16 + 3 * c.nstage] = clock64();
+            HZ_CTRACE(16 + 3 * c.nstage);
             mbar_wait(c.bar0 + 8u * (B_WFULL + c.stage), c.ph, c.fault, 0x400 + c.stage);
             if (TI == 0 && kh == 0) {   // first touch of the pass's accumulators for this tile: previous tenants must be drained
 #pragma unroll
@@ -233,15 +273,15 @@ struct StageLoop {
             const uint32_t a_lo = DESC_LO_SW128 | ((c.sW + c.stage * W_BYTES) >> 4);
             const uint32_t b_lo = (KMAJOR ? DESC_LO_SW128 : DESC_LO_T16) | ((c.sX + (uint32_t)kh * KH_BYTES) >> 4);
             const uint32_t acc0 = kh == 0 ? 0u : 1u;
-            if (c.dual && c.nstage > 0) named_bar_sync(c.parity ? 1 : 2);   // the other issuer has handed over
+            if (c.dual && first_in_turn && c.nturn > 0) named_bar_sync(c.parity ? 1 : 2);   // the other issuer has handed over
             tc_fence_after();
-            if (c.trace && c.nstage < 600) c.trace[16 + 3 * c.nstage + 1] = clock64();
+            HZ_CTRACE(16 + 3 * c.nstage + 1);
             // (handing over BEFORE the last k-step, with that step issued without collector hints, was measured: the
             // interleaved MMAs corrupt the other issuer's collector group — results differ — so the hand-over stays behind
             // the last MMA; the commits, which only track this thread's own MMAs, come after it)
             if (lead && !(c.dbg & 1)) issue_stage<KMAJOR, PASS, TI, 0, 4>(a_lo, b_lo, c.tbase, acc0);
             __syncwarp();
-            if (c.dual) named_bar_arrive(c.parity ? 2 : 1);
+            if (c.dual && last_in_turn) named_bar_arrive(c.parity ? 2 : 1);
             if (lead) {
                 umma_commit(c.bar0 + 8u * (B_WEMPTY + c.stage));      // frees the weight stage when these MMAs have read it
                 if (last_kh) {
@@ -252,9 +292,10 @@ struct StageLoop {
                 if (PASS == 1 && TI == 8) umma_commit(c.bar0 + 8u * (B_AEMPTY + kh));   // the tile's channel half is no longer read
             }
             __syncwarp();
-            if (c.trace && c.nstage < 600) c.trace[16 + 3 * c.nstage + 2] = clock64();
+            HZ_CTRACE(16 + 3 * c.nstage + 2);
         }
         c.nstage++;
+        if (last_in_turn) c.nturn++;
         if (++c.stage == NSTAGE) { c.stage = 0; c.ph ^= 1; }
         if constexpr (TI < 8) StageLoop<KMAJOR, PASS, TI + 1>::run(c, kh, it, last_kh);
     }
@@ -265,8 +306,9 @@ struct IssueCtx {
     unsigned int* fault;
     int dbg;
     unsigned long long* trace;   // null unless CTA 0 is being traced
-    int nstage;                  // running stage count of the CTA (trace index; parity = issuing warp)
-    int parity;                  // this warp issues the stages with nstage % 2 == parity
+    int nstage;                  // running stage count of the CTA (trace index)
+    int nturn;                   // running turn count of the CTA
+    int parity;                  // this warp issues the turns with nturn % 2 == parity
     bool dual;                   // two issuer warps (false: this warp issues everything)
 };
 
@@ -324,7 +366,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
     tc_fence_after();
     const uint32_t tbase = *tmem_slot;
     if (warp == 0) HZ_TRACE(0);
-    if (warp == 0 && P.trace && blockIdx.x == 0 && lane == 0) P.trace[2] = globaltimer_ns();
+    if (HZ_TOWER_TRACE && warp == 0 && P.trace && blockIdx.x == 0 && lane == 0) P.trace[2] = globaltimer_ns();
 
     // every role walks the CTA's work items in the order the scheduler (warp 3) publishes them; -1 ends the walk.
     // NEXT_ITEM: whole-warp roles call it converged; single-lane roles call it from their one lane.
@@ -370,7 +412,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                         for (int ti = 0; ti < 9; ti++, ns++) {
                             int tap = TAP_ORDER[pass][ti];
                             mbar_wait(bar(B_WEMPTY + stage), ph ^ 1, P.fault, 0x100 + stage);
-                            if (ns < 600) HZ_TRACE(2000 + ns);
+                            if (ns < 600) { HZ_TRACE(2000 + ns); }
                             if (P.dbg & 4) mbar_arrive(bar(B_WFULL + stage));
                             else {
                                 mbar_expect_tx(bar(B_WFULL + stage), W_BYTES);
@@ -398,7 +440,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 for (int kh = 0; kh < L.nkh; kh++, na++) {
                     mbar_wait(bar(B_AEMPTY + kh), ((kh ? cnt1 : cnt0) & 1u) ^ 1u, P.fault, 0x200 + kh);
                     if (kh) cnt1++; else cnt0++;
-                    if (na < 400) HZ_TRACE(3600 + na);
+                    if (na < 400) { HZ_TRACE(3600 + na); }
                     if (P.dbg & 8) { mbar_arrive(bar(B_AFULL + kh)); continue; }
                     mbar_expect_tx(bar(B_AFULL + kh), KH_BYTES);
                     const uint8_t* src = P.buf[L.in_buf] + ((size_t)tile * L.nkh + kh) * KH_BYTES;
@@ -413,7 +455,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
         if (warp == 12 && !dual) {
             // single-issuer mode (profiling A/B): nothing to do
         } else {
-            IssueCtx c{sBar, sW, sX, tbase, 0u, 0u, P.fault, P.dbg, (blockIdx.x == 0 && lane == 0) ? P.trace : nullptr, 0, warp == 12 ? 1 : 0, dual};
+            IssueCtx c{sBar, sW, sX, tbase, 0u, 0u, P.fault, P.dbg, (blockIdx.x == 0 && lane == 0) ? P.trace : nullptr, 0, 0, warp == 12 ? 1 : 0, dual};
             uint32_t cnt0 = 0, cnt1 = 0;
             int wi = 0, k = 0;                 // wi: work items done (phase of the accumulator units)
             for (;; wi++) {
@@ -435,7 +477,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 }
             }
             // the last hand-over has no taker yet: the warp whose turn would be next consumes it
-            if (dual && c.nstage > 0 && (c.nstage & 1) == c.parity) named_bar_sync(c.parity ? 1 : 2);
+            if (dual && c.nturn > 0 && (c.nturn & 1) == c.parity) named_bar_sync(c.parity ? 1 : 2);
             if (elect_one()) umma_commit(bar(B_DONE));
             __syncwarp();
             mbar_wait(bar(B_DONE), 0, P.fault, 0x600);
@@ -479,10 +521,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                             rv[2 * j + 1] = *reinterpret_cast<const uint4*>(rp + 128);
                         }
                 }
-                if (warp == 4 && nrow < 200) HZ_TRACE(2700 + 4 * nrow);
+                if (warp == 4 && nrow < 200) { HZ_TRACE(2700 + 4 * nrow); }
                 mbar_wait(bar(B_TFULL + unit), use_of(r, wi) & 1, P.fault, 0x700 + unit);
                 tc_fence_after();
-                if (warp == 4 && nrow < 200) HZ_TRACE(2700 + 4 * nrow + 1);
+                if (warp == 4 && nrow < 200) { HZ_TRACE(2700 + 4 * nrow + 1); }
                 uint32_t v[4][16];
                 const uint32_t ta = tbase + ((uint32_t)(q * 32) << 16) + unit * UNIT_COLS + x0 * G;
                 tmem_ld16(ta, v[0]);
@@ -493,7 +535,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(B_TEMPTY + unit));      // the accumulator may be overwritten from here on
-                if (warp == 4 && nrow < 200) HZ_TRACE(2700 + 4 * nrow + 2);
+                if (warp == 4 && nrow < 200) { HZ_TRACE(2700 + 4 * nrow + 2); }
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     if (j == 3 && half) break;
@@ -521,7 +563,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                     *reinterpret_cast<uint4*>(yp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     *reinterpret_cast<uint4*>(yp + 128) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 }
-                if (warp == 4 && nrow < 200) HZ_TRACE(2700 + 4 * nrow + 3);
+                if (warp == 4 && nrow < 200) { HZ_TRACE(2700 + 4 * nrow + 3); }
             }
             if (P.sched && l + 1 < P.n_layers) {
                 // publish the tile's output: generic-proxy stores -> visible at gpu scope and to async-proxy readers
@@ -540,7 +582,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
     tc_fence_before();
     __syncthreads();
     if (warp == 0) HZ_TRACE(1);
-    if (warp == 0 && P.trace && blockIdx.x == 0 && lane == 0) P.trace[3] = globaltimer_ns();
+    if (HZ_TOWER_TRACE && warp == 0 && P.trace && blockIdx.x == 0 && lane == 0) P.trace[3] = globaltimer_ns();
     if (warp == 3) tmem_dealloc(tbase, 512);
 }
 
@@ -656,6 +698,7 @@ int hz_tower_set_debug(int flags) {
 }
 
 int hz_tower_set_trace(unsigned long long* device_buffer_4096) {
+    if (device_buffer_4096 && !HZ_TOWER_TRACE) return HZ_ERR_ARG;   // the time stamps are compiled in with -DHZ_TOWER_TRACE=1 only
     hz::tower::g_trace = device_buffer_4096;
     return HZ_OK;
 }

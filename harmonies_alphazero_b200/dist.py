@@ -68,10 +68,11 @@ def gather_trajectories(traj, dst=None, group=None):
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     dev = traj.states.device
+    # example counts of all ranks: one collective into one tensor and ONE host read (the sizes are needed on the host)
     n = torch.tensor([len(traj)], dtype=torch.int64, device=dev)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n, group=group)
-    counts = [int(c.item()) for c in counts]
+    all_n = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_n, n, group=group)
+    counts = all_n.tolist()
     m = max(counts) if counts else 0
     # one packed row per example: state (32 x i32) | visits (143 x i16 -> 72 x i32) | game_id(2) | z | move
     row = torch.zeros((m, 32 + 72 + 1 + 2 + 1), dtype=torch.int32, device=dev)
@@ -84,9 +85,16 @@ def gather_trajectories(traj, dst=None, group=None):
         row[:k, 104:106] = traj.game_id.contiguous().view(torch.int32).view(k, 2)
         row[:k, 106] = traj.z.contiguous().view(torch.int32)
         row[:k, 107] = traj.move_no.to(torch.int32)
-    rows = [torch.zeros_like(row) for _ in range(world)]
-    dist.all_gather(rows, row, group=group)
-    if dst is not None and rank != dst:
+    if dst is None:
+        buf = torch.empty((world * m, row.shape[1]), dtype=torch.int32, device=dev)     # concatenated form (gloo accepts only this one)
+        dist.all_gather_into_tensor(buf, row, group=group)
+        rows = list(buf.view(world, m, row.shape[1]).unbind(0))
+    elif rank == dst:
+        # a true gather: only the destination receives the other ranks' rows
+        rows = [torch.empty_like(row) for _ in range(world)]
+        dist.gather(row, gather_list=rows, dst=dst, group=group)
+    else:
+        dist.gather(row, gather_list=None, dst=dst, group=group)
         rows, counts = [], []
     parts = [r[:c] for r, c in zip(rows, counts) if c]
     allr = torch.cat(parts) if parts else row[:0]

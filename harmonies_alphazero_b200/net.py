@@ -221,7 +221,7 @@ class InferenceNet:
                 torch.zeros((rows, 143), dtype=torch.float32, device=dev), torch.zeros(rows, dtype=torch.float32, device=dev))
 
     @torch.no_grad()
-    def forward_tiles(self, x0, glob, n, out=None, n_active=None):
+    def forward_tiles(self, x0, glob, n, out=None, n_active=None, tag=0):
         """Leaves already in the T16K image (hz_tree_select, HZ_LAYOUT_T16K): hand-written tower, the
         1x1 head convolutions straight from its T16 output, then the FC heads.  No layout-conversion
         kernels on this path.  n_active: int32 device tensor (one element): only rows 0..n_active-1
@@ -234,10 +234,10 @@ class InferenceNet:
         if out is None:
             out = (torch.empty((n, 143), dtype=torch.float32, device=self.device), torch.empty(n, dtype=torch.float32, device=self.device))
         logits, value = out
-        hc = self._hc.get(n)
+        hc = self._hc.get((n, tag))     # tag: callers running concurrently on different streams keep separate scratch
         if hc is None:
-            hc = self._hc[n] = torch.zeros((n, 105), dtype=torch.float32, device=self.device)
-        x_ptr = self.hand.forward_tiles(x0, n, n_active=n_active)
+            hc = self._hc[(n, tag)] = torch.zeros((n, 105), dtype=torch.float32, device=self.device)
+        x_ptr = self.hand.forward_tiles(x0, n, n_active=n_active, tag=tag)
         lib = _lib.load()
         glob = glob.contiguous()
         na = None if n_active is None else n_active.data_ptr()

@@ -163,7 +163,7 @@ class _Group:
         if getattr(o.net, "tree_eval", False):
             t.fake_eval(self.logits, self.value)       # priors, not logits
         elif self.tiles:
-            o.net.forward_tiles(self.board, self.glob, self.glob.shape[0], out=(self.logits, self.value), n_active=self.n_active[1:2])
+            o.net.forward_tiles(self.board, self.glob, self.glob.shape[0], out=(self.logits, self.value), n_active=self.n_active[1:2], tag=self.lo)
         elif o._net_takes_out:        # InferenceNet writes straight into the static buffers
             o.net(self.board, self.glob, out=(self.logits, self.value))
         else:

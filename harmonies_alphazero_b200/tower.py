@@ -70,12 +70,13 @@ class HandTower:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def _buffers(self, n_pad):
-        b = self._bufs.get(n_pad)
+    def _buffers(self, n_pad, tag=0):
+        """scratch of one caller: callers that run concurrently on different streams pass different tags"""
+        b = self._bufs.get((n_pad, tag))
         if b is None:
             tiles = n_pad // G
             mk = lambda halves: torch.zeros(tiles * halves * KH_BYTES, dtype=torch.uint8, device=self.device)  # noqa: E731
-            b = self._bufs[n_pad] = dict(x0=mk(1), a=mk(2), b=mk(2), c=mk(2),
+            b = self._bufs[(n_pad, tag)] = dict(x0=mk(1), a=mk(2), b=mk(2), c=mk(2),
                                          sched=torch.zeros(self.lib.hz_tower_sched_bytes(n_pad, len(self.blocks)), dtype=torch.uint8, device=self.device),
                                          out=torch.zeros((n_pad, 35, 128), dtype=torch.bfloat16, device=self.device))
         return b
@@ -106,12 +107,12 @@ class HandTower:
         return torch.zeros(n_pad // G * KH_BYTES, dtype=torch.uint8, device=self.device)
 
     @torch.no_grad()
-    def forward_tiles(self, x0, n, n_active=None):
+    def forward_tiles(self, x0, n, n_active=None, tag=0):
         """x0: T16K tiles of n boards.  Returns the address of the T16 tiles holding the tower output
         (one of this object's scratch buffers: valid until the next call with the same n).
         n_active: int32 device tensor (one element) = boards to compute, read on the device."""
         n_pad = (n + G - 1) // G * G
-        buf = self._buffers(n_pad)
+        buf = self._buffers(n_pad, tag)
         x, y, z = buf["a"], buf["b"], buf["c"]
         if self.fused_layers:
             res = ct.c_void_p()

@@ -362,7 +362,9 @@ int hz_tower_set_max_ctas(int max_ctas);
 int hz_tower_set_debug(int flags);
 /* Profiling: a device buffer of 4096 uint64 (or NULL to switch off) into which CTA 0 of every
  * following hz_tower_conv3x3 launch writes SM-clock timestamps of its producer / MMA / epilogue
- * roles (slot map in csrc/hz_tower.cu). */
+ * roles (slot map in csrc/hz_tower.cu).  The time stamps are compiled in only with
+ * -DHZ_TOWER_TRACE=1 (they cost instruction-cache space); otherwise a non-NULL buffer is refused
+ * with HZ_ERR_ARG. */
 int hz_tower_set_trace(unsigned long long *device_buffer_4096);
 
 /* NHWC bf16 [n,35,channels] -> tiles.  kmajor != 0: T16K (channels % 8 == 0, <= 64; missing

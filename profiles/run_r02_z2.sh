@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_tower.py -q -m gpu -x 2>&1 | tail -n 3
+echo "== loop build (NR-templated)"; timeout 300 python profiles/mcts_step.py 2>&1 | tail -n 1
+timeout 300 python profiles/mcts_step.py 2>&1 | tail -n 1
+HZ_NVCC_EXTRA="-DHZ_TOWER_TRACE=1" python -m harmonies_alphazero_b200.build --force > gpurun_out/z_build.log 2>&1
+timeout 300 python profiles/tower_trace.py --json gpurun_out/tower_trace_loop2.json 2>&1 | tail -n 1
+HZ_NVCC_EXTRA="-DHZ_TOWER_UNROLLED=1" python -m harmonies_alphazero_b200.build --force >> gpurun_out/z_build.log 2>&1
+echo "== unrolled stage bodies, k loop rolled"; timeout 300 python profiles/mcts_step.py 2>&1 | tail -n 1
+timeout 300 python profiles/mcts_step.py 2>&1 | tail -n 1

@@ -36,7 +36,7 @@ def _run_group(mods, roots, skeys, sims, cpuct, noise, eps, key_mode=1):
 
 
 def test_golden_reference_searches(mods):
-    """69 searches run by the reference's own MCTS.py: N, W, P, node/edge counts, pi, move."""
+    """84 searches run by the reference's own MCTS.py: N, W, P, node/edge counts, pi, move."""
     g = load_golden("mcts")
     groups = {}
     for i in range(len(g["sims"])):

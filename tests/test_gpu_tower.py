@@ -339,3 +339,43 @@ def test_self_play_with_live_prefix_compaction_equals_plain(tw):
         out.append((t.states[order].cpu(), t.visits[order].cpu(), t.z[order].cpu(), t.stats["searched_slots"], t.stats["move_steps"]))
     assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
     assert out[1][3] < out[0][3] and out[1][3] == len(out[1][0])      # compacted: exactly one searched slot per example
+
+
+def test_search_is_a_function_of_the_priors_whichever_tower_produced_them(tw):
+    """the priors and values the hand-written path produced during a search are captured
+    per simulation and fed to a second set of trees that encodes its leaves for the cuDNN path: visit counts, W
+    and P of the roots are bit-identical (the tree kernels see the evaluator only through (policy, value)), and
+    a cuDNN-evaluated search from the same roots agrees with the hand-evaluated one on the bf16-level."""
+    from harmonies_alphazero_b200 import batched as hb
+    from harmonies_alphazero_b200 import net as hnet
+    from harmonies_alphazero_b200 import tree as htree
+
+    torch.manual_seed(1)
+    model = hnet.AlphaZeroNet.from_config(hnet.DEFAULT_MODEL_CONFIG).eval()
+    hand = hnet.InferenceNet(model, device="cuda", tower="hand")
+    lib = hnet.InferenceNet(model, device="cuda", tower="cudnn")
+    n, sims = 96, 24
+    st = hb.init_states(n, seed=31)
+    hb.playout(st, max_steps=11)
+    t1 = htree.BatchedMCTS(n, sims)
+    t1.reset(st)
+    board, glob, logits, value = hand.leaf_buffers(n)
+    captured = []
+    for _ in range(sims):
+        t1.select(2.0, board, glob, dtype=torch.bfloat16, tiles=True)
+        hand.forward_tiles(board, glob, n, out=(logits, value))
+        captured.append((logits.clone(), value.clone()))
+        t1.expand_backup(logits, value, is_logits=True)
+    t2 = htree.BatchedMCTS(n, sims)
+    t2.reset(st)
+    b2, g2, l2, v2 = lib.leaf_buffers(n)
+    worst = 0.0
+    for lg, vl in captured:
+        t2.select(2.0, b2, g2, dtype=torch.bfloat16, channels_last=True, pad40=b2.shape[1] == 40)
+        lib(b2, g2, out=(l2, v2))                      # the cuDNN path on the same leaves
+        worst = max(worst, float((torch.softmax(l2, 1) - torch.softmax(lg, 1)).abs().max()), float((v2 - vl).abs().max()))
+        t2.expand_backup(lg, vl, is_logits=True)       # ... but the tree is fed the captured values
+    t1.check_status(); t2.check_status()
+    N1, W1, P1, _ = t1.root_edges(); N2, W2, P2, _ = t2.root_edges()
+    assert torch.equal(N1, N2) and torch.equal(W1, W2) and torch.equal(P1, P2)
+    assert worst < 0.03          # same leaves, two towers: bf16-level agreement of priors and values
