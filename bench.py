@@ -159,7 +159,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def headline_roofline(n_games, steps_per_launch, launch_s, clocks, pk, pk_src):
+def headline_roofline(n_games, steps_per_launch, launch_s, clocks, pk, pk_src, at4=None):
     """hz::k_playout keeps a game's state in registers for all of its ~62 steps, so DRAM sees one 128-byte
     record per GAME and the kernel is bound by instruction issue, not HBM.  The roofline is therefore the
     issue roofline (warp instructions per second against SMs x 4 schedulers x clock), from the warp-instruction
@@ -179,7 +179,13 @@ def headline_roofline(n_games, steps_per_launch, launch_s, clocks, pk, pk_src):
     sm_mhz = (clocks or {}).get("sm_mhz") or pk.get("sm_max_mhz") or 1965.0
     peak = 148 * 4 * sm_mhz * 1e6 / 1e9
     ach = winst / launch_s / 1e9
-    return {"bound": "issue", "achieved": ach, "peak": peak, "unit": "Gwarp-inst/s", "frac": ach / peak,
+    if at4:
+        # warp instructions scale with the games (same kernel, same game-length distribution): 4x the counted launch
+        a4 = 4.0 * winst / (at4["us_per_launch"] * 1e-6) / 1e9
+        at4 = dict(at4, achieved=a4, frac=a4 / peak,
+                   note="the same kernel with 4x the games per launch (14 warps per scheduler instead of 3.5); warp instructions "
+                        "taken as 4x the counted 65,536-game launch")
+    return {"bound": "issue", "achieved": ach, "peak": peak, "unit": "Gwarp-inst/s", "frac": ach / peak, "at_4x_batch": at4,
             "traffic": m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"],
             "kernel": "hz::k_playout", "peak_source": f"148 SMs x 4 schedulers x {sm_mhz:.0f} MHz (SM clock sampled during the timed region)",
             "warp_inst_per_launch": winst, "active_lanes_per_warp_inst": m["smsp__thread_inst_executed.sum"] / winst,
@@ -555,6 +561,29 @@ def run_b200(args):
     ms_max, steps_all, launches_all = float(t.item()), int(s[0].item()), int(s[1].item())
     value = steps_all / (ms_max * 1e-3)
 
+    # ---- the same kernel at 4x the batch (rank 0, 3 launches): how much of the issue roofline it reaches when every
+    # scheduler has 14 warps instead of 3.5 (the configuration's 65,536 games are the only parallelism it offers)
+    at4 = None
+    if rank == 0 and n == 65536:
+        n4 = 4 * n
+        steps4 = torch.empty(n4, dtype=torch.int32, device=dev)
+        tot4 = torch.zeros(1, dtype=torch.int64, device=dev)
+        for _ in range(2):
+            hb.playout(hb.init_states(n4, device=dev, seed=5, first_id=0), steps=steps4, total=tot4)
+        tot4.zero_()
+        ms4 = 0.0
+        for k in range(3):
+            st4 = hb.init_states(n4, device=dev, seed=2000 + k, first_id=0)
+            flush.fill_(k)
+            a4, b4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a4.record(stream)
+            hb.playout(st4, steps=steps4, total=tot4)
+            b4.record(stream)
+            torch.cuda.synchronize()
+            ms4 += a4.elapsed_time(b4)
+        at4 = {"games_per_launch": n4, "us_per_launch": ms4 / 3 * 1e3, "steps_per_s": int(tot4.item()) / (ms4 * 1e-3)}
+        del steps4, st4
+
     # ---- end to end through the public host-buffer API (HostPlayout.run): every step copies its
     # inputs from pinned host memory (H2D) and reads the final records back (D2H) inside the
     # timed region; the call pipelines 4 chunks on 4 streams so copies overlap the kernel
@@ -676,7 +705,7 @@ def run_b200(args):
                              "api": "HostPlayout.run_many: K batches of 128-byte records in and out, pipelined over 3 device buffers (PCIe-bound)"},
         "gpu_launches": launches_all,
         "clocks": clocks,
-        "roofline": headline_roofline(n, steps_done / K, avg_launch_s, clocks, pk, pk_src),
+        "roofline": headline_roofline(n, steps_done / K, avg_launch_s, clocks, pk, pk_src, at4),
         "wall_s": wall,
         "unfused": {"value": unfused_steps / (unfused_ms * 1e-3), "unit": UNIT, "launches": 76 * 3, "ms": unfused_ms,
                     "achieved_GBps": unfused_steps * ALGO_BYTES_PER_STEP / (unfused_ms * 1e-3) / 1e9,
