@@ -63,10 +63,67 @@ constexpr int B_WFULL = 0, B_WEMPTY = NSTAGE, B_AFULL = 2 * NSTAGE, B_AEMPTY = 2
 
 // tap = ky*3 + kx (dy = ky-1, dx = kx-1).  Within a dy group the dx = 0 tap comes first: the first
 // MMA into a row accumulator overwrites it and must cover all 112 columns.
-// pass 0 (rows 0,1,2): dy = +1, 0, -1  -> row 0 (no dy = -1) completes after two thirds of the pass
-// pass 1 (rows 3,4)  : dy = -1, 0, +1  -> row 4 (no dy = +1) completes after two thirds of the pass
-__constant__ int8_t TAP_ORDER[2][9] = {{7, 6, 8, 4, 3, 5, 1, 0, 2}, {1, 0, 2, 4, 3, 5, 7, 6, 8}};
+//
+// A tile's five board rows do not fit the four accumulator units at once, so a work item is a sequence of
+// SEGMENTS, each a list of taps applied to a range of rows, run per channel half (segment-outer, half-inner):
+//   HZ_TOWER_SPLIT41 = 0 (default), rows {0,1,2} + {3,4}, 9 taps each:
+//     seg 0: rows 0..2, dy = +1, 0, -1  -> row 0 (no dy = -1 tap) completes after two thirds of the segment
+//     seg 1: rows 3..4, dy = -1, 0, +1  -> row 4 (no dy = +1 tap) completes after two thirds of the segment
+//     so the unit rows 0 and 4 share is always drained before its next tenant arrives.
+//   HZ_TOWER_SPLIT41 = 1, rows {0,1,2,3} + {4}: seg 0: rows 0..3, dy = 0, +1 (6 taps); seg 1: rows 0..3, dy = -1 (3 taps);
+//     seg 2: row 4, dy = -1, 0 (6 taps).  30 weight stages per item instead of 36 and 3-4 rows per weight tile in segments
+//     0/1 (tensor-pipe bound: 830 / 640 cycles per stage in the role timeline), but the single-row segment's stages are
+//     4 MMAs (~210 tensor cycles) against a weight ring that delivers one 16 KB stage per >= 400 cycles (5 stages in flight,
+//     ~2,000 cycles from issue to arrival under load): measured 415-420 us against 394 us for the default.
+#ifndef HZ_TOWER_SPLIT41
+#define HZ_TOWER_SPLIT41 0
+#endif
+#if HZ_TOWER_SPLIT41
+constexpr int NSEG = 3;
+__host__ __device__ constexpr int seg_nt(int seg) { return seg == 1 ? 3 : 6; }
+__host__ __device__ constexpr int seg_r0(int seg) { return seg == 2 ? 4 : 0; }
+__host__ __device__ constexpr int seg_r1(int seg) { return seg == 2 ? 5 : 4; }
+__host__ __device__ constexpr int tap_at(int seg, int ti) {
+    constexpr int O[3][6] = {{4, 3, 5, 7, 6, 8}, {1, 0, 2, 0, 0, 0}, {1, 0, 2, 4, 3, 5}};
+    return O[seg][ti];
+}
+__constant__ int8_t SEG_NT[3] = {6, 3, 6};
+__constant__ int8_t SEG_TAPS[3][9] = {{4, 3, 5, 7, 6, 8, 0, 0, 0}, {1, 0, 2, 0, 0, 0, 0, 0, 0}, {1, 0, 2, 4, 3, 5, 0, 0, 0}};
+__constant__ int8_t EPI_ORDER[5] = {0, 1, 2, 3, 4};  // order in which the row accumulators complete
+#else
+constexpr int NSEG = 2;
+__host__ __device__ constexpr int seg_nt(int) { return 9; }
+__host__ __device__ constexpr int seg_r0(int seg) { return seg ? 3 : 0; }
+__host__ __device__ constexpr int seg_r1(int seg) { return seg ? 5 : 3; }
+__host__ __device__ constexpr int tap_at(int seg, int ti) {
+    constexpr int O[2][9] = {{7, 6, 8, 4, 3, 5, 1, 0, 2}, {1, 0, 2, 4, 3, 5, 7, 6, 8}};
+    return O[seg][ti];
+}
+__constant__ int8_t SEG_NT[3] = {9, 9, 0};
+__constant__ int8_t SEG_TAPS[3][9] = {{7, 6, 8, 4, 3, 5, 1, 0, 2}, {1, 0, 2, 4, 3, 5, 7, 6, 8}, {0, 0, 0, 0, 0, 0, 0, 0, 0}};
 __constant__ int8_t EPI_ORDER[5] = {0, 1, 2, 4, 3};  // order in which the row accumulators complete
+#endif
+// does stage (seg, ti) multiply into board row r?  (rows of the segment whose source row r + dy is on the board)
+__host__ __device__ constexpr bool touches(int seg, int ti, int r) {
+    const int dy = tap_at(seg, ti) / 3 - 1;
+    return r >= seg_r0(seg) && r < seg_r1(seg) && r + dy >= 0 && r + dy < BROWS;
+}
+// is (seg, ti) the first / the last stage of the item's sequence that touches row r?  (for one channel half; the first
+// touch of the first half overwrites the accumulator, the last touch of the last half completes it)
+__host__ __device__ constexpr bool first_touch(int seg, int ti, int r) {
+    if (!touches(seg, ti, r)) return false;
+    for (int s2 = 0; s2 <= seg; s2++)
+        for (int t2 = 0; t2 < (s2 == seg ? ti : seg_nt(s2)); t2++)
+            if (touches(s2, t2, r)) return false;
+    return true;
+}
+__host__ __device__ constexpr bool last_touch(int seg, int ti, int r) {
+    if (!touches(seg, ti, r)) return false;
+    for (int s2 = seg; s2 < NSEG; s2++)
+        for (int t2 = (s2 == seg ? ti + 1 : 0); t2 < seg_nt(s2); t2++)
+            if (touches(s2, t2, r)) return false;
+    return true;
+}
 // accumulator unit of board row r and how many times the unit has been used before (tile iteration it)
 __device__ __forceinline__ int unit_of(int r) { return r == 4 ? 0 : r; }
 __device__ __forceinline__ int use_of(int r, int it) { return r == 0 ? 2 * it : r == 4 ? 2 * it + 1 : it; }
@@ -185,14 +242,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
 // a handful of instructions per MMA: the whole warp runs the (warp-uniform) control flow, taps /
 // rows / k-steps are compile-time, descriptors are a 32-bit add on a precomputed low word, and only
 // the tcgen05 instructions themselves sit behind elect.sync.
-__host__ __device__ constexpr int tap_at(int pass, int ti) {
-    constexpr int O[2][9] = {{7, 6, 8, 4, 3, 5, 1, 0, 2}, {1, 0, 2, 4, 3, 5, 7, 6, 8}};
-    return O[pass][ti];
-}
-__host__ __device__ constexpr int last_tap_of(int r) {
-    constexpr int L[5] = {5, 2, 2, 8, 5};
-    return L[r];
-}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -209,10 +258,11 @@ __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((
 template <bool KMAJOR, int PASS, int TI, int K0, int K1>
 __device__ __forceinline__ void issue_stage(uint32_t a_lo, uint32_t b_lo, uint32_t tbase, uint32_t acc_first) {
     constexpr int tap = tap_at(PASS, TI), dy = tap / 3 - 1, dx = tap % 3 - 1;
-    constexpr int r0 = PASS ? 3 : 0, r1 = PASS ? 5 : 3;
+    constexpr int r0 = seg_r0(PASS), r1 = seg_r1(PASS);
     constexpr uint32_t idesc = idesc_bf16_f32(128, dx ? 96 : 112) | (KMAJOR ? 0u : (1u << 16));
-    // rows of the pass this tap touches: [ra, rb) (always a contiguous range)
-    constexpr int ra = (r0 + dy < 0) ? r0 + 1 : r0, rb = (r1 - 1 + dy >= BROWS) ? r1 - 1 : r1;
+    // rows of the segment this tap touches: [ra, rb) (always a contiguous range)
+    constexpr int ra = (r0 + dy < 0) ? -dy : r0, rb = (r1 - 1 + dy >= BROWS) ? BROWS - dy : r1;
+    static_assert(ra < rb, "a stage without rows");
     // the k loop is NOT unrolled: with it unrolled the issue code of a residual layer is 41 KB, more than the instruction
     // cache keeps beside the epilogue, and every change of pass stalled both issuers on instruction fetch (role timeline,
     // profiles/tower_trace.py: 2-14 thousand cycles at the first stage of pass 1 of every work item; tower 435 -> 400 us).
@@ -228,7 +278,7 @@ __device__ __forceinline__ void issue_stage(uint32_t a_lo, uint32_t b_lo, uint32
             const uint32_t boff = KMAJOR ? (uint32_t)((cell0 * (G * 128) + k * 32) >> 4) : (uint32_t)((k * 2 * KG_BYTES + cell0 * (G * 16)) >> 4);
             const uint32_t d = tbase + (uint32_t)(unit_of(r) * UNIT_COLS + (dx < 0 ? G : 0));
             const uint64_t db = desc64(b_lo + boff, KMAJOR ? DESC_HI_SW128 : DESC_HI_T16);
-            const uint32_t acc = (TI == 0 && k == 0) ? acc_first : 1u;
+            const uint32_t acc = (k == 0 && first_touch(PASS, TI, r)) ? acc_first : 1u;
             // the rows share the weight tile: it is read from shared memory for the first one only
             if (rb - ra == 1 || !HZ_TOWER_COLLECTOR) umma_bf16_coll<COLL_DISCARD>(d, da, db, idesc, acc);
             else if (r == ra) umma_bf16_coll<COLL_FILL>(d, da, db, idesc, acc);
@@ -253,20 +303,21 @@ struct StageLoop {
     // runs stages TI..8 of a pass for one channel half; each stage is issued by the warp whose parity matches
     template <class Ctx>
     static __device__ __forceinline__ void run(Ctx& c, int kh, int it, bool last_kh) {
-        constexpr int tap = tap_at(PASS, TI);
-        constexpr int r0 = PASS ? 3 : 0, r1 = PASS ? 5 : 3;
+        constexpr int NT = seg_nt(PASS);
+        constexpr int r0 = seg_r0(PASS), r1 = seg_r1(PASS);
         // a TURN = the consecutive stages one issuer runs between two hand-overs (HZ_TOWER_TURN_P0 / _P1 stages of the pass,
         // counted across its channel halves; the pass's last stage always ends a turn)
-        constexpr int T = PASS ? HZ_TOWER_TURN_P1 : HZ_TOWER_TURN_P0;
-        const int idx = kh * 9 + TI;
-        const bool first_in_turn = T == 1 || idx % T == 0, last_in_turn = T == 1 || idx % T == T - 1 || (last_kh && TI == 8);
+        constexpr int T = PASS ? HZ_TOWER_TURN_P1 : HZ_TOWER_TURN_P0;   // (segment 0 / later segments)
+        const int idx = kh * NT + TI;
+        const bool first_in_turn = T == 1 || idx % T == 0, last_in_turn = T == 1 || idx % T == T - 1 || (last_kh && TI == NT - 1);
         const bool mine = !c.dual || ((c.nturn & 1) == c.parity);
         if (mine) {
             HZ_CTRACE(16 + 3 * c.nstage);
             mbar_wait(c.bar0 + 8u * (B_WFULL + c.stage), c.ph, c.fault, 0x400 + c.stage);
-            if (TI == 0 && kh == 0) {   // first touch of the pass's accumulators for this tile: previous tenants must be drained
+            if (kh == 0) {   // first touch of a row's accumulator for this tile: the unit's previous tenant must be drained
 #pragma unroll
-                for (int r = r0; r < r1; r++) mbar_wait(c.bar0 + 8u * (B_TEMPTY + unit_of(r)), (use_of(r, it) & 1) ^ 1, c.fault, 0x500 + r);
+                for (int r = r0; r < r1; r++)
+                    if (first_touch(PASS, TI, r)) mbar_wait(c.bar0 + 8u * (B_TEMPTY + unit_of(r)), (use_of(r, it) & 1) ^ 1, c.fault, 0x500 + r);
             }
             // everything the first MMA needs is computed before the hand-over is awaited
             const bool lead = elect_one();
@@ -287,9 +338,9 @@ struct StageLoop {
                 if (last_kh) {
 #pragma unroll
                     for (int r = r0; r < r1; r++)
-                        if (tap == last_tap_of(r)) umma_commit(c.bar0 + 8u * (B_TFULL + unit_of(r)));
+                        if (last_touch(PASS, TI, r)) umma_commit(c.bar0 + 8u * (B_TFULL + unit_of(r)));
                 }
-                if (PASS == 1 && TI == 8) umma_commit(c.bar0 + 8u * (B_AEMPTY + kh));   // the tile's channel half is no longer read
+                if (PASS == NSEG - 1 && TI == NT - 1) umma_commit(c.bar0 + 8u * (B_AEMPTY + kh));   // the tile's channel half is no longer read
             }
             __syncwarp();
             HZ_CTRACE(16 + 3 * c.nstage + 2);
@@ -297,7 +348,7 @@ struct StageLoop {
         c.nstage++;
         if (last_in_turn) c.nturn++;
         if (++c.stage == NSTAGE) { c.stage = 0; c.ph ^= 1; }
-        if constexpr (TI < 8) StageLoop<KMAJOR, PASS, TI + 1>::run(c, kh, it, last_kh);
+        if constexpr (TI < NT - 1) StageLoop<KMAJOR, PASS, TI + 1>::run(c, kh, it, last_kh);
     }
 };
 
@@ -407,10 +458,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 if (item < 0) break;
                 const Layer& L = P.layers[item / n_tiles];
                 const int nkh = L.nkh;
-                for (int pass = 0; pass < 2; pass++)
+                for (int seg = 0; seg < NSEG; seg++)
                     for (int kh = 0; kh < nkh; kh++)
-                        for (int ti = 0; ti < 9; ti++, ns++) {
-                            int tap = TAP_ORDER[pass][ti];
+                        for (int ti = 0; ti < SEG_NT[seg]; ti++, ns++) {
+                            int tap = SEG_TAPS[seg][ti];
                             mbar_wait(bar(B_WEMPTY + stage), ph ^ 1, P.fault, 0x100 + stage);
                             if (ns < 600) { HZ_TRACE(2000 + ns); }
                             if (P.dbg & 4) mbar_arrive(bar(B_WFULL + stage));
@@ -474,6 +525,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 for (int kh = 0; kh < nkh; kh++) {
                     if (kmajor) StageLoop<true, 1, 0>::run(c, kh, wi, kh == nkh - 1);
                     else StageLoop<false, 1, 0>::run(c, kh, wi, kh == nkh - 1);
+                }
+                if constexpr (NSEG > 2) {
+                    for (int kh = 0; kh < nkh; kh++) {
+                        if (kmajor) StageLoop<true, NSEG - 1, 0>::run(c, kh, wi, kh == nkh - 1);
+                        else StageLoop<false, NSEG - 1, 0>::run(c, kh, wi, kh == nkh - 1);
+                    }
                 }
             }
             // the last hand-over has no taker yet: the warp whose turn would be next consumes it

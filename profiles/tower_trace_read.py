@@ -12,10 +12,12 @@ st = [(rel(t[16 + 3 * i]), rel(t[16 + 3 * i + 1]), rel(t[16 + 3 * i + 2])) for i
 w = [rel(t[2000 + i]) for i in range(600) if t[2000 + i]]
 act = [rel(t[3600 + i]) for i in range(400) if t[3600 + i]]
 rows = [tuple(rel(t[2700 + 4 * j + k]) for k in range(4)) for j in range(200) if t[2700 + 4 * j + 3]]
-# stem item has 18 stages (nkh = 1), the others 36
-bounds = [0, 18]
-while bounds[-1] + 36 <= len(st):
-    bounds.append(bounds[-1] + 36)
+# stages per channel half: 15 with the 4+1 row split (default build), 18 with 3+2; the stem item has one half
+SPH = int(sys.argv[2]) if len(sys.argv) > 2 else 15
+NS = 2 * SPH
+bounds = [0, SPH]
+while bounds[-1] + NS <= len(st):
+    bounds.append(bounds[-1] + NS)
 print("items traced", len(bounds) - 1)
 tot_span = tot_gap = 0
 for k in range(len(bounds) - 1):
@@ -35,7 +37,7 @@ lead = [st[i][1] - w[i] for i in range(min(len(st), len(w)))]
 print("  min", min(lead), "avg", sum(lead) / len(lead), "max", max(lead))
 print("stages of item 3 (wait, issue, period):")
 a = bounds[3]
-for i in range(a, a + 36):
+for i in range(a, a + NS):
     print("  ", i - a, st[i][1] - st[i][0], st[i][2] - st[i][1], st[i][2] - st[i - 1][2], "w_issue->ready", st[i][1] - w[i])
 print("epilogue rows (wait, ld, work):")
 for r in rows[10:30]:
