@@ -47,7 +47,7 @@ SIGNATURES = {
     "hz_net_head_conv_t16": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "hz_net_heads_fc": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "hz_net_head_conv_t16_active": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
-    "hz_net_heads_fc_active": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
+    "hz_net_heads_fc_active": (_i, [_vp, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "hz_tower_tile_bytes": (C.c_size_t, [_i64, _i]),
     "hz_tower_set_max_ctas": (_i, [_i]),
     "hz_tower_set_debug": (_i, [_i]),
@@ -57,6 +57,7 @@ SIGNATURES = {
     "hz_tower_sched_bytes": (C.c_size_t, [_i64, _i]),
     "hz_tower_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "hz_tower_forward_active": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "hz_tower_forward_heads": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hz_tower_conv3x3": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
 }
 

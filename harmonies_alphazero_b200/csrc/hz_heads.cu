@@ -220,7 +220,7 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 lo, __nv_bfloat16 hi
 __global__ void __launch_bounds__(FTPB, 1) k_heads_p(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ glob,
                                                      int64_t n, HeadParams P, float* __restrict__ logits,
                                                      float* __restrict__ value, const float* __restrict__ hc,
-                                                     const int* __restrict__ n_active) {
+                                                     const int* __restrict__ n_active, int hc_tiled) {
     extern __shared__ __align__(16) float smem[];
     if (n_active) n = min(n, (int64_t)max(*n_active, 0));   // only the active prefix of the rows (hz_tree_set_active)
     float* s_wp = smem;                      // [112][143] (+ slack)
@@ -260,7 +260,9 @@ __global__ void __launch_bounds__(FTPB, 1) k_heads_p(const __nv_bfloat16* __rest
         if (hc) {
             for (int i = t; i < cnt * 3 * CELLS; i += FTPB) {
                 int p = i / (3 * CELLS), j = i - 3 * CELLS * p;
-                float v = hc[(base + p) * (3 * CELLS) + j];
+                // hc_tiled: the layout the tower's head item writes: [tile of 16 boards][filter * 35 + cell][board in tile]
+                const int64_t bd = base + p;
+                float v = hc_tiled ? hc[(bd >> 4) * (3 * CELLS * 16) + j * 16 + (bd & 15)] : hc[bd * (3 * CELLS) + j];
                 if (j < 2 * CELLS) s_pin[p * PIN + j] = v;
                 else s_vin[p * 80 + j - 2 * CELLS] = v;
             }
@@ -474,10 +476,10 @@ extern "C" int hz_net_head_conv_t16_active(const void* x_tiles, int64_t n, const
 extern "C" int hz_net_heads_fc(const float* head_conv, const void* glob, int64_t n, int H, const float* w_pol_t, const float* b_pol,
                                const float* w_v1_t, const float* b_v1, const float* w_v2, float b_v2, float* logits, float* value,
                                void* stream) {
-    return hz_net_heads_fc_active(head_conv, glob, n, nullptr, H, w_pol_t, b_pol, w_v1_t, b_v1, w_v2, b_v2, logits, value, stream);
+    return hz_net_heads_fc_active(head_conv, glob, n, nullptr, 0, H, w_pol_t, b_pol, w_v1_t, b_v1, w_v2, b_v2, logits, value, stream);
 }
 
-extern "C" int hz_net_heads_fc_active(const float* head_conv, const void* glob, int64_t n, const int32_t* n_active, int H,
+extern "C" int hz_net_heads_fc_active(const float* head_conv, const void* glob, int64_t n, const int32_t* n_active, int hc_tiled, int H,
                                       const float* w_pol_t, const float* b_pol, const float* w_v1_t, const float* b_v1,
                                       const float* w_v2, float b_v2, float* logits, float* value, void* stream) {
     if (n == 0) return HZ_OK;
@@ -495,7 +497,7 @@ extern "C" int hz_net_heads_fc_active(const float* head_conv, const void* glob, 
     }
     int64_t fgroups = (n + hz::FG - 1) / hz::FG;
     int fgrid = (int)(fgroups < 148 ? fgroups : 148);
-    hz::k_heads_p<<<fgrid, hz::FTPB, hz::FSMEM, (cudaStream_t)stream>>>(nullptr, (const __nv_bfloat16*)glob, n, P, logits, value, head_conv, n_active);
+    hz::k_heads_p<<<fgrid, hz::FTPB, hz::FSMEM, (cudaStream_t)stream>>>(nullptr, (const __nv_bfloat16*)glob, n, P, logits, value, head_conv, n_active, hc_tiled);
     return hz_launched(1);
 }
 
@@ -521,7 +523,7 @@ extern "C" int hz_net_heads(const void* x, const void* glob, int64_t n, int C, i
         int64_t fgroups = (n + hz::FG - 1) / hz::FG;
         int fgrid = (int)(fgroups < 148 ? fgroups : 148);
         hz::k_heads_p<<<fgrid, hz::FTPB, hz::FSMEM, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)glob,
-                                                                            n, P, logits, value, nullptr, nullptr);
+                                                                            n, P, logits, value, nullptr, nullptr, 0);
         return hz_launched(1);
     }
     size_t smem = sizeof(float) * (size_t)(3 * C + hz::HP * hz::PIN + hz::HP * 80 + hz::HP * 8);

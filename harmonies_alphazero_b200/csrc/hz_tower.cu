@@ -137,6 +137,11 @@ struct Layer {
     const float* bias;     // [128]
     int in_buf, res_buf, out_buf;   // indices into Params::buf; res_buf < 0: no residual
     int nkh, kmajor, relu; // input channel halves; input image T16K (stem) or T16
+    // head != 0: the 1x1 head convolutions (model.py:340-343,349-351) as ONE tap: w = [nkh][128][128 B] with rows 0..2 the
+    // bf16 high parts of the three head filters and rows 3..5 their low parts (w = hi + lo: fp32-weight accuracy), bias[3],
+    // output relu(conv + bias) as fp32 into head_out[tile][filter 0..2][cell][board] (1,680 floats per tile)
+    int head;
+    float* head_out;
 };
 // One launch runs layers[0..n_layers) for all tiles.  Work item i = (layer i / n_tiles, tile i % n_tiles);
 // boards are independent, so item (l, t) depends on item (l-1, t) only.  With `sched` the CTAs take items
@@ -352,6 +357,61 @@ struct StageLoop {
     }
 };
 
+// the head item's stages: one tap (dy = dx = 0) over the rows {0,1,2} then {3,4}, per channel half; same protocol as StageLoop
+template <int HSEG>
+struct HeadStage {
+    template <class Ctx>
+    static __device__ __forceinline__ void run(Ctx& c, int kh, int it, bool last_kh) {
+        constexpr int r0 = HSEG ? 3 : 0, r1 = HSEG ? 5 : 3;
+        const bool mine = !c.dual || ((c.nturn & 1) == c.parity);
+        if (mine) {
+            mbar_wait(c.bar0 + 8u * (B_WFULL + c.stage), c.ph, c.fault, 0x400 + c.stage);
+            if (kh == 0) {
+#pragma unroll
+                for (int r = r0; r < r1; r++) mbar_wait(c.bar0 + 8u * (B_TEMPTY + unit_of(r)), (use_of(r, it) & 1) ^ 1, c.fault, 0x500 + r);
+            }
+            const bool lead = elect_one();
+            const uint32_t a_lo = DESC_LO_SW128 | ((c.sW + c.stage * W_BYTES) >> 4);
+            const uint32_t b_lo = DESC_LO_T16 | ((c.sX + (uint32_t)kh * KH_BYTES) >> 4);
+            const uint32_t acc0 = kh == 0 ? 0u : 1u;
+            if (c.dual && c.nturn > 0) named_bar_sync(c.parity ? 1 : 2);
+            tc_fence_after();
+            if (lead && !(c.dbg & 1)) {
+                constexpr uint32_t idesc = idesc_bf16_f32(128, 112) | (1u << 16);
+#pragma unroll 1
+                for (int k = 0; k < 4; k++) {
+                    const uint64_t da = desc64(a_lo + (uint32_t)(k * 2), DESC_HI_SW128);
+#pragma unroll
+                    for (int r = r0; r < r1; r++) {
+                        const uint32_t boff = (uint32_t)((k * 2 * KG_BYTES + r * BCOLS * (G * 16)) >> 4);
+                        const uint32_t d = c.tbase + (uint32_t)(unit_of(r) * UNIT_COLS);
+                        const uint64_t db = desc64(b_lo + boff, DESC_HI_T16);
+                        const uint32_t acc = k == 0 ? acc0 : 1u;
+                        if (!HZ_TOWER_COLLECTOR) umma_bf16_coll<COLL_DISCARD>(d, da, db, idesc, acc);
+                        else if (r == r0) umma_bf16_coll<COLL_FILL>(d, da, db, idesc, acc);
+                        else if (r == r1 - 1) umma_bf16_coll<COLL_LASTUSE>(d, da, db, idesc, acc);
+                        else umma_bf16_coll<COLL_USE>(d, da, db, idesc, acc);
+                    }
+                }
+            }
+            __syncwarp();
+            if (c.dual) named_bar_arrive(c.parity ? 2 : 1);
+            if (lead) {
+                umma_commit(c.bar0 + 8u * (B_WEMPTY + c.stage));
+                if (last_kh) {
+#pragma unroll
+                    for (int r = r0; r < r1; r++) umma_commit(c.bar0 + 8u * (B_TFULL + unit_of(r)));
+                }
+                if (HSEG == 1) umma_commit(c.bar0 + 8u * (B_AEMPTY + kh));
+            }
+            __syncwarp();
+        }
+        c.nstage++;
+        c.nturn++;
+        if (++c.stage == NSTAGE) { c.stage = 0; c.ph ^= 1; }
+    }
+};
+
 struct IssueCtx {
     uint32_t bar0, sW, sX, tbase, stage, ph;
     unsigned int* fault;
@@ -458,10 +518,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 if (item < 0) break;
                 const Layer& L = P.layers[item / n_tiles];
                 const int nkh = L.nkh;
-                for (int seg = 0; seg < NSEG; seg++)
+                const int nseg = L.head ? 2 : NSEG;
+                for (int seg = 0; seg < nseg; seg++)
                     for (int kh = 0; kh < nkh; kh++)
-                        for (int ti = 0; ti < SEG_NT[seg]; ti++, ns++) {
-                            int tap = SEG_TAPS[seg][ti];
+                        for (int ti = 0; ti < (L.head ? 1 : SEG_NT[seg]); ti++, ns++) {
+                            int tap = L.head ? 0 : SEG_TAPS[seg][ti];
                             mbar_wait(bar(B_WEMPTY + stage), ph ^ 1, P.fault, 0x100 + stage);
                             if (ns < 600) { HZ_TRACE(2000 + ns); }
                             if (P.dbg & 4) mbar_arrive(bar(B_WFULL + stage));
@@ -516,6 +577,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 const Layer& L = P.layers[item / n_tiles];
                 const int nkh = L.nkh;
                 const bool kmajor = L.kmajor != 0;
+                if (L.head) {
+                    for (int kh = 0; kh < nkh; kh++) {
+                        mbar_wait(bar(B_AFULL + kh), (kh ? cnt1 : cnt0) & 1u, P.fault, 0x300 + kh);
+                        if (kh) cnt1++; else cnt0++;
+                        HeadStage<0>::run(c, kh, wi, kh == nkh - 1);
+                    }
+                    for (int kh = 0; kh < nkh; kh++) HeadStage<1>::run(c, kh, wi, kh == nkh - 1);
+                    continue;
+                }
                 for (int kh = 0; kh < nkh; kh++) {
                     mbar_wait(bar(B_AFULL + kh), (kh ? cnt1 : cnt0) & 1u, P.fault, 0x300 + kh);   // both issuers observe the tile half
                     if (kh) cnt1++; else cnt0++;
@@ -557,6 +627,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
             if (item < 0) break;
             const int l = item / n_tiles, tile = item - l * n_tiles;
             const Layer& L = P.layers[l];
+            if (L.head) {
+                // head item: output filter j = accumulator lanes j (high part) and j + 3 (low part): only the first warp of
+                // each cell half has data; every warp keeps the accumulator protocol
+                const float hbias = (q == 0 && lane < 3) ? L.bias[lane] : 0.0f;
+                float* hout = L.head_out + (size_t)tile * (3 * CELLS * G);
+                for (int ri = 0; ri < BROWS; ri++, nrow++) {
+                    const int r = EPI_ORDER[ri], unit = unit_of(r);
+                    mbar_wait(bar(B_TFULL + unit), use_of(r, wi) & 1, P.fault, 0x700 + unit);
+                    tc_fence_after();
+                    if (q == 0) {
+                        // one cell at a time (16 registers): the head item is short, register pressure here must not
+                        // spill the convolution epilogue below
+                        const uint32_t ta = tbase + unit * UNIT_COLS + x0 * G;
+#pragma unroll 1
+                        for (int j = 0; j < (half ? 3 : 4); j++) {
+                            uint32_t v[16];
+                            tmem_ld16(ta + j * G, v);
+                            tmem_ld_wait();
+                            float o[16];
+#pragma unroll
+                            for (int b = 0; b < G; b++) {
+                                const float hi = __uint_as_float(v[b]);
+                                o[b] = fmaxf(hi + __shfl_down_sync(0xFFFFFFFFu, hi, 3) + hbias, 0.0f);
+                            }
+                            if (lane < 3 && mem) {
+                                float4* dst = reinterpret_cast<float4*>(hout + ((size_t)lane * CELLS + (r * BCOLS + x0 + j)) * G);
+#pragma unroll
+                                for (int e = 0; e < 4; e++) dst[e] = make_float4(o[4 * e], o[4 * e + 1], o[4 * e + 2], o[4 * e + 3]);
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(B_TEMPTY + unit));
+                }
+                continue;
+            }
             const float bias = L.bias[c];
             const uint8_t* resb = (L.res_buf >= 0 && mem) ? P.buf[L.res_buf] : nullptr;
             uint8_t* yb = P.buf[L.out_buf];
@@ -808,7 +915,7 @@ int hz_tower_conv3x3(const void* x_tiles, int in_channel_halves, int in_kmajor, 
 size_t hz_tower_sched_bytes(int64_t n_boards, int n_blocks) {
     if (n_boards <= 0 || n_blocks < 0) return 0;
     int64_t tiles = (n_boards + hz::tower::G - 1) / hz::tower::G;
-    return sizeof(unsigned int) * (size_t)(2 + 2 * (1 + 2 * n_blocks) * tiles);
+    return sizeof(unsigned int) * (size_t)(2 + 2 * (2 + 2 * n_blocks) * tiles);   // + the optional head item per tile
 }
 
 int hz_tower_forward(const void* x0_tiles, const void* const* w_tiles, const float* const* biases, int n_blocks, void* buf_a,
@@ -819,8 +926,17 @@ int hz_tower_forward(const void* x0_tiles, const void* const* w_tiles, const flo
 int hz_tower_forward_active(const void* x0_tiles, const void* const* w_tiles, const float* const* biases, int n_blocks, void* buf_a,
                             void* buf_b, void* buf_c, void* sched, void** out_tiles, int64_t n_boards, const int32_t* n_active,
                             unsigned int* fault, void* stream) {
+    return hz_tower_forward_heads(x0_tiles, w_tiles, biases, n_blocks, buf_a, buf_b, buf_c, sched, out_tiles, n_boards, n_active, nullptr,
+                                  nullptr, nullptr, fault, stream);
+}
+
+int hz_tower_forward_heads(const void* x0_tiles, const void* const* w_tiles, const float* const* biases, int n_blocks, void* buf_a,
+                           void* buf_b, void* buf_c, void* sched, void** out_tiles, int64_t n_boards, const int32_t* n_active,
+                           const void* w_head_tiles, const float* b_head, float* head_conv_tiled, unsigned int* fault, void* stream) {
     using namespace hz::tower;
     if ((uintptr_t)n_active & 3) return HZ_ERR_ARG;
+    if (w_head_tiles && (!b_head || !head_conv_tiled || (((uintptr_t)w_head_tiles | (uintptr_t)head_conv_tiled) & 15) || 2 + 2 * n_blocks > MAX_LAYERS))
+        return HZ_ERR_ARG;
     if (!x0_tiles || !w_tiles || !biases || !buf_a || !buf_b || !buf_c || !sched || n_boards <= 0 || (n_boards % G) || n_blocks < 0 ||
         1 + 2 * n_blocks > MAX_LAYERS)
         return HZ_ERR_ARG;
@@ -844,6 +960,10 @@ int hz_tower_forward_active(const void* x0_tiles, const void* const* w_tiles, co
         P.layers[n] = Layer{(const uint8_t*)w_tiles[n], biases[n], 2, cur, nxt, 2, 0, 1};
         n++;
         int t = cur; cur = nxt; nxt = t;
+    }
+    if (w_head_tiles) {
+        P.layers[n] = Layer{(const uint8_t*)w_head_tiles, b_head, cur, -1, 0, 2, 0, 1, 1, head_conv_tiled};
+        n++;
     }
     P.n_layers = n;
     P.n_tiles = (int)(n_boards / G);

@@ -108,6 +108,7 @@ class InferenceNet:
         self.tower = tower
         self.hand = None
         self._hc = {}
+        self.heads_in_tower = True     # tile path: 1x1 head convolutions as a work item of the tower launch (False: k_head_conv_t16, the A/B switch)
         self.load(model)
 
     def load(self, model):
@@ -135,6 +136,8 @@ class InferenceNet:
             from .tower import HandTower
 
             self.hand = HandTower(model, dev)
+            if self.heads is not None and self.heads["C"] == 128:
+                self.hand.set_heads(self.heads["w_conv"], self.heads["b_conv"])
         if self.fused:
             # the fused cuDNN entry points do not cover every dtype/arch combination: probe once
             # and use conv2d + relu (still cuDNN) if they refuse
@@ -234,18 +237,25 @@ class InferenceNet:
         if out is None:
             out = (torch.empty((n, 143), dtype=torch.float32, device=self.device), torch.empty(n, dtype=torch.float32, device=self.device))
         logits, value = out
-        hc = self._hc.get((n, tag))     # tag: callers running concurrently on different streams keep separate scratch
-        if hc is None:
-            hc = self._hc[(n, tag)] = torch.zeros((n, 105), dtype=torch.float32, device=self.device)
-        x_ptr = self.hand.forward_tiles(x0, n, n_active=n_active, tag=tag)
         lib = _lib.load()
         glob = glob.contiguous()
         na = None if n_active is None else n_active.data_ptr()
+        fold = self.heads_in_tower and self.hand.fused_layers
+        if fold:
+            # the 1x1 head convolutions run inside the tower launch, as one more work item per tile
+            self.hand.forward_tiles(x0, n, n_active=n_active, tag=tag, heads=True)
+            hc = self.hand.head_conv(n, tag)
+        else:
+            hc = self._hc.get((n, tag))     # tag: callers running concurrently on different streams keep separate scratch
+            if hc is None:
+                hc = self._hc[(n, tag)] = torch.zeros((n, 105), dtype=torch.float32, device=self.device)
+            x_ptr = self.hand.forward_tiles(x0, n, n_active=n_active, tag=tag)
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream(self.device).cuda_stream
-            _lib.check(lib.hz_net_head_conv_t16_active(x_ptr, n, na, h["w_conv"].data_ptr(), h["b_conv"].data_ptr(), hc.data_ptr(), st),
-                       "hz_net_head_conv_t16")
-            _lib.check(lib.hz_net_heads_fc_active(hc.data_ptr(), glob.data_ptr(), n, na, h["H"], h["w_pol_t"].data_ptr(), h["b_pol"].data_ptr(),
+            if not fold:
+                _lib.check(lib.hz_net_head_conv_t16_active(x_ptr, n, na, h["w_conv"].data_ptr(), h["b_conv"].data_ptr(), hc.data_ptr(), st),
+                           "hz_net_head_conv_t16")
+            _lib.check(lib.hz_net_heads_fc_active(hc.data_ptr(), glob.data_ptr(), n, na, 1 if fold else 0, h["H"], h["w_pol_t"].data_ptr(), h["b_pol"].data_ptr(),
                                                   h["w_v1_t"].data_ptr(), h["b_v1"].data_ptr(), h["w_v2"].data_ptr(), h["b_v2"],
                                                   logits.data_ptr(), value.data_ptr(), st), "hz_net_heads_fc")
         return logits, value

@@ -38,6 +38,20 @@ def pack_conv_weight(w):
     return img.view(torch.uint8).reshape(9, nkh, O, 128), nkh
 
 
+def pack_head_weight(w_conv):
+    """[3, 128] fp32 (the two policy and the value 1x1 filters, BatchNorm folded) -> uint8 [2, 128, 128]: the head item's
+    A operand (hz_tower_forward_heads): rows 0..2 = bf16 high parts, rows 3..5 = bf16 low parts (filter = hi + lo), rows
+    6..127 zero; per 64-channel half a K-major SWIZZLE_128B tile like pack_conv_weight's."""
+    w = w_conv.detach().float().cpu()
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    full = torch.zeros((128, 128, 3, 3), dtype=torch.float32)
+    full[0:3, :, 1, 1] = hi.float()
+    full[3:6, :, 1, 1] = lo.float()
+    img, nkh = pack_conv_weight(full)          # exact: the values are bf16 already
+    return img[4].contiguous(), nkh            # the centre tap: [nkh][128][128 B]
+
+
 class HandTower:
     """Folded stem + residual blocks of an AlphaZeroNet on one CUDA device."""
 
@@ -107,7 +121,22 @@ class HandTower:
         return torch.zeros(n_pad // G * KH_BYTES, dtype=torch.uint8, device=self.device)
 
     @torch.no_grad()
-    def forward_tiles(self, x0, n, n_active=None, tag=0):
+    def set_heads(self, w_conv, b_conv):
+        """1x1 head filters [3,128] + bias [3] (fp32, BatchNorm folded): forward_tiles(..., heads=True) then also runs them
+        inside the tower launch and leaves relu(conv + bias) in the buffer ``head_conv(n, tag)``."""
+        img, nkh = pack_head_weight(w_conv)
+        assert nkh == 2
+        self._head_w = img.to(self.device)
+        self._head_b = b_conv.detach().float().contiguous().to(self.device)
+
+    def head_conv(self, n, tag=0):
+        n_pad = (n + G - 1) // G * G
+        buf = self._buffers(n_pad, tag)
+        if "hc" not in buf:
+            buf["hc"] = torch.zeros(n_pad // G * 3 * 35 * G, dtype=torch.float32, device=self.device)
+        return buf["hc"]
+
+    def forward_tiles(self, x0, n, n_active=None, tag=0, heads=False):
         """x0: T16K tiles of n boards.  Returns the address of the T16 tiles holding the tower output
         (one of this object's scratch buffers: valid until the next call with the same n).
         n_active: int32 device tensor (one element) = boards to compute, read on the device."""
@@ -117,13 +146,16 @@ class HandTower:
         if self.fused_layers:
             res = ct.c_void_p()
             with torch.cuda.device(self.device):
-                _lib.check(self.lib.hz_tower_forward_active(
+                hw = hb = hc = None
+                if heads:
+                    hw, hb, hc = self._head_w.data_ptr(), self._head_b.data_ptr(), self.head_conv(n, tag).data_ptr()
+                _lib.check(self.lib.hz_tower_forward_heads(
                     x0.data_ptr(), self._w_ptrs, self._b_ptrs, len(self.blocks), x.data_ptr(), y.data_ptr(), z.data_ptr(),
                     buf["sched"].data_ptr(), ct.byref(res), n_pad, None if n_active is None else n_active.data_ptr(),
-                    self.fault, self._stream()), "hz_tower_forward")
+                    hw, hb, hc, self.fault, self._stream()), "hz_tower_forward")
             return res.value
-        if n_active is not None:
-            raise ValueError("n_active needs the fused all-layers launch")
+        if n_active is not None or heads:
+            raise ValueError("n_active / heads need the fused all-layers launch")
         self.conv(x0, 1, self.stem, None, x, n_pad, kmajor=True)
         for c1, c2 in self.blocks:
             self.conv(x, 2, c1, None, y, n_pad)

@@ -329,12 +329,13 @@ int hz_net_heads_fc(const float *head_conv, const void *glob, int64_t n, int H, 
                     const float *b_pol, const float *w_v1_t, const float *b_v1, const float *w_v2,
                     float b_v2, float *logits, float *value, void *stream);
 /* The same with the row count taken from the device: rows min(n, *n_active) are evaluated
- * (n_active NULL = n; see hz_tree_set_active). */
+ * (n_active NULL = n; see hz_tree_set_active).  hc_tiled != 0: head_conv is in the layout
+ * hz_tower_forward_heads writes: [tile of 16 boards][filter * 35 + cell][board in tile] fp32. */
 int hz_net_head_conv_t16_active(const void *x_tiles, int64_t n, const int32_t *n_active,
                                 const float *w_conv, const float *b_conv, float *head_conv,
                                 void *stream);
 int hz_net_heads_fc_active(const float *head_conv, const void *glob, int64_t n,
-                           const int32_t *n_active, int H, const float *w_pol_t, const float *b_pol,
+                           const int32_t *n_active, int hc_tiled, int H, const float *w_pol_t, const float *b_pol,
                            const float *w_v1_t, const float *b_v1, const float *w_v2, float b_v2,
                            float *logits, float *value, void *stream);
 
@@ -406,6 +407,19 @@ int hz_tower_forward_active(const void *x0_tiles, const void *const *w_tiles,
                             const float *const *biases, int n_blocks, void *buf_a, void *buf_b,
                             void *buf_c, void *sched, void **out_tiles, int64_t n_boards,
                             const int32_t *n_active, unsigned int *fault, void *stream);
+
+/* hz_tower_forward_active followed, in the same launch, by the 1x1 head convolutions + BatchNorm +
+ * ReLU (model.py:340-343,349-351) as one more work item per tile: a single-tap tcgen05.mma pass
+ * over the tile the last block just wrote.  w_head_tiles: [2 channel halves][128 rows][128 B]
+ * K-major SWIZZLE_128B bf16 with rows 0..2 = high parts of the three head filters (policy 0,
+ * policy 1, value), rows 3..5 = low parts (filter = hi + lo: fp32-weight accuracy), other rows
+ * zero; b_head [3] fp32; head_conv_tiled: [n_boards/16][3*35][16] fp32 (read it with
+ * hz_net_heads_fc_active(..., hc_tiled = 1)).  w_head_tiles == NULL: no head item. */
+int hz_tower_forward_heads(const void *x0_tiles, const void *const *w_tiles,
+                           const float *const *biases, int n_blocks, void *buf_a, void *buf_b,
+                           void *buf_c, void *sched, void **out_tiles, int64_t n_boards,
+                           const int32_t *n_active, const void *w_head_tiles, const float *b_head,
+                           float *head_conv_tiled, unsigned int *fault, void *stream);
 
 #define HZ_PLAYOUT_SALT 0xA5A5F00DC0FFEE11ull
 #define HZ_SEARCH_SALT  0x5EA2C47EE5A17B00ull
