@@ -528,6 +528,10 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks over the WHOLE engine leg (warm-up, timed waves, end-to-end legs, unfused comparison: tens of milliseconds,
+    # i.e. more than the one or two NVML samples that fit in the 2 ms timed region itself)
+    leg_sampler = ClockSampler(local)
+    leg_sampler.start()
     # ---- kernel-resident timing: inputs already in HBM
     for w in range(W):
         st = fresh(-1 - w)
@@ -683,6 +687,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     unfused_steps = int(st[:, 27].sum().item())
     unfused_ms = u0.elapsed_time(u1)
+    leg_clocks = leg_sampler.stop()
 
     pk, pk_src = peaks()
     avg_launch_s = (ms / K) * 1e-3
@@ -704,7 +709,7 @@ def run_b200(args):
         "e2e_full_records": {"value": e2e_full_value, "unit": UNIT, "h2d_bytes_per_step": n * 128, "d2h_bytes_per_step": n * 128,
                              "api": "HostPlayout.run_many: K batches of 128-byte records in and out, pipelined over 3 device buffers (PCIe-bound)"},
         "gpu_launches": launches_all,
-        "clocks": clocks,
+        "clocks": clocks, "clocks_engine_leg": leg_clocks,
         "roofline": headline_roofline(n, steps_done / K, avg_launch_s, clocks, pk, pk_src, at4),
         "wall_s": wall,
         "unfused": {"value": unfused_steps / (unfused_ms * 1e-3), "unit": UNIT, "launches": 76 * 3, "ms": unfused_ms,

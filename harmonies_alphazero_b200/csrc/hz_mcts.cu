@@ -14,6 +14,7 @@
 // Parity mode is one in-flight simulation per tree (the reference is strictly sequential,
 // MCTS.py:291-352); parallelism comes from thousands of concurrent trees.
 #include <math.h>
+#include <stdlib.h>
 
 #include "hz_common.cuh"
 #include "hz_core.cuh"
