@@ -249,7 +249,6 @@ __global__ void __launch_bounds__(FTPB, 1) k_heads_p(const __nv_bfloat16* __rest
         }
     }
     const float bc0 = hc ? 0.0f : P.b_conv[0], bc1 = hc ? 0.0f : P.b_conv[1], bc2 = hc ? 0.0f : P.b_conv[2];
-    hz_grid_dep_wait();                                      // weights are on their way; inputs and the active count are predecessors' output
     if (n_active) n = min(n, (int64_t)max(*n_active, 0));   // only the active prefix of the rows (hz_tree_set_active)
     int64_t n_groups = (n + FG - 1) / FG;
     bool weights_pending = true;
@@ -403,7 +402,6 @@ __global__ void __launch_bounds__(HCT, 2) k_head_conv_t16(const uint8_t* __restr
     const int t = threadIdx.x;
     for (int i = t; i < 3 * 128; i += HCT) s_w[i] = w_conv[i];
     __syncthreads();
-    hz_grid_dep_wait();
     if (n_active) n = min(n, (int64_t)max(*n_active, 0));
     if ((int64_t)blockIdx.x * 16 >= n) return;
     const int64_t tile = blockIdx.x;
@@ -471,7 +469,7 @@ extern "C" int hz_net_head_conv_t16_active(const void* x_tiles, int64_t n, const
     if (n == 0) return HZ_OK;
     if (!x_tiles || !w_conv || !b_conv || !head_conv || n < 0 || ((uintptr_t)x_tiles & 15) || ((uintptr_t)n_active & 3)) return HZ_ERR_ARG;
     int64_t tiles = (n + 15) / 16;
-    hz_launch(hz::k_head_conv_t16, dim3((unsigned)tiles), dim3(hz::HCT), 0, (cudaStream_t)stream, (const uint8_t*)x_tiles, n, w_conv, b_conv, head_conv, n_active);
+    hz::k_head_conv_t16<<<(unsigned)tiles, hz::HCT, 0, (cudaStream_t)stream>>>((const uint8_t*)x_tiles, n, w_conv, b_conv, head_conv, n_active);
     return hz_launched(1);
 }
 
@@ -499,7 +497,7 @@ extern "C" int hz_net_heads_fc_active(const float* head_conv, const void* glob, 
     }
     int64_t fgroups = (n + hz::FG - 1) / hz::FG;
     int fgrid = (int)(fgroups < 148 ? fgroups : 148);
-    hz_launch(hz::k_heads_p, dim3(fgrid), dim3(hz::FTPB), (size_t)hz::FSMEM, (cudaStream_t)stream, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)glob, n, P, logits, value, (const float*)head_conv, n_active, hc_tiled);
+    hz::k_heads_p<<<fgrid, hz::FTPB, hz::FSMEM, (cudaStream_t)stream>>>(nullptr, (const __nv_bfloat16*)glob, n, P, logits, value, head_conv, n_active, hc_tiled);
     return hz_launched(1);
 }
 

@@ -204,7 +204,6 @@ __global__ void __launch_bounds__(TTPB) k_tree_select(hz_tree T, float cpuct, ui
     }
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t = blockIdx.x * WPB + warp;
-    hz_grid_dep_wait();                       // everything above is tables; the trees are the previous kernel's output
     if (t >= active_trees(T)) return;
     TreeView v = view_of(T, t);
     const int K = T.leaves;
@@ -360,7 +359,6 @@ __global__ void __launch_bounds__(TTPB, HZ_EXPAND_MIN_BLOCKS) k_tree_expand_back
     const NbrLut* lut = global_nbr_lut();
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t = blockIdx.x * WPB + warp;
-    hz_grid_dep_wait();                       // logits / values are the previous kernel's output
     if (t >= active_trees(T)) return;
     TreeView v = view_of(T, t);
     const int K = T.leaves, sim0 = T.sim[t];
@@ -726,7 +724,7 @@ int hz_tree_select(hz_tree* t, float cpuct, void* leaf_states, void* board, void
     uint4* ls = (uint4*)leaf_states;
     if (layout != HZ_LAYOUT_NCHW && layout != HZ_LAYOUT_NHWC && layout != HZ_LAYOUT_NHWC40 && layout != HZ_LAYOUT_T16K) return HZ_ERR_ARG;
     if (layout == HZ_LAYOUT_T16K && dtype != HZ_DTYPE_BF16) return HZ_ERR_ARG;
-#define HZ_SELECT(T, L) hz_launch(k_tree_select<T, L>, dim3(grid), dim3(TTPB), 0, st, *t, cpuct, ls, (T*)board, (T*)glob)
+#define HZ_SELECT(T, L) k_tree_select<T, L><<<grid, TTPB, 0, st>>>(*t, cpuct, ls, (T*)board, (T*)glob)
     if (dtype == HZ_DTYPE_F32) {
         if (layout == HZ_LAYOUT_NHWC40) HZ_SELECT(float, HZ_LAYOUT_NHWC40);
         else if (layout == HZ_LAYOUT_NHWC) HZ_SELECT(float, HZ_LAYOUT_NHWC);
@@ -746,7 +744,7 @@ int hz_tree_select(hz_tree* t, float cpuct, void* leaf_states, void* board, void
 int hz_tree_expand_backup(hz_tree* t, const float* policy, const float* value, int is_logits, const float* noise,
                           double eps, void* stream) {
     if (!t || !policy || !value) return HZ_ERR_ARG;
-    hz_launch(k_tree_expand_backup, dim3(tree_blocks(t->n_trees, WPB)), dim3(TTPB), 0, (cudaStream_t)stream, *t, policy, value, is_logits, noise, eps);
+    k_tree_expand_backup<<<tree_blocks(t->n_trees, WPB), TTPB, 0, (cudaStream_t)stream>>>(*t, policy, value, is_logits, noise, eps);
     return hz_launched(1);
 }
 

@@ -473,7 +473,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *tmem_slot;
-    hz_grid_dep_wait();      // barriers and tensor memory are set up; the input tiles, the active count and the ready queue are predecessors' output
     const int n_tiles = tiles_of(P.n_active, P.n_tiles);
     const int n_items = P.n_layers * n_tiles;
     if (warp == 0) HZ_TRACE(0);
@@ -752,7 +751,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
 
 // ready queue before the launch: head 0, tail n_tiles, no completions, the stem items in slots 0..n_tiles-1
 __global__ void k_sched_init(unsigned int* sched, int n_tiles_max, int n_layers, const int* n_active) {
-    hz_grid_dep_wait();
     const int n_tiles = tiles_of(n_active, n_tiles_max), n_items = n_layers * n_tiles;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 + 2 * n_items; i += gridDim.x * blockDim.x) {
         unsigned int v = 0u;
@@ -975,8 +973,8 @@ int hz_tower_forward_heads(const void* x0_tiles, const void* const* w_tiles, con
     P.n_active = n_active;
     if (out_tiles) *out_tiles = P.buf[cur];
     const int n_items = P.n_layers * P.n_tiles;
-    hz_launch(k_sched_init, dim3((2 + 2 * n_items + 255) / 256), dim3(256), 0, (cudaStream_t)stream, P.sched, P.n_tiles, P.n_layers, n_active);
-    hz_launch(k_tower, dim3(grid_for(P.n_tiles)), dim3(NTHREADS), (size_t)SMEM_BYTES, (cudaStream_t)stream, P);
+    k_sched_init<<<(2 + 2 * n_items + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P.sched, P.n_tiles, P.n_layers, n_active);
+    k_tower<<<grid_for(P.n_tiles), NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(P);
     return hz_launched(2);
 }
 
