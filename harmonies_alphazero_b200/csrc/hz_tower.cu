@@ -237,10 +237,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
 #ifndef HZ_TOWER_TURN_P1
 #define HZ_TOWER_TURN_P1 1
 #endif
-// drop dead activation tiles from L2 (see the epilogue); -DHZ_TOWER_DISCARD=0 is the A/B switch
-#ifndef HZ_TOWER_DISCARD
-#define HZ_TOWER_DISCARD 1
-#endif
 #ifndef HZ_TOWER_COLLECTOR
 #define HZ_TOWER_COLLECTOR 1
 #endif
@@ -742,21 +738,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 last = __shfl_sync(0xFFFFFFFFu, last, 0);
                 if (last) {
                     // last of the 8 epilogue warps to finish the item
-#if HZ_TOWER_DISCARD
-                    // a block's second convolution is the last reader of both its input (the first convolution's output) and its
-                    // residual (the block input): drop the two tiles from L2 instead of letting 2 x 143 KB of dead dirty lines be
-                    // written back to HBM later (555 MB per 4,096-board launch otherwise)
-                    if (L.res_buf >= 0 && mem) {
-                        const uint8_t* t_in = P.buf[L.in_buf] + (size_t)tile * 2 * KH_BYTES;
-                        const uint8_t* t_res = P.buf[L.res_buf] + (size_t)tile * 2 * KH_BYTES;
-                        for (int i = lane; i < 2 * KH_BYTES / 128; i += 32) {
-                            asm volatile("discard.global.L2 [%0], 128;" ::"l"(t_in + (size_t)i * 128) : "memory");
-                            asm volatile("discard.global.L2 [%0], 128;" ::"l"(t_res + (size_t)i * 128) : "memory");
-                        }
-                        __threadfence();
-                        __syncwarp();
-                    }
-#endif
                     // the tile's next layer becomes ready
                     if (lane == 0) {
                         const unsigned int slot = atomicAdd(P.sched + 1, 1u);
