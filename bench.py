@@ -359,7 +359,8 @@ def mcts_measure(args, dev, world, rank, dist, with_collectives=True, tower=None
     pk, pk_src = peaks()
     flops = hznet.flops_per_position()
     hand = inf.hand is not None
-    own_per_sim = (2 + (4 if hand else (inf.heads is not None))) if drv.graph is not None else 0   # select, expand (+ tower, head convs, heads / heads)
+    # select, expand + (queue init, tower [with the head-convolution items], FC heads [+ the separate head-conv kernel]) / fused heads
+    own_per_sim = (2 + ((3 if getattr(inf, "heads_in_tower", False) else 4) if hand else (inf.heads is not None))) if drv.graph is not None else 0
     peak_step = {"value": v_step, "unit": "sims/s", "ms_per_move": ms / K, "moves": K,
                  "what": f"{K} moves of all {B} games from ply 8 (every slot live): the step rate of the search itself"}
     whole = None
