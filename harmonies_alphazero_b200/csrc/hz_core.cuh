@@ -371,13 +371,25 @@ __device__ __forceinline__ void score_board(const NbrLut* lut, const Board& b, i
 // all threads of the block, between two __syncthreads(): q->extra[owner] += points of each queued component
 template <int CAP, int OWNERS>
 __device__ __forceinline__ void resolve_water(const NbrLut* lut, WaterQueue<CAP, OWNERS>* q) {
-    int n = min(q->count, CAP), lane = threadIdx.x & 31;
-    for (int e = threadIdx.x >> 5; e < n; e += blockDim.x >> 5) {
-        uint32_t comp = q->comp[e], f = (1u << lane) & comp, nf;
+    // FOUR components per warp: a group of 8 lanes takes one component, lane j of the group the BFS from its j-th, (j+8)-th ...
+    // hex.  (One component per warp with one source per lane left 24-27 lanes idle: these components have 5-8 hexes.)
+    const int n = min(q->count, CAP), lane = threadIdx.x & 31, sub = lane >> 3, j0 = lane & 7;
+    const int nw = blockDim.x >> 5;
+    for (int base = (threadIdx.x >> 5) * 4; base < n; base += nw * 4) {
+        const int e = base + sub;
+        const uint32_t comp = e < n ? q->comp[e] : 0u;
+        const int size = __popc(comp);
         int d = 0;
-        if (f) while ((nf = (f | nbr(lut, f)) & comp) != f) { f = nf; d++; }
-        d = __reduce_max_sync(0xFFFFFFFFu, d);
-        if (lane == 0) atomicAdd(&q->extra[q->owner[e]], water_points(d + 1));
+        for (int j = j0; j < size; j += 8) {
+            uint32_t f = 1u << __fns(comp, 0, j + 1), nf;
+            int dd = 0;
+            while ((nf = (f | nbr(lut, f)) & comp) != f) { f = nf; dd++; }
+            d = max(d, dd);
+        }
+        d = max(d, __shfl_xor_sync(0xFFFFFFFFu, d, 1));
+        d = max(d, __shfl_xor_sync(0xFFFFFFFFu, d, 2));
+        d = max(d, __shfl_xor_sync(0xFFFFFFFFu, d, 4));
+        if (e < n && j0 == 0) atomicAdd(&q->extra[q->owner[e]], water_points(d + 1));
     }
 }
 __device__ __forceinline__ int score_player(const NbrLut* lut, const State& s, int p) {
