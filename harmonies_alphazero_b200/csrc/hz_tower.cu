@@ -34,6 +34,8 @@
 //   * warp roles: 0 = weight producer, 1 and 12 = MMA issuers (alternating weight stages), 2 =
 //     activation producer, 3 = TMEM allocator + work scheduler, 4..11 = epilogue (bias + residual +
 //     ReLU + bf16, thread = output channel).
+#include <stdlib.h>
+
 #include "hz_common.cuh"
 #include "hz_sm100.cuh"
 
@@ -161,6 +163,12 @@ struct Params {
     unsigned int* fault;
     unsigned long long* trace;   // profiling only (hz_tower_set_trace): SM-clock timestamps of CTA 0's roles
     const int* n_active;         // device word (nullable): only the tiles that hold boards 0..*n_active-1 are computed
+    // pair mode (hz_tower_forward*, clusters of two CTAs): a work item is a PAIR of neighbouring tiles of one layer, one tile
+    // per CTA, so both CTAs stream the same weights: each loads half of every weight stage and multicasts it to both (the
+    // weights are 57 % of what a launch pulls through L2).  mailbox: [cluster][64] words through which CTA 0 of a cluster
+    // tells CTA 1 which item it drew.
+    int pair;
+    unsigned int* mailbox;
 };
 // tiles to compute: all of them, or those of the active board prefix (every thread of the grid reads the same word)
 __device__ __forceinline__ int tiles_of(const int* n_active, int n_tiles) {
@@ -339,7 +347,8 @@ struct StageLoop {
             __syncwarp();
             if (c.dual && last_in_turn) named_bar_arrive(c.parity ? 2 : 1);
             if (lead) {
-                umma_commit(c.bar0 + 8u * (B_WEMPTY + c.stage));      // frees the weight stage when these MMAs have read it
+                if (c.pair) umma_commit_mc(c.bar0 + 8u * (B_WEMPTY + c.stage), (uint16_t)3);   // ... in both CTAs of the pair
+                else umma_commit(c.bar0 + 8u * (B_WEMPTY + c.stage));      // frees the weight stage when these MMAs have read it
                 if (last_kh) {
 #pragma unroll
                     for (int r = r0; r < r1; r++)
@@ -397,7 +406,8 @@ struct HeadStage {
             __syncwarp();
             if (c.dual) named_bar_arrive(c.parity ? 2 : 1);
             if (lead) {
-                umma_commit(c.bar0 + 8u * (B_WEMPTY + c.stage));
+                if (c.pair) umma_commit_mc(c.bar0 + 8u * (B_WEMPTY + c.stage), (uint16_t)3);
+                else umma_commit(c.bar0 + 8u * (B_WEMPTY + c.stage));
                 if (last_kh) {
 #pragma unroll
                     for (int r = r0; r < r1; r++) umma_commit(c.bar0 + 8u * (B_TFULL + unit_of(r)));
@@ -421,6 +431,7 @@ struct IssueCtx {
     int nturn;                   // running turn count of the CTA
     int parity;                  // this warp issues the turns with nturn % 2 == parity
     bool dual;                   // two issuer warps (false: this warp issues everything)
+    bool pair;                   // pair mode: weight stages are shared with the other CTA of the cluster
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
@@ -460,8 +471,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
     volatile int* qitem = (volatile int*)(sm + OFF_BAR + N_BARS * 8 + 16);   // work-item queue, 2 entries
     auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crank = P.pair ? (int)cluster_ctarank() : 0;     // rank inside the cluster of two (pair mode)
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NSTAGE; i++) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
+        // pair mode: a weight stage is free again when the MMAs of BOTH CTAs have read it (each CTA's copies land in both)
+        for (int i = 0; i < NSTAGE; i++) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), P.pair ? 2 : 1); }
         for (int i = 0; i < 2; i++) { mbar_init(bar(B_AFULL + i), 1); mbar_init(bar(B_AEMPTY + i), 1); }
         for (int i = 0; i < NUNIT; i++) { mbar_init(bar(B_TFULL + i), 1); mbar_init(bar(B_TEMPTY + i), 8); }
         mbar_init(bar(B_DONE), (P.dbg & 32) ? 1 : 2);
@@ -471,10 +484,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
     if (warp == 3) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
     __syncthreads();
+    if (P.pair) cluster_sync_all();          // the peer's barriers exist before anything of ours can arrive on them
     tc_fence_after();
     const uint32_t tbase = *tmem_slot;
     const int n_tiles = tiles_of(P.n_active, P.n_tiles);
-    const int n_items = P.n_layers * n_tiles;
+    const int n_units = P.pair ? (n_tiles + 1) / 2 : n_tiles;   // work units per layer: tiles, or pairs of tiles
+    const int n_items = P.n_layers * n_units;
+    // this CTA's tile of work unit u (an odd tile count makes both CTAs of the last pair compute the same tile)
+    auto tile_of = [&](int u) { return P.pair ? min(2 * u + crank, n_tiles - 1) : u; };
     if (warp == 0) HZ_TRACE(0);
     if (HZ_TOWER_TRACE && warp == 0 && P.trace && blockIdx.x == 0 && lane == 0) P.trace[2] = globaltimer_ns();
 
@@ -493,10 +510,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
         // ---- scheduler ----
         if (lane == 0) {
             const int per_cta = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // static map: tiles blockIdx.x + j*gridDim.x
+            unsigned int* mbox = P.pair ? P.mailbox + (size_t)(blockIdx.x >> 1) * 64 : nullptr;
             for (int k = 0;; k++) {
                 int item;
-                if (P.sched) {
+                if (P.pair && crank == 1) {
+                    // the item CTA 0 of this cluster drew as its k-th: entry = tag(k) << 20 | item + 2
+                    const unsigned int want = (unsigned int)(k % 4095 + 1) << 20;     // never 0: a cleared mailbox matches nothing
+                    unsigned int v;
+                    for (uint32_t it = 0; ((v = ld_acquire_gpu(mbox + (k & 63))) & 0xFFF00000u) != want; ++it) {
+                        __nanosleep(32);
+                        if (it > (1u << 22)) {
+                            if (P.fault) { atomicExch(P.fault, 0xB01u); __threadfence_system(); }
+                            __trap();
+                        }
+                    }
+                    item = (int)(v & 0xFFFFFu) - 2;
+                } else if (P.sched) {
                     item = dequeue_item(P.sched, n_items, P.fault);
+                    if (P.pair) st_release_gpu(mbox + (k & 63), ((unsigned int)(k % 4095 + 1) << 20) | (unsigned int)(item + 2));
                 } else {
                     item = k < per_cta * P.n_layers ? (k / per_cta) * n_tiles + (int)blockIdx.x + (k % per_cta) * (int)gridDim.x : -1;
                 }
@@ -515,7 +546,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 int item;
                 HZ_NEXT_ITEM(k, item, false);
                 if (item < 0) break;
-                const Layer& L = P.layers[item / n_tiles];
+                const Layer& L = P.layers[item / n_units];
                 const int nkh = L.nkh;
                 const int nseg = L.head ? 2 : NSEG;
                 for (int seg = 0; seg < nseg; seg++)
@@ -527,7 +558,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                             if (P.dbg & 4) mbar_arrive(bar(B_WFULL + stage));
                             else {
                                 mbar_expect_tx(bar(B_WFULL + stage), W_BYTES);
-                                bulk_g2s(sW + stage * W_BYTES, L.w + (size_t)(tap * nkh + kh) * W_BYTES, W_BYTES, bar(B_WFULL + stage));
+                                const uint8_t* wsrc = L.w + (size_t)(tap * nkh + kh) * W_BYTES;
+                                if (P.pair)     // this CTA's half of the stage, delivered to both CTAs of the cluster
+                                    bulk_g2s_mc(sW + stage * W_BYTES + crank * (W_BYTES / 2), wsrc + crank * (W_BYTES / 2), W_BYTES / 2,
+                                                bar(B_WFULL + stage), (uint16_t)3);
+                                else bulk_g2s(sW + stage * W_BYTES, wsrc, W_BYTES, bar(B_WFULL + stage));
                             }
                             if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
                         }
@@ -542,7 +577,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 int item;
                 HZ_NEXT_ITEM(k, item, false);
                 if (item < 0) break;
-                const int l = item / n_tiles, tile = item - l * n_tiles;
+                const int l = item / n_units, tile = tile_of(item - l * n_units);
                 const Layer& L = P.layers[l];
                 // the tile's input is the previous layer's output, possibly written by another CTA through the generic
                 // proxy; the ready queue (acquired by the scheduler, handed over through the item barrier) makes it
@@ -566,14 +601,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
         if (warp == 12 && !dual) {
             // single-issuer mode (profiling A/B): nothing to do
         } else {
-            IssueCtx c{sBar, sW, sX, tbase, 0u, 0u, P.fault, P.dbg, (blockIdx.x == 0 && lane == 0) ? P.trace : nullptr, 0, 0, warp == 12 ? 1 : 0, dual};
+            IssueCtx c{sBar, sW, sX, tbase, 0u, 0u, P.fault, P.dbg, (blockIdx.x == 0 && lane == 0) ? P.trace : nullptr, 0, 0, warp == 12 ? 1 : 0, dual, P.pair != 0};
             uint32_t cnt0 = 0, cnt1 = 0;
             int wi = 0, k = 0;                 // wi: work items done (phase of the accumulator units)
             for (;; wi++) {
                 int item;
                 HZ_NEXT_ITEM(k, item, true);
                 if (item < 0) break;
-                const Layer& L = P.layers[item / n_tiles];
+                const Layer& L = P.layers[item / n_units];
                 const int nkh = L.nkh;
                 const bool kmajor = L.kmajor != 0;
                 if (L.head) {
@@ -624,7 +659,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
             int item;
             HZ_NEXT_ITEM(k, item, true);
             if (item < 0) break;
-            const int l = item / n_tiles, tile = item - l * n_tiles;
+            const int l = item / n_units, tile = tile_of(item - l * n_units);
             const Layer& L = P.layers[l];
             if (L.head) {
                 // head item: output filter j = accumulator lanes j (high part) and j + 3 (low part): only the first warp of
@@ -734,14 +769,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 fence_proxy_async();
                 __syncwarp();
                 unsigned int last = 0;
-                if (lane == 0) last = atom_add_acq_rel_gpu(P.sched + 2 + item, 1u) == FLAG_DONE - 1 ? 1u : 0u;
+                if (lane == 0) last = atom_add_acq_rel_gpu(P.sched + 2 + item, 1u) == (P.pair ? 2 * FLAG_DONE : FLAG_DONE) - 1 ? 1u : 0u;
                 last = __shfl_sync(0xFFFFFFFFu, last, 0);
                 if (last) {
                     // last of the 8 epilogue warps to finish the item
                     // the tile's next layer becomes ready
                     if (lane == 0) {
                         const unsigned int slot = atomicAdd(P.sched + 1, 1u);
-                        st_release_gpu(P.sched + 2 + n_items + slot, (unsigned int)(item + n_tiles) + 1u);
+                        st_release_gpu(P.sched + 2 + n_items + slot, (unsigned int)(item + n_units) + 1u);
                     }
                 }
             }
@@ -750,20 +785,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
 #undef HZ_NEXT_ITEM
     tc_fence_before();
     __syncthreads();
+    if (P.pair) cluster_sync_all();          // neither CTA leaves while the other may still deliver weights or commits to it
     if (warp == 0) HZ_TRACE(1);
     if (HZ_TOWER_TRACE && warp == 0 && P.trace && blockIdx.x == 0 && lane == 0) P.trace[3] = globaltimer_ns();
     if (warp == 3) tmem_dealloc(tbase, 512);
 }
 
 // ready queue before the launch: head 0, tail n_tiles, no completions, the stem items in slots 0..n_tiles-1
-__global__ void k_sched_init(unsigned int* sched, int n_tiles_max, int n_layers, const int* n_active) {
-    const int n_tiles = tiles_of(n_active, n_tiles_max), n_items = n_layers * n_tiles;
+constexpr int MAILBOX_WORDS = 128 * 64;     // pair mode: 64 words per cluster
+__global__ void k_sched_init(unsigned int* sched, int n_tiles_max, int n_layers, const int* n_active, int pair, unsigned int* mailbox) {
+    const int n_tiles = tiles_of(n_active, n_tiles_max), n_units = pair ? (n_tiles + 1) / 2 : n_tiles, n_items = n_layers * n_units;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 + 2 * n_items; i += gridDim.x * blockDim.x) {
         unsigned int v = 0u;
-        if (i == 1) v = (unsigned int)n_tiles;
-        else if (i >= 2 + n_items && i < 2 + n_items + n_tiles) v = (unsigned int)(i - (2 + n_items)) + 1u;
+        if (i == 1) v = (unsigned int)n_units;
+        else if (i >= 2 + n_items && i < 2 + n_items + n_units) v = (unsigned int)(i - (2 + n_items)) + 1u;
         sched[i] = v;
     }
+    if (mailbox)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < MAILBOX_WORDS; i += gridDim.x * blockDim.x) mailbox[i] = 0u;
 }
 
 // ---- layout conversion (interop with NHWC tensors: tests, the heads kernel) -----------------------
@@ -821,6 +860,7 @@ __global__ void k_from_tiles(const __nv_bfloat16* __restrict__ src, __nv_bfloat1
     }
 }
 
+#define MAX_LAYERS_SCHED(n_blocks) (2 + 2 * (n_blocks))   /* layers hz_tower_sched_bytes reserves queue space for */
 static int g_debug = 0;
 static unsigned long long* g_trace = nullptr;
 static int g_max_ctas = 0;   // 0 = one CTA per SM; tests lower it to drive several tiles through one CTA
@@ -920,7 +960,7 @@ int hz_tower_conv3x3(const void* x_tiles, int in_channel_halves, int in_kmajor, 
 size_t hz_tower_sched_bytes(int64_t n_boards, int n_blocks) {
     if (n_boards <= 0 || n_blocks < 0) return 0;
     int64_t tiles = (n_boards + hz::tower::G - 1) / hz::tower::G;
-    return sizeof(unsigned int) * (size_t)(2 + 2 * (2 + 2 * n_blocks) * tiles);   // + the optional head item per tile
+    return sizeof(unsigned int) * ((size_t)(2 + 2 * (2 + 2 * n_blocks) * tiles) + hz::tower::MAILBOX_WORDS);   // + the optional head item per tile, + the pair-mode mailboxes
 }
 
 int hz_tower_forward(const void* x0_tiles, const void* const* w_tiles, const float* const* biases, int n_blocks, void* buf_a,
@@ -979,8 +1019,30 @@ int hz_tower_forward_heads(const void* x0_tiles, const void* const* w_tiles, con
     P.n_active = n_active;
     if (out_tiles) *out_tiles = P.buf[cur];
     const int n_items = P.n_layers * P.n_tiles;
-    k_sched_init<<<(2 + 2 * n_items + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P.sched, P.n_tiles, P.n_layers, n_active);
-    k_tower<<<grid_for(P.n_tiles), NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    // pair mode (clusters of two CTAs sharing the weight stream by multicast) unless switched off or there is a single tile
+    static const bool no_pair = getenv("HZ_TOWER_NO_PAIR") != nullptr;
+    P.pair = (!no_pair && P.n_tiles >= 2 && grid_for(P.n_tiles) >= 2) ? 1 : 0;
+    P.mailbox = P.sched + (2 + 2 * (size_t)MAX_LAYERS_SCHED(n_blocks) * P.n_tiles);
+    k_sched_init<<<(2 + 2 * n_items + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P.sched, P.n_tiles, P.n_layers, n_active, P.pair, P.mailbox);
+    if (P.pair) {
+        const int n_pairs = (P.n_tiles + 1) / 2;
+        int clusters = grid_for(P.n_tiles) / 2;
+        if (clusters > n_pairs) clusters = n_pairs;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(NTHREADS);
+        cfg.dynamicSmemBytes = SMEM_BYTES;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_tower, P);
+        if (e != cudaSuccess) return hz_record_launch(1, e);
+    } else {
+        k_tower<<<grid_for(P.n_tiles), NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    }
     return hz_launched(2);
 }
 
