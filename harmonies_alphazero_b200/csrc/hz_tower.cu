@@ -163,10 +163,10 @@ struct Params {
     unsigned int* fault;
     unsigned long long* trace;   // profiling only (hz_tower_set_trace): SM-clock timestamps of CTA 0's roles
     const int* n_active;         // device word (nullable): only the tiles that hold boards 0..*n_active-1 are computed
-    // pair mode (hz_tower_forward*, clusters of two CTAs): a work item is a PAIR of neighbouring tiles of one layer, one tile
-    // per CTA, so both CTAs stream the same weights: each loads half of every weight stage and multicasts it to both (the
-    // weights are 57 % of what a launch pulls through L2).  mailbox: [cluster][64] words through which CTA 0 of a cluster
-    // tells CTA 1 which item it drew.
+    // cluster mode (hz_tower_forward*, clusters of `pair` = 2 or 4 CTAs; 0 = off): a work item is a group of neighbouring tiles
+    // of one layer, one tile per CTA, so all CTAs of the cluster stream the same weights: each loads its share of every weight
+    // stage and multicasts it to all of them (the weights are 57 % of what a launch pulls through L2).  mailbox: [cluster][64]
+    // words through which CTA 0 of a cluster tells the others which item it drew.
     int pair;
     unsigned int* mailbox;
 };
@@ -347,7 +347,7 @@ struct StageLoop {
             __syncwarp();
             if (c.dual && last_in_turn) named_bar_arrive(c.parity ? 2 : 1);
             if (lead) {
-                if (c.pair) umma_commit_mc(c.bar0 + 8u * (B_WEMPTY + c.stage), (uint16_t)3);   // ... in both CTAs of the pair
+                if (c.pair) umma_commit_mc(c.bar0 + 8u * (B_WEMPTY + c.stage), c.cmask);   // ... in every CTA of the cluster
                 else umma_commit(c.bar0 + 8u * (B_WEMPTY + c.stage));      // frees the weight stage when these MMAs have read it
                 if (last_kh) {
 #pragma unroll
@@ -406,7 +406,7 @@ struct HeadStage {
             __syncwarp();
             if (c.dual) named_bar_arrive(c.parity ? 2 : 1);
             if (lead) {
-                if (c.pair) umma_commit_mc(c.bar0 + 8u * (B_WEMPTY + c.stage), (uint16_t)3);
+                if (c.pair) umma_commit_mc(c.bar0 + 8u * (B_WEMPTY + c.stage), c.cmask);
                 else umma_commit(c.bar0 + 8u * (B_WEMPTY + c.stage));
                 if (last_kh) {
 #pragma unroll
@@ -431,7 +431,8 @@ struct IssueCtx {
     int nturn;                   // running turn count of the CTA
     int parity;                  // this warp issues the turns with nturn % 2 == parity
     bool dual;                   // two issuer warps (false: this warp issues everything)
-    bool pair;                   // pair mode: weight stages are shared with the other CTA of the cluster
+    bool pair;                   // cluster mode: weight stages are shared with the other CTAs of the cluster
+    uint16_t cmask;              // ... their mask
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
     const int crank = P.pair ? (int)cluster_ctarank() : 0;     // rank inside the cluster of two (pair mode)
     if (threadIdx.x == 0) {
         // pair mode: a weight stage is free again when the MMAs of BOTH CTAs have read it (each CTA's copies land in both)
-        for (int i = 0; i < NSTAGE; i++) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), P.pair ? 2 : 1); }
+        for (int i = 0; i < NSTAGE; i++) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), P.pair ? P.pair : 1); }
         for (int i = 0; i < 2; i++) { mbar_init(bar(B_AFULL + i), 1); mbar_init(bar(B_AEMPTY + i), 1); }
         for (int i = 0; i < NUNIT; i++) { mbar_init(bar(B_TFULL + i), 1); mbar_init(bar(B_TEMPTY + i), 8); }
         mbar_init(bar(B_DONE), (P.dbg & 32) ? 1 : 2);
@@ -488,10 +489,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
     tc_fence_after();
     const uint32_t tbase = *tmem_slot;
     const int n_tiles = tiles_of(P.n_active, P.n_tiles);
-    const int n_units = P.pair ? (n_tiles + 1) / 2 : n_tiles;   // work units per layer: tiles, or pairs of tiles
+    const int csize = P.pair ? P.pair : 1;                       // CTAs per cluster = tiles per work unit (1, 2 or 4)
+    const int n_units = (n_tiles + csize - 1) / csize;           // work units per layer: tiles, or groups of neighbouring tiles
     const int n_items = P.n_layers * n_units;
     // this CTA's tile of work unit u (an odd tile count makes both CTAs of the last pair compute the same tile)
-    auto tile_of = [&](int u) { return P.pair ? min(2 * u + crank, n_tiles - 1) : u; };
+    auto tile_of = [&](int u) { return min(csize * u + crank, n_tiles - 1); };
     if (warp == 0) HZ_TRACE(0);
     if (HZ_TOWER_TRACE && warp == 0 && P.trace && blockIdx.x == 0 && lane == 0) P.trace[2] = globaltimer_ns();
 
@@ -510,10 +512,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
         // ---- scheduler ----
         if (lane == 0) {
             const int per_cta = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // static map: tiles blockIdx.x + j*gridDim.x
-            unsigned int* mbox = P.pair ? P.mailbox + (size_t)(blockIdx.x >> 1) * 64 : nullptr;
+            unsigned int* mbox = P.pair ? P.mailbox + (size_t)(blockIdx.x / (unsigned)P.pair) * 64 : nullptr;
             for (int k = 0;; k++) {
                 int item;
-                if (P.pair && crank == 1) {
+                if (P.pair && crank != 0) {
                     // the item CTA 0 of this cluster drew as its k-th: entry = tag(k) << 20 | item + 2
                     const unsigned int want = (unsigned int)(k % 4095 + 1) << 20;     // never 0: a cleared mailbox matches nothing
                     unsigned int v;
@@ -559,9 +561,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                             else {
                                 mbar_expect_tx(bar(B_WFULL + stage), W_BYTES);
                                 const uint8_t* wsrc = L.w + (size_t)(tap * nkh + kh) * W_BYTES;
-                                if (P.pair)     // this CTA's half of the stage, delivered to both CTAs of the cluster
-                                    bulk_g2s_mc(sW + stage * W_BYTES + crank * (W_BYTES / 2), wsrc + crank * (W_BYTES / 2), W_BYTES / 2,
-                                                bar(B_WFULL + stage), (uint16_t)3);
+                                if (P.pair) {   // this CTA's share of the stage, delivered to every CTA of the cluster
+                                    const uint32_t part = W_BYTES / (uint32_t)P.pair;
+                                    bulk_g2s_mc(sW + stage * W_BYTES + crank * part, wsrc + crank * part, part, bar(B_WFULL + stage),
+                                                (uint16_t)((1u << P.pair) - 1u));
+                                }
                                 else bulk_g2s(sW + stage * W_BYTES, wsrc, W_BYTES, bar(B_WFULL + stage));
                             }
                             if (++stage == NSTAGE) { stage = 0; ph ^= 1; }
@@ -601,7 +605,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
         if (warp == 12 && !dual) {
             // single-issuer mode (profiling A/B): nothing to do
         } else {
-            IssueCtx c{sBar, sW, sX, tbase, 0u, 0u, P.fault, P.dbg, (blockIdx.x == 0 && lane == 0) ? P.trace : nullptr, 0, 0, warp == 12 ? 1 : 0, dual, P.pair != 0};
+            IssueCtx c{sBar, sW, sX, tbase, 0u, 0u, P.fault, P.dbg, (blockIdx.x == 0 && lane == 0) ? P.trace : nullptr, 0, 0, warp == 12 ? 1 : 0, dual, P.pair != 0, (uint16_t)((1u << (P.pair ? P.pair : 1)) - 1u)};
             uint32_t cnt0 = 0, cnt1 = 0;
             int wi = 0, k = 0;                 // wi: work items done (phase of the accumulator units)
             for (;; wi++) {
@@ -769,7 +773,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
                 fence_proxy_async();
                 __syncwarp();
                 unsigned int last = 0;
-                if (lane == 0) last = atom_add_acq_rel_gpu(P.sched + 2 + item, 1u) == (P.pair ? 2 * FLAG_DONE : FLAG_DONE) - 1 ? 1u : 0u;
+                if (lane == 0) last = atom_add_acq_rel_gpu(P.sched + 2 + item, 1u) == (unsigned)csize * FLAG_DONE - 1 ? 1u : 0u;
                 last = __shfl_sync(0xFFFFFFFFu, last, 0);
                 if (last) {
                     // last of the 8 epilogue warps to finish the item
@@ -794,7 +798,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tower(const __grid_constant__ P
 // ready queue before the launch: head 0, tail n_tiles, no completions, the stem items in slots 0..n_tiles-1
 constexpr int MAILBOX_WORDS = 128 * 64;     // pair mode: 64 words per cluster
 __global__ void k_sched_init(unsigned int* sched, int n_tiles_max, int n_layers, const int* n_active, int pair, unsigned int* mailbox) {
-    const int n_tiles = tiles_of(n_active, n_tiles_max), n_units = pair ? (n_tiles + 1) / 2 : n_tiles, n_items = n_layers * n_units;
+    const int n_tiles = tiles_of(n_active, n_tiles_max), n_units = pair ? (n_tiles + pair - 1) / pair : n_tiles, n_items = n_layers * n_units;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 + 2 * n_items; i += gridDim.x * blockDim.x) {
         unsigned int v = 0u;
         if (i == 1) v = (unsigned int)n_units;
@@ -1021,21 +1025,24 @@ int hz_tower_forward_heads(const void* x0_tiles, const void* const* w_tiles, con
     const int n_items = P.n_layers * P.n_tiles;
     // pair mode (clusters of two CTAs sharing the weight stream by multicast) unless switched off or there is a single tile
     static const bool no_pair = getenv("HZ_TOWER_NO_PAIR") != nullptr;
-    P.pair = (!no_pair && P.n_tiles >= 2 && grid_for(P.n_tiles) >= 2) ? 1 : 0;
+    static const int want_c = getenv("HZ_TOWER_CLUSTER") ? atoi(getenv("HZ_TOWER_CLUSTER")) : 2;     // CTAs per cluster: 2 (default) or 4
+    int csz = (no_pair || want_c < 2) ? 0 : (want_c >= 4 ? 4 : 2);
+    while (csz >= 2 && (P.n_tiles < csz || grid_for(P.n_tiles) < csz)) csz >>= 1;
+    P.pair = csz >= 2 ? csz : 0;
     P.mailbox = P.sched + (2 + 2 * (size_t)MAX_LAYERS_SCHED(n_blocks) * P.n_tiles);
     k_sched_init<<<(2 + 2 * n_items + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P.sched, P.n_tiles, P.n_layers, n_active, P.pair, P.mailbox);
     if (P.pair) {
-        const int n_pairs = (P.n_tiles + 1) / 2;
-        int clusters = grid_for(P.n_tiles) / 2;
-        if (clusters > n_pairs) clusters = n_pairs;
+        const int n_units = (P.n_tiles + P.pair - 1) / P.pair;
+        int clusters = grid_for(P.n_tiles) / P.pair;
+        if (clusters > n_units) clusters = n_units;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * clusters);
+        cfg.gridDim = dim3(P.pair * clusters);
         cfg.blockDim = dim3(NTHREADS);
         cfg.dynamicSmemBytes = SMEM_BYTES;
         cfg.stream = (cudaStream_t)stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[0].val.clusterDim.x = P.pair; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
         cudaError_t e = cudaLaunchKernelEx(&cfg, k_tower, P);
