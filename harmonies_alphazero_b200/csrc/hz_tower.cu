@@ -31,6 +31,8 @@
 //     complete and drained before pass 1 starts; pass 1 runs dy = -1, 0, +1, so row 4 (no dy = +1)
 //     is drained before the next tile's row 0 needs the unit.  The epilogue of one row therefore
 //     always overlaps the MMAs of the others.
+//   * hz_tower_forward*: clusters of two CTAs take pairs of neighbouring tiles of one layer and share the weight
+//     stream: each CTA loads half of every stage and multicasts it to both (cluster mode, see Params::pair).
 //   * warp roles: 0 = weight producer, 1 and 12 = MMA issuers (alternating weight stages), 2 =
 //     activation producer, 3 = TMEM allocator + work scheduler, 4..11 = epilogue (bias + residual +
 //     ReLU + bf16, thread = output channel).
