@@ -649,19 +649,24 @@ def run_b200(args):
     e2e_sync_value = int(host_api.total.item()) / (q0.elapsed_time(q1) * 1e-3)
     # the K batches as one pipelined stream (HostPlayout.run_keys_many): every batch is still copied
     # in from pinned host memory and read back, the copies of neighbouring batches overlap the kernel
-    host_api.total.zero_()
-    barrier()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record(stream)
-    host_api.run_keys_many(key_stream, res_stream)      # returns after the last D2H completed
-    k1.record(stream)
-    barrier()
-    t3 = torch.tensor([k0.elapsed_time(k1)], dtype=torch.float64, device=dev)
-    s3 = host_api.total.clone()
-    if world > 1:
-        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
-        dist.all_reduce(s3, op=dist.ReduceOp.SUM)
-    e2e_value = int(s3.item()) / (float(t3.item()) * 1e-3)
+    # The call lasts ~2 ms, so one descheduled host thread on one rank is visible in the max over ranks: the K-batch call is
+    # timed three times (each bracketed by barriers, max over ranks) and the MEDIAN repetition is reported; all three are kept.
+    e2e_reps = []
+    for _rep in range(3):
+        host_api.total.zero_()
+        barrier()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        host_api.run_keys_many(key_stream, res_stream)      # returns after the last D2H completed
+        k1.record(stream)
+        barrier()
+        t3 = torch.tensor([k0.elapsed_time(k1)], dtype=torch.float64, device=dev)
+        s3 = host_api.total.clone()
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+            dist.all_reduce(s3, op=dist.ReduceOp.SUM)
+        e2e_reps.append(int(s3.item()) / (float(t3.item()) * 1e-3))
+    e2e_value = sorted(e2e_reps)[1]
     assert int((pinned_res[:, 0] >> 29).min()) >= 1, "every game must have a winner code"
 
     # ---- the same wave with unfused per-step kernels (K1 legal_mask + policy + K2 apply): the
@@ -702,6 +707,7 @@ def run_b200(args):
                    "games_per_gpu": n, "engine_steps_per_wave": steps_all // K,
                    "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"games sharded x{world}, no collective"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * 12,
+                "repetitions": e2e_reps, "reported": "median of three K-batch calls",
                 "api": "HostPlayout.run_keys_many: K batches of pinned host keys in, (meta, scores, length) per game out, "
                        "copies of neighbouring batches overlap the kernel (3 device buffer pairs); the call replays the "
                        "whole copy/kernel pipeline as one CUDA graph when it is given the same pinned buffer ring again",

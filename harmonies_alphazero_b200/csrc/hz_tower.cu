@@ -349,8 +349,8 @@ struct StageLoop {
             __syncwarp();
             if (c.dual && last_in_turn) named_bar_arrive(c.parity ? 2 : 1);
             if (lead) {
-                if (c.pair) umma_commit_mc(c.bar0 + 8u * (B_WEMPTY + c.stage), c.cmask);   // ... in every CTA of the cluster
-                else umma_commit(c.bar0 + 8u * (B_WEMPTY + c.stage));      // frees the weight stage when these MMAs have read it
+                // frees the weight stage when these MMAs have read it — in every CTA of the cluster (mask 1 = this CTA alone)
+                umma_commit_mc(c.bar0 + 8u * (B_WEMPTY + c.stage), c.cmask);
                 if (last_kh) {
 #pragma unroll
                     for (int r = r0; r < r1; r++)
@@ -408,8 +408,7 @@ struct HeadStage {
             __syncwarp();
             if (c.dual) named_bar_arrive(c.parity ? 2 : 1);
             if (lead) {
-                if (c.pair) umma_commit_mc(c.bar0 + 8u * (B_WEMPTY + c.stage), c.cmask);
-                else umma_commit(c.bar0 + 8u * (B_WEMPTY + c.stage));
+                umma_commit_mc(c.bar0 + 8u * (B_WEMPTY + c.stage), c.cmask);
                 if (last_kh) {
 #pragma unroll
                     for (int r = r0; r < r1; r++) umma_commit(c.bar0 + 8u * (B_TFULL + unit_of(r)));
