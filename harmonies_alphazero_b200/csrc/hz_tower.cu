@@ -349,8 +349,10 @@ struct StageLoop {
             __syncwarp();
             if (c.dual && last_in_turn) named_bar_arrive(c.parity ? 2 : 1);
             if (lead) {
-                // frees the weight stage when these MMAs have read it — in every CTA of the cluster (mask 1 = this CTA alone)
-                umma_commit_mc(c.bar0 + 8u * (B_WEMPTY + c.stage), c.cmask);
+                // frees the weight stage when these MMAs have read it (cluster mode: in every CTA of the cluster; the multicast
+                // form with a mask of 1 in a launch without clusters was tried to save the branch: it faults)
+                if (c.pair) umma_commit_mc(c.bar0 + 8u * (B_WEMPTY + c.stage), c.cmask);
+                else umma_commit(c.bar0 + 8u * (B_WEMPTY + c.stage));
                 if (last_kh) {
 #pragma unroll
                     for (int r = r0; r < r1; r++)
@@ -408,7 +410,8 @@ struct HeadStage {
             __syncwarp();
             if (c.dual) named_bar_arrive(c.parity ? 2 : 1);
             if (lead) {
-                umma_commit_mc(c.bar0 + 8u * (B_WEMPTY + c.stage), c.cmask);
+                if (c.pair) umma_commit_mc(c.bar0 + 8u * (B_WEMPTY + c.stage), c.cmask);
+                else umma_commit(c.bar0 + 8u * (B_WEMPTY + c.stage));
                 if (last_kh) {
 #pragma unroll
                     for (int r = r0; r < r1; r++) umma_commit(c.bar0 + 8u * (B_TFULL + unit_of(r)));
