@@ -112,8 +112,10 @@ class InferenceNet:
         self.load(model)
 
     def load(self, model):
-        """(Re)build the folded weights from ``model`` (after a weight broadcast / checkpoint)."""
+        """(Re)build the folded weights from ``model`` (after a weight broadcast / checkpoint).  Every load gets a new
+        ``version``: drivers that captured CUDA graphs over the previous weight tensors re-capture (selfplay._Group)."""
         dev, dt = self.device, self.dtype
+        self.version = getattr(self, "version", 0) + 1
 
         def conv_params(conv, bn):
             w, b = _fold(conv, bn)

@@ -145,6 +145,7 @@ class _Group:
         self.noise = None if cfg.testing else torch.ones((n, 143), dtype=torch.float32, device=dev)
         self.alpha = None if cfg.testing else torch.full((n, 143), cfg.dirichlet_alpha, dtype=torch.float32, device=dev)
         self.graph = None
+        self.graph_version = 0
         self.stream = torch.cuda.Stream(device=dev) if owner.n_groups > 1 else None
         # [active trees, active leaf rows]: read on the device by the tree kernels and the hand-written network path,
         # so the captured graph follows it (hz_tree_set_active)
@@ -235,8 +236,11 @@ class BatchedSelfPlay:
         main = torch.cuda.current_stream(self.device)
         for g in self.groups:
             g.prepare(states)
+            if g.graph is not None and g.graph_version != getattr(self.net, "version", 0):
+                g.graph = None                    # the network was reloaded: the captured launches point at the old weights
             if cfg.use_cuda_graph and g.graph is None:
                 g.capture()
+                g.graph_version = getattr(self.net, "version", 0)
                 g.tree.reset(states[g.lo:g.hi])   # the warm-up/capture advanced the trees
         for g in self.groups:
             if g.stream is not None:

@@ -416,3 +416,32 @@ def test_head_convolutions_as_a_tower_work_item(tw):
     torch.cuda.synchronize()
     assert torch.equal(out[0][:77], l_in[:77]) and torch.equal(out[1][:77], v_in[:77])
     assert bool((out[0][77:] == -7.0).all())
+
+
+def test_reloaded_weights_take_effect_under_the_captured_graph(tw):
+    """InferenceNet.load() after a weight broadcast: a driver that already captured its simulation step as a CUDA graph
+    must search with the NEW weights (it re-captures on the network's version), exactly like a fresh driver."""
+    from harmonies_alphazero_b200 import batched as hb
+    from harmonies_alphazero_b200 import net as hnet
+    from harmonies_alphazero_b200 import selfplay as sp
+
+    def model(seed):
+        torch.manual_seed(seed)
+        return hnet.AlphaZeroNet.from_config(hnet.DEFAULT_MODEL_CONFIG).eval()
+
+    cfg = sp.SelfPlayConfig(n_slots=32, num_simulations=16, seed=9, testing=True)
+    states = hb.init_states(32, seed=17)
+    hb.playout(states, max_steps=13)
+    inf = hnet.InferenceNet(model(1), device="cuda", tower="hand")
+    drv = sp.BatchedSelfPlay(inf, cfg)
+    drv.search(states)
+    v_old = drv.root_policy()[0].clone()
+    assert drv.graph is not None
+    inf.load(model(2))
+    drv.search(states)
+    v_new = drv.root_policy()[0].clone()
+    fresh = sp.BatchedSelfPlay(hnet.InferenceNet(model(2), device="cuda", tower="hand"), cfg)
+    fresh.search(states)
+    v_ref = fresh.root_policy()[0]
+    assert torch.equal(v_new, v_ref)
+    assert not torch.equal(v_old, v_new)
