@@ -285,6 +285,8 @@ class BatchedSelfPlay:
         chunks, bad_status = [], torch.zeros((), dtype=torch.uint8, device=dev)
         live_sims = 0
         compact = cfg.compact_live and self.n_groups == 1
+        for g in self.groups:
+            g.set_active(g.hi - g.lo)             # (a previous call that raised may have left a smaller active prefix)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         step = 0
