@@ -81,7 +81,11 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, interval=0.0002):
+        # interval: seconds between NVML polls.  The engine leg lasts milliseconds and is polled as fast as NVML answers;
+        # the seconds-long MCTS legs are polled every 20 ms (NVML calls take driver locks that kernel launches need too:
+        # eight ranks polling at kHz rates slowed each other's whole-game loops)
+        self.interval = interval
         self.index, self.rows, self.proc = index, [], None
         self.nvml, self.samples, self.stop_flag = None, [], False
         try:  # in-process NVML polls every ~1 ms: the timed region of this bench is milliseconds long
@@ -103,7 +107,7 @@ class ClockSampler:
                 self.samples.append((time.perf_counter(), sm, [k for k, bit in R.items() if rs & bit]))
             except Exception:
                 break
-            time.sleep(0.0002)
+            time.sleep(self.interval)
 
     def start(self):
         if self.nvml:
@@ -136,7 +140,7 @@ class ClockSampler:
             except Exception:
                 mx = None
             return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": reasons,
-                    "samples": len(sm), "source": "nvml, ~1 ms polling during the timed region"}
+                    "samples": len(sm), "source": f"nvml, polled every {self.interval * 1e3:g} ms (plus the call) during the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -310,7 +314,7 @@ def mcts_measure(args, dev, world, rank, dist, with_collectives=True, tower=None
         dist.barrier()
     torch.cuda.synchronize()
     l0 = hb.launch_count()
-    sampler = ClockSampler(dev.index if dev.index is not None else 0)
+    sampler = ClockSampler(dev.index if dev.index is not None else 0, interval=0.02)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -378,7 +382,7 @@ def mcts_measure(args, dev, world, rank, dist, with_collectives=True, tower=None
             dist.barrier()
         torch.cuda.synchronize()
         l1 = hb.launch_count()
-        sampler2 = ClockSampler(dev.index if dev.index is not None else 0)
+        sampler2 = ClockSampler(dev.index if dev.index is not None else 0, interval=0.02)
         sampler2.start()
         traj = drv.play(play_games)
         torch.cuda.synchronize()
