@@ -535,7 +535,7 @@ def run_b200(args):
 
     # clocks over the WHOLE engine leg (warm-up, timed waves, end-to-end legs, unfused comparison: tens of milliseconds,
     # i.e. more than the one or two NVML samples that fit in the 2 ms timed region itself)
-    leg_sampler = ClockSampler(local)
+    leg_sampler = ClockSampler(local, interval=0.005)     # (kHz polling here slowed the end-to-end legs of eight ranks)
     leg_sampler.start()
     # ---- kernel-resident timing: inputs already in HBM
     for w in range(W):
