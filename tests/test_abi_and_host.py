@@ -156,3 +156,44 @@ def test_network_is_the_reference_model():
     l2, v2 = inf(b, gl)
     assert np.abs(l2.numpy() - g["logits"]).max() < 1e-4 and np.abs(v2.numpy() - g["value"]).max() < 1e-5
     assert np.abs(torch.softmax(l2, 1).numpy() - g["probs"]).max() < 1e-5      # ModelManager.predict: unmasked softmax
+
+
+def test_tower_weight_images_follow_the_documented_layout():
+    """tower.pack_conv_weight / pack_head_weight (host side of hz_tower_forward*): element (tap, out o, in i) of the folded
+    weights sits where include/harmonies_b200.h says the K-major SWIZZLE_128B tile keeps it — half i // 64, row o of 128
+    bytes, 16-byte group ((i % 64) // 8) ^ (o & 7), element i % 8 — and the head filters are split into bf16 high + low rows
+    whose sum reproduces the fp32 filter to 2^-16 relative."""
+    import torch
+
+    from harmonies_alphazero_b200 import tower
+
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn((128, 128, 3, 3), generator=g)
+    img, nkh = tower.pack_conv_weight(w)
+    assert nkh == 2 and tuple(img.shape) == (9, 2, 128, 128) and img.dtype == torch.uint8
+    as_bf16 = img.view(torch.bfloat16).reshape(9, 2, 128, 64)          # [tap][half][row o][64 elements of the row]
+    wb = w.to(torch.bfloat16)
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        tap, o, i = int(rng.integers(9)), int(rng.integers(128)), int(rng.integers(128))
+        half, grp, e = i // 64, (i % 64) // 8, i % 8
+        pos = ((grp ^ (o & 7)) * 8) + e
+        assert as_bf16[tap, half, o, pos] == wb[o, i, tap // 3, tap % 3]
+    # 38 input planes (the stem): one half, planes 38..63 zero
+    ws = torch.randn((128, 38, 3, 3), generator=g)
+    simg, snkh = tower.pack_conv_weight(ws)
+    assert snkh == 1
+    sb = simg.view(torch.bfloat16).reshape(9, 1, 128, 64)
+    assert float(sb.float().abs().sum()) == pytest.approx(float(ws.to(torch.bfloat16).float().abs().sum()), rel=1e-6)
+    # head filters: rows 0..2 high parts, rows 3..5 low parts, the rest zero
+    wh = torch.randn((3, 128), generator=g) * 0.3
+    himg, hnkh = tower.pack_head_weight(wh)
+    assert hnkh == 2 and tuple(himg.shape) == (2, 128, 128)
+    hb = himg.view(torch.bfloat16).reshape(2, 128, 64).float()
+    assert float(hb[:, 6:, :].abs().max()) == 0.0
+    for j in range(3):
+        for i in (0, 7, 8, 63, 64, 100, 127):
+            half, grp, e = i // 64, (i % 64) // 8, i % 8
+            hi = hb[half, j, ((grp ^ (j & 7)) * 8) + e]
+            lo = hb[half, j + 3, ((grp ^ ((j + 3) & 7)) * 8) + e]
+            assert abs(float(hi + lo) - float(wh[j, i])) <= abs(float(wh[j, i])) * 2.0 ** -15 + 1e-12
