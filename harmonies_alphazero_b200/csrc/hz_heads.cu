@@ -388,6 +388,122 @@ __global__ void __launch_bounds__(FTPB, 1) k_heads_p(const __nv_bfloat16* __rest
     }
 }
 
+// ---- FC heads on the tensor cores (the tile path's default) --------------------------------------------------
+// policy_fc (112 -> 143) and value_fc1 (77 -> 256) + value_fc2 + tanh for 32 positions per block, as mma.sync
+// m16n8k16: M = 16 output units, N = 8 positions, K = 16 inputs.  Weights AND inputs are split into bf16 high + low
+// parts and three products are accumulated in fp32 (hi*hi + hi*lo + lo*hi: 2^-16 relative, fp32-weight accuracy).
+// A warp owns output-unit tiles; it reads its weight fragments straight from global memory (L2) into registers ONCE
+// and reuses them for the block's four position tiles, so the 143 KB of weights are never staged in shared memory and
+// there is a single block barrier before the arithmetic (the FMA kernel above spent most of its 21 us at barriers).
+constexpr int MB = 32;                        // positions per block
+constexpr int MT_POL = 9, MT_VAL = 16;        // 16-unit tiles: 144 >= 143 policy logits, 256 hidden units
+constexpr int KS_POL = 7, KS_VAL = 5;         // 16-input steps: 112, 80 >= 77
+constexpr int SP = 120, SV = 88;              // shared-memory row strides in bf16 (bank-conflict free for the B fragments)
+constexpr int MTPB = 512;
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__global__ void __launch_bounds__(MTPB, 1) k_heads_fc_mma(const float* __restrict__ hc, const __nv_bfloat16* __restrict__ glob, int64_t n,
+                                                          HeadParams P, float* __restrict__ logits, float* __restrict__ value,
+                                                          const int* __restrict__ n_active, int hc_tiled) {
+    __shared__ __align__(16) __nv_bfloat16 s_ph[MB][SP], s_pl[MB][SP], s_vh[MB][SV], s_vl[MB][SV];
+    __shared__ float s_part[MT_VAL][MB];       // value_fc2 partial sums per unit tile: summed in a fixed order (bit-reproducible)
+    if (n_active) n = min(n, (int64_t)max(*n_active, 0));
+    const int64_t base = (int64_t)blockIdx.x * MB;
+    if (base >= n) return;
+    const int cnt = (int)min((int64_t)MB, n - base), t = threadIdx.x;
+    auto hc_at = [&](int64_t bd, int j) { return hc_tiled ? hc[(bd >> 4) * (3 * CELLS * 16) + j * 16 + (bd & 15)] : hc[bd * (3 * CELLS) + j]; };
+    // inputs (model.py:343-346,351-352): policy = [conv ch0 | conv ch1 | global], value = [conv ch2 | global], as bf16 hi + lo
+    for (int i = t; i < MB * PIN; i += MTPB) {
+        const int p = i / PIN, j = i - PIN * p;
+        float v = 0.0f;
+        if (p < cnt) v = j < 2 * CELLS ? hc_at(base + p, j) : __bfloat162float(glob[(base + p) * NGLOB + (j - 2 * CELLS)]);
+        split_bf16(v, s_ph[p][j], s_pl[p][j]);
+    }
+    for (int i = t; i < MB * 80; i += MTPB) {
+        const int p = i / 80, j = i - 80 * p;
+        float v = 0.0f;
+        if (p < cnt && j < VIN) v = j < CELLS ? hc_at(base + p, 2 * CELLS + j) : __bfloat162float(glob[(base + p) * NGLOB + (j - CELLS)]);
+        split_bf16(v, s_vh[p][j], s_vl[p][j]);
+    }
+    for (int i = t; i < MT_VAL * MB; i += MTPB) (&s_part[0][0])[i] = 0.0f;
+    __syncthreads();
+    const int warp = t >> 5, lane = t & 31, g = lane >> 2, q = lane & 3;
+    for (int mt = warp; mt < MT_POL + MT_VAL; mt += MTPB / 32) {
+        const bool pol = mt < MT_POL;
+        const int m = pol ? mt : mt - MT_POL, KS = pol ? KS_POL : KS_VAL, NU = pol ? NPOL : FH, KR = pol ? PIN : VIN;
+        const float* __restrict__ WT = pol ? P.w_pol_t : P.w_v1_t;          // [input j][unit u]
+        const int u0 = m * 16 + g, u1 = u0 + 8;
+        uint32_t ah[KS_POL][4], al[KS_POL][4];
+#pragma unroll
+        for (int ks = 0; ks < KS_POL; ks++) {
+            if (ks < KS) {
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const int u = (r & 1) ? u1 : u0, j = ks * 16 + 2 * q + (r >> 1) * 8;
+                    const float w0 = (u < NU && j < KR) ? WT[(size_t)j * NU + u] : 0.0f;
+                    const float w1 = (u < NU && j + 1 < KR) ? WT[(size_t)(j + 1) * NU + u] : 0.0f;
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    split_bf16(w0, h0, l0);
+                    split_bf16(w1, h1, l1);
+                    ah[ks][r] = pack_bf16(h0, h1);
+                    al[ks][r] = pack_bf16(l0, l1);
+                }
+            }
+        }
+        const float* __restrict__ B = pol ? P.b_pol : P.b_v1;
+        const float bias0 = u0 < NU ? B[u0] : 0.0f, bias1 = u1 < NU ? B[u1] : 0.0f;
+        const float w2a = (!pol) ? P.w_v2[u0] : 0.0f, w2b = (!pol) ? P.w_v2[u1] : 0.0f;
+#pragma unroll 1
+        for (int nt = 0; nt < MB / 8; nt++) {
+            if (nt * 8 >= cnt) break;
+            float c[4] = {bias0, bias0, bias1, bias1};
+            const int p = nt * 8 + g;
+            const __nv_bfloat16* rh = pol ? &s_ph[p][0] : &s_vh[p][0];
+            const __nv_bfloat16* rl = pol ? &s_pl[p][0] : &s_vl[p][0];
+#pragma unroll
+            for (int ks = 0; ks < KS_POL; ks++) {
+                if (ks < KS) {
+                    const int j = ks * 16 + 2 * q;
+                    const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(rh + j), bh1 = *reinterpret_cast<const uint32_t*>(rh + j + 8);
+                    const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(rl + j), bl1 = *reinterpret_cast<const uint32_t*>(rl + j + 8);
+                    mma_bf16_16816(c, ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], bh0, bh1);
+                    mma_bf16_16816(c, ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], bl0, bl1);
+                    mma_bf16_16816(c, al[ks][0], al[ks][1], al[ks][2], al[ks][3], bh0, bh1);
+                }
+            }
+            const int pc = nt * 8 + 2 * q;                               // this lane's two positions (accumulator columns)
+            if (pol) {
+                if (pc < cnt) {
+                    if (u0 < NPOL) logits[(base + pc) * NPOL + u0] = c[0];
+                    if (u1 < NPOL) logits[(base + pc) * NPOL + u1] = c[2];
+                }
+                if (pc + 1 < cnt) {
+                    if (u0 < NPOL) logits[(base + pc + 1) * NPOL + u0] = c[1];
+                    if (u1 < NPOL) logits[(base + pc + 1) * NPOL + u1] = c[3];
+                }
+            } else {
+                // value_fc2 on relu(hidden) (model.py:353-355): this lane's two units, then the eight unit rows of the tile
+                float s0 = fmaf(fmaxf(c[2], 0.0f), w2b, fmaxf(c[0], 0.0f) * w2a), s1 = fmaf(fmaxf(c[3], 0.0f), w2b, fmaxf(c[1], 0.0f) * w2a);
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, o);
+                    s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, o);
+                }
+                if (g == 0) { s_part[m][pc] = s0; s_part[m][pc + 1] = s1; }
+            }
+        }
+    }
+    __syncthreads();
+    if (t < cnt) {
+        float sum = P.b_v2;
+#pragma unroll
+        for (int m = 0; m < MT_VAL; m++) sum += s_part[m][t];
+        value[base + t] = tanhf(sum);                                    // model.py:355
+    }
+}
+
 // ---- 1x1 head convolutions on the tower's T16 tiles (include/harmonies_b200.h) --------------------
 // One block per 16-board tile, all 256 tiles of a 4,096-leaf step resident at once (two blocks per SM).
 // Thread = (8 consecutive positions, one quarter of the channels): a 16-byte load is 8 positions of one
@@ -487,6 +603,12 @@ extern "C" int hz_net_heads_fc_active(const float* head_conv, const void* glob, 
     if (!head_conv || !glob || !w_pol_t || !b_pol || !w_v1_t || !b_v1 || !w_v2 || !logits || !value || n < 0) return HZ_ERR_ARG;
     if (H != hz::FH || (((uintptr_t)w_v1_t | (uintptr_t)w_pol_t) & 15)) return HZ_ERR_ARG;
     hz::HeadParams P{nullptr, nullptr, w_pol_t, b_pol, w_v1_t, b_v1, w_v2, b_v2, hz::FC, H};
+    static const bool use_fma = getenv("HZ_FC_FMA") != nullptr;           // A/B switch: the fp32-FMA kernel
+    if (!use_fma) {
+        hz::k_heads_fc_mma<<<(unsigned)((n + hz::MB - 1) / hz::MB), hz::MTPB, 0, (cudaStream_t)stream>>>(
+            head_conv, (const __nv_bfloat16*)glob, n, P, logits, value, n_active, hc_tiled);
+        return hz_launched(1);
+    }
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
