@@ -605,6 +605,76 @@ __device__ __forceinline__ int apply_move(State& s, int a, uint32_t explicit_cod
     return end_turn<DEFER_SCORE, REL>(s, pl, t.occ0 | bit, hand, use_explicit, explicit_code, dkey, devent, bump_event, lut, rtab);
 }
 
+// ---- one step of the uniform-random playout (fused kernel only) -------------------------------------
+// legal_of + random_action + apply_move for a mover-relative state, for a move that is legal BY CONSTRUCTION: the action is
+// drawn from the legal set computed here, so apply_move's validation (harmonies_engine.py:217-281) cannot fail and is not
+// repeated, tile and hex are not re-derived from the action index, and the planes are updated in place (apply_move works
+// on a copy because it must leave the state untouched on an error: that copy was 36 register moves per placement).
+// Same draws, same result as the three calls (tests: fused playout == unfused kernels == oracle).  false: no legal move.
+template <bool DEFER_SCORE>
+__device__ __forceinline__ bool playout_step(State& s, const NbrLut* lut, const uint64_t* rtab) {
+    const int ph = phase_of(s);
+    const uint64_t r = rand64_t(rtab, key_of(s) ^ HZ_PLAYOUT_SALT, (uint64_t)s.w[HZ_W_MOVES]);
+    const uint32_t rh = (uint32_t)(r >> 32);
+    if (ph == HZ_PHASE_CHOOSE) {                                      // :158, :217-223
+        const int np = n_piles_of(s);
+        if (np == 0) return false;
+        const int a = (int)__umulhi(rh, (uint32_t)np);
+        Piles P = piles_of(s);
+        uint32_t hand = P.p[0];
+#pragma unroll
+        for (int j = 1; j < 5; j++) hand = (a == j) ? P.p[j] : hand;
+#pragma unroll
+        for (int j = 0; j < 4; j++) P.p[j] = (j >= a) ? P.p[j + 1] : P.p[j];
+        P.p[4] = 0;
+        set_piles(s, P, hand, np - 1);
+        set_meta(s, (meta(s) & ~0xEu) | (HZ_PHASE_PLACE1 << 1));
+        s.w[HZ_W_MOVES]++;
+        return true;
+    }
+    if (ph > HZ_PHASE_PLACE3) return false;
+    uint32_t hand = hand_of(s);
+    Board b;
+#pragma unroll
+    for (int k = 0; k < 9; k++) b.p[k] = s.w[k];
+    const Tops t = tops_of(b);
+    const uint32_t empty = ~t.occ0 & VALID;                            // :173
+    const uint32_t x1 = top_wood(t) & ~t.occ2, x3 = top_stone(t) & ~t.occ2;                     // :183, :186
+    const uint32_t x4 = (top_wood(t) | top_stone(t) | top_building(t)) & ~t.occ1;               // :190-192
+    const uint32_t m0 = (hand & 0x003) ? empty : 0, m1 = (hand & 0x00C) ? (empty | x1) : 0, m2 = (hand & 0x030) ? empty : 0;
+    const uint32_t m3 = (hand & 0x0C0) ? (empty | x3) : 0, m4 = (hand & 0x300) ? (empty | x4) : 0, m5 = (hand & 0xC00) ? empty : 0;
+    const int c0 = __popc(m0), c1 = c0 + __popc(m1), c2 = c1 + __popc(m2), c3 = c2 + __popc(m3), c4 = c3 + __popc(m4);
+    const int n = c4 + __popc(m5);
+    if (n == 0) return false;
+    const int k = (int)__umulhi(rh, (uint32_t)n);
+    // the type whose cumulative count covers k: the five comparisons are monotone, each one moves (type, mask, base) on
+    int tile = 0, below = 0;
+    uint32_t m = m0;
+    if (k >= c0) { tile = 1; m = m1; below = c0; }
+    if (k >= c1) { tile = 2; m = m2; below = c1; }
+    if (k >= c2) { tile = 3; m = m3; below = c2; }
+    if (k >= c3) { tile = 4; m = m4; below = c3; }
+    if (k >= c4) { tile = 5; m = m5; below = c4; }
+    const uint32_t bit = 1u << nth_set_bit(m, k - below);
+    // place the tile on level h of the hex (:257,275)
+    const uint32_t code = (uint32_t)tile + 1u;
+    const uint32_t at0 = bit & ~t.occ0, at1 = bit & t.occ0 & ~t.occ1, at2 = bit & t.occ1;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        const uint32_t on = (code >> q) & 1u ? 0xFFFFFFFFu : 0u;
+        s.w[q] |= at0 & on; s.w[3 + q] |= at1 & on; s.w[6 + q] |= at2 & on;
+    }
+    hand -= 1u << (2 * tile);                                         // hand.remove, :250
+    s.w[HZ_W_PILE4H] = (s.w[HZ_W_PILE4H] & 0xFFFFu) | (hand << 16);
+    s.w[HZ_W_MOVES]++;
+    if (ph != HZ_PHASE_PLACE3) {
+        set_meta(s, meta(s) + 2u);                                    // phase+1, :287-290
+        return true;
+    }
+    end_turn<DEFER_SCORE, true>(s, player_of(s), t.occ0 | bit, hand, false, HZ_NO_DRAW, key_of(s), s.w[HZ_W_EVENT], true, lut, rtab);
+    return true;
+}
+
 // ---- canonical keys ----------------------------------------------------------------------------
 // Leftmost-embedding normal form of one board under the reference's hash aliasing
 // (HZ_KEY_REFERENCE in harmonies_b200.h).  Alias pairs {1,6},{2,7},{3,8} (shift 5) and

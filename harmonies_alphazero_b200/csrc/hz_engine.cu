@@ -266,9 +266,13 @@ __global__ void __launch_bounds__(PTPB) k_playout(void* states, int64_t n, int m
         else load_state(s, states, g);
         if (player_of(s)) swap_boards(s);   // mover-relative board order inside the loop (see REL)
         while ((int)k < max_steps && phase_of(s) != HZ_PHASE_OVER) {
+#ifdef HZ_PLAYOUT_CHECKED   // A/B: the three general calls (validation + board copy in apply_move)
             int a = random_action(s, legal_of<true>(s), rtab);
             if (a < 0) break;  // stuck position (no legal move, not over): harmonies_engine.py:205-208
             if (apply_move<true, true>(s, a, HZ_NO_DRAW, key_of(s), s.w[HZ_W_EVENT], true, &lut, rtab) != HZ_MOVE_OK) break;
+#else
+            if (!playout_step<true>(s, &lut, rtab)) break;  // stuck position (no legal move, not over): harmonies_engine.py:205-208
+#endif
             k++;
         }
         if (player_of(s)) swap_boards(s);   // back to absolute order
