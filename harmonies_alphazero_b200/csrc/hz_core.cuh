@@ -75,13 +75,33 @@ __host__ __device__ __forceinline__ uint64_t rand64(uint64_t key, uint64_t ctr) 
 }
 // The inner mix depends on the counter only, and counters are small (move numbers < 200, draw
 // events*8+k < 400): a per-block shared table of the first RTAB_N inner values halves the cost
-// of every random number in the fused playout.  rtab == nullptr computes it.
+// of every random number in the fused playout.  RandTab() computes it.
 constexpr int RTAB_N = 512;
 __device__ __forceinline__ void build_rand_table(uint64_t* rtab) {
     for (int i = threadIdx.x; i < RTAB_N; i += blockDim.x) rtab[i] = mix64((uint64_t)i + 0x9E3779B97F4A7C15ull);
 }
-__device__ __forceinline__ uint64_t rand64_t(const uint64_t* rtab, uint64_t key, uint64_t ctr) {
-    uint64_t inner = (rtab != nullptr && ctr < (uint64_t)RTAB_N) ? rtab[ctr] : mix64(ctr + 0x9E3779B97F4A7C15ull);
+// The table is handed around as its 32-bit shared-window address (0: no table, compute): through a generic pointer the
+// compiler rebuilds the window address (S2R SR_CgaCtaId + LEA) in front of every lookup.
+struct RandTab {
+    uint32_t saddr;
+    __device__ __forceinline__ RandTab(decltype(nullptr) = nullptr) : saddr(0) {}
+    __device__ __forceinline__ explicit RandTab(uint32_t a) : saddr(a) {}
+};
+__device__ __forceinline__ RandTab rand_table_handle(const uint64_t* rtab) {   // rtab: the __shared__ array built above
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(rtab);
+    asm volatile("" : "+r"(a));          // one register for the whole kernel, not rematerialised
+    __builtin_assume(a != 0);
+    return RandTab(a);
+}
+__device__ __forceinline__ uint64_t rand64_t(RandTab rtab, uint64_t key, uint64_t ctr) {
+    uint64_t inner;
+    if (rtab.saddr != 0 && ctr < (uint64_t)RTAB_N) {
+        uint32_t lo, hi;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(rtab.saddr + (uint32_t)ctr * 8u));
+        inner = (uint64_t)lo | ((uint64_t)hi << 32);
+    } else {
+        inner = mix64(ctr + 0x9E3779B97F4A7C15ull);
+    }
     return mix64(key ^ inner);
 }
 
@@ -238,7 +258,7 @@ __device__ __forceinline__ int kth_action(const Legal& L, int k) {
     return 5 + 23 * t + nth_set_bit(m, k - below);
 }
 // the uniform-random playout policy (see hz_random_actions in harmonies_b200.h)
-__device__ __forceinline__ int random_action(const State& s, const Legal& L, const uint64_t* rtab = nullptr) {
+__device__ __forceinline__ int random_action(const State& s, const Legal& L, RandTab rtab = nullptr) {
     int n = legal_count(L);
     if (n == 0) return -1;
     uint64_t r = rand64_t(rtab, key_of(s) ^ HZ_PLAYOUT_SALT, (uint64_t)s.w[HZ_W_MOVES]);
@@ -413,23 +433,31 @@ __device__ __forceinline__ int bag_total(uint64_t bag) {
     return (s & 0xFFFFu) + (s >> 16);
 }
 // draws min(3,total) tiles; returns the pile's multiset code (0 if the bag was empty)
+__device__ __forceinline__ uint32_t shl_clamped(uint32_t v, uint32_t n) {   // v << n, 0 for n >= 32 (PTX shl.b32 clamps)
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+    return r;
+}
 __device__ __forceinline__ uint32_t draw_pile(uint64_t& bag, uint64_t z) {
-    uint32_t code = 0;
+    // the bag as two 32-bit halves (types 0..3 | 4,5): the cumulative counts and the decrement stay 32-bit operations
+    uint32_t lo = (uint32_t)bag, hi = (uint32_t)(bag >> 32), code = 0;
     int total = bag_total(bag);
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         if (total > 0) {
             uint32_t x = (uint32_t)(z >> (21 * j)) & 0x1FFFFFu;
             uint32_t r = (x * (uint32_t)total) >> 21;               // 21+7 bits < 32
-            uint64_t cum = bag * 0x0101010101010101ull;              // byte k = sum of bytes 0..k
-            uint32_t clo = (uint32_t)cum, c4 = (uint32_t)(cum >> 32) & 0xFFu;
+            uint32_t clo = lo * 0x01010101u;                         // byte k = sum of bytes 0..k (totals <= 255: no carries)
+            uint32_t c4 = (clo >> 24) + (hi & 0xFFu);
             uint32_t rr = r * 0x01010101u;
             int t = __popc(__vcmpleu4(clo, rr) & 0x01010101u) + (c4 <= r ? 1 : 0);
-            bag -= 1ull << (8 * t);
+            lo -= shl_clamped(1u, 8u * (uint32_t)t);                 // t >= 4: shifted out
+            hi -= shl_clamped(1u, 8u * (uint32_t)t - 32u);           // t < 4: the count wraps to >= 32, shifted out
             code += 1u << (2 * t);
             total--;
         }
     }
+    bag = (uint64_t)lo | ((uint64_t)hi << 32);
     return code;
 }
 __device__ __forceinline__ bool pile_available(uint64_t bag, uint32_t code) {
@@ -497,7 +525,7 @@ __device__ __forceinline__ void partial_scores(const State& s, const NbrLut* lut
 // draw k of event `devent` of stream `dkey` being rand(dkey, devent*8 + k).  Returns whether the bag
 // was empty BEFORE replenishing (:307).
 __device__ __forceinline__ bool replenish_piles(State& s, uint32_t hand, bool use_explicit, uint32_t explicit_code, uint64_t dkey,
-                                                uint32_t devent, const uint64_t* rtab, int& np_out) {
+                                                uint32_t devent, RandTab rtab, int& np_out) {
     int np = n_piles_of(s);
     uint64_t bag = bag_of(s);
     bool bag_empty_before = bag_total(bag) == 0;                      // :307
@@ -520,7 +548,7 @@ __device__ __forceinline__ bool replenish_piles(State& s, uint32_t hand, bool us
 // _end_turn_actions, also called directly by its GUI: GUI/main.py:364-365.)
 template <bool DEFER_SCORE = false, bool REL = false>
 __device__ __forceinline__ int end_turn(State& s, int pl, uint32_t occ_after, uint32_t hand, bool use_explicit, uint32_t explicit_code,
-                                        uint64_t dkey, uint32_t devent, bool bump_event, const NbrLut* lut, const uint64_t* rtab) {
+                                        uint64_t dkey, uint32_t devent, bool bump_event, const NbrLut* lut, RandTab rtab) {
     bool player_trigger = (23 - __popc(occ_after)) <= 2;              // :304-305
     int np;
     bool bag_empty_before = replenish_piles(s, hand, use_explicit, explicit_code, dkey, devent, rtab, np);
@@ -546,7 +574,7 @@ __device__ __forceinline__ int end_turn(State& s, int pl, uint32_t occ_after, ui
 template <bool DEFER_SCORE = false, bool REL = false>
 __device__ __forceinline__ int apply_move(State& s, int a, uint32_t explicit_code, uint64_t dkey,
                                           uint32_t devent, bool bump_event, const NbrLut* lut,
-                                          const uint64_t* rtab = nullptr) {
+                                          RandTab rtab = nullptr) {
     int ph = phase_of(s);
     if (ph == HZ_PHASE_CHOOSE) {
         int np = n_piles_of(s);
@@ -606,13 +634,15 @@ __device__ __forceinline__ int apply_move(State& s, int a, uint32_t explicit_cod
 }
 
 // ---- one step of the uniform-random playout (fused kernel only) -------------------------------------
-// legal_of + random_action + apply_move for a mover-relative state, for a move that is legal BY CONSTRUCTION: the action is
+// legal_of + random_action + apply_move for a state whose mover is player P (a template parameter: the kernel branches on the
+// player once per step, so the mover's planes are words 9P..9P+8 statically — no per-word select on the player bit and no
+// swapping of the two boards when the player changes), for a move that is legal BY CONSTRUCTION: the action is
 // drawn from the legal set computed here, so apply_move's validation (harmonies_engine.py:217-281) cannot fail and is not
 // repeated, tile and hex are not re-derived from the action index, and the planes are updated in place (apply_move works
 // on a copy because it must leave the state untouched on an error: that copy was 36 register moves per placement).
 // Same draws, same result as the three calls (tests: fused playout == unfused kernels == oracle).  false: no legal move.
-template <bool DEFER_SCORE>
-__device__ __forceinline__ bool playout_step(State& s, const NbrLut* lut, const uint64_t* rtab) {
+template <int P, bool DEFER_SCORE>
+__device__ __forceinline__ bool playout_step(State& s, const NbrLut* lut, RandTab rtab) {
     const int ph = phase_of(s);
     const uint64_t r = rand64_t(rtab, key_of(s) ^ HZ_PLAYOUT_SALT, (uint64_t)s.w[HZ_W_MOVES]);
     const uint32_t rh = (uint32_t)(r >> 32);
@@ -636,7 +666,7 @@ __device__ __forceinline__ bool playout_step(State& s, const NbrLut* lut, const 
     uint32_t hand = hand_of(s);
     Board b;
 #pragma unroll
-    for (int k = 0; k < 9; k++) b.p[k] = s.w[k];
+    for (int k = 0; k < 9; k++) b.p[k] = s.w[9 * P + k];
     const Tops t = tops_of(b);
     const uint32_t empty = ~t.occ0 & VALID;                            // :173
     const uint32_t x1 = top_wood(t) & ~t.occ2, x3 = top_stone(t) & ~t.occ2;                     // :183, :186
@@ -658,11 +688,11 @@ __device__ __forceinline__ bool playout_step(State& s, const NbrLut* lut, const 
     const uint32_t bit = 1u << nth_set_bit(m, k - below);
     // place the tile on level h of the hex (:257,275)
     const uint32_t code = (uint32_t)tile + 1u;
-    const uint32_t at0 = bit & ~t.occ0, at1 = bit & t.occ0 & ~t.occ1, at2 = bit & t.occ1;
+    const uint32_t lvl1 = t.occ0 & ~t.occ1;
 #pragma unroll
     for (int q = 0; q < 3; q++) {
-        const uint32_t on = (code >> q) & 1u ? 0xFFFFFFFFu : 0u;
-        s.w[q] |= at0 & on; s.w[3 + q] |= at1 & on; s.w[6 + q] |= at2 & on;
+        const uint32_t bq = (code & (1u << q)) ? bit : 0u;            // the hex in the planes of the code's set bits
+        s.w[9 * P + q] |= bq & ~t.occ0; s.w[9 * P + 3 + q] |= bq & lvl1; s.w[9 * P + 6 + q] |= bq & t.occ1;
     }
     hand -= 1u << (2 * tile);                                         // hand.remove, :250
     s.w[HZ_W_PILE4H] = (s.w[HZ_W_PILE4H] & 0xFFFFu) | (hand << 16);
@@ -671,7 +701,7 @@ __device__ __forceinline__ bool playout_step(State& s, const NbrLut* lut, const 
         set_meta(s, meta(s) + 2u);                                    // phase+1, :287-290
         return true;
     }
-    end_turn<DEFER_SCORE, true>(s, player_of(s), t.occ0 | bit, hand, false, HZ_NO_DRAW, key_of(s), s.w[HZ_W_EVENT], true, lut, rtab);
+    end_turn<DEFER_SCORE, false>(s, P, t.occ0 | bit, hand, false, HZ_NO_DRAW, key_of(s), s.w[HZ_W_EVENT], true, lut, rtab);
     return true;
 }
 

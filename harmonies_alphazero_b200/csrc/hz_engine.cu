@@ -250,10 +250,11 @@ __global__ void __launch_bounds__(PTPB) k_playout(void* states, int64_t n, int m
                                                   unsigned long long* total_steps, const uint64_t* keys,
                                                   uint64_t seed, uint64_t first_id, uint32_t* results) {
     __shared__ NbrLut lut;
-    __shared__ uint64_t rtab[RTAB_N];
+    __shared__ uint64_t rtab_s[RTAB_N];
     __shared__ WaterQueue<2 * PTPB, 2 * PTPB> wq;
     build_nbr_lut(&lut);
-    build_rand_table(rtab);
+    build_rand_table(rtab_s);
+    const RandTab rtab = rand_table_handle(rtab_s);
     water_queue_init(&wq);
     __syncthreads();
     int64_t g = (int64_t)blockIdx.x * PTPB + threadIdx.x;
@@ -264,18 +265,24 @@ __global__ void __launch_bounds__(PTPB) k_playout(void* states, int64_t n, int m
     if (g < n) {
         if (FROM_KEYS) init_state(s, keys ? keys[g] : rand64(seed, first_id + (uint64_t)g));
         else load_state(s, states, g);
-        if (player_of(s)) swap_boards(s);   // mover-relative board order inside the loop (see REL)
+#ifdef HZ_PLAYOUT_CHECKED   // A/B: the three general calls on a mover-relative state (validation + board copy in apply_move)
+        if (player_of(s)) swap_boards(s);
         while ((int)k < max_steps && phase_of(s) != HZ_PHASE_OVER) {
-#ifdef HZ_PLAYOUT_CHECKED   // A/B: the three general calls (validation + board copy in apply_move)
             int a = random_action(s, legal_of<true>(s), rtab);
             if (a < 0) break;  // stuck position (no legal move, not over): harmonies_engine.py:205-208
             if (apply_move<true, true>(s, a, HZ_NO_DRAW, key_of(s), s.w[HZ_W_EVENT], true, &lut, rtab) != HZ_MOVE_OK) break;
-#else
-            if (!playout_step<true>(s, &lut, rtab)) break;  // stuck position (no legal move, not over): harmonies_engine.py:205-208
-#endif
             k++;
         }
-        if (player_of(s)) swap_boards(s);   // back to absolute order
+        if (player_of(s)) swap_boards(s);
+#else
+        // one branch on the player per step: fresh games move in lockstep (same player, same phase in every lane until games
+        // end), and inside a branch the mover's planes are fixed registers
+        while ((int)k < max_steps && phase_of(s) != HZ_PHASE_OVER) {
+            const bool ok = player_of(s) ? playout_step<1, true>(s, &lut, rtab) : playout_step<0, true>(s, &lut, rtab);
+            if (!ok) break;  // stuck position (no legal move, not over): harmonies_engine.py:205-208
+            k++;
+        }
+#endif
         // final scoring deferred to here: the lanes of the warp are converged again; rivers of >= 5
         // hexes go to the block's queue and get a whole warp each (resolve_water)
         fin = phase_of(s) == HZ_PHASE_OVER && winner_code(s) == 0;
