@@ -193,6 +193,10 @@ def headline_roofline(n_games, steps_per_launch, launch_s, clocks, pk, pk_src, a
             "traffic": m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"],
             "kernel": "hz::k_playout", "peak_source": f"148 SMs x 4 schedulers x {sm_mhz:.0f} MHz (SM clock sampled during the timed region)",
             "warp_inst_per_launch": winst, "active_lanes_per_warp_inst": m["smsp__thread_inst_executed.sum"] / winst,
+            "thread_inst_per_engine_step": m["smsp__thread_inst_executed.sum"] / steps_per_launch,
+            "frac_meaning": "issue-slot utilisation of the instructions the kernel executes: it falls when instructions are removed "
+                            "at constant latency.  The round-1 kernel executed 338 thread instructions per engine step at frac 0.46 "
+                            "(95 us per wave); thread_inst_per_engine_step and the launch time say what this build does (DESIGN.md §8)",
             "ncu": {"duration_us": m.get("gpu__time_duration.sum", 0) / 1e3, "issue_active_pct": m.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                     "warps_active_pct": m.get("sm__warps_active.avg.pct_of_peak_sustained_active"), "source": "profiles/r02_playout_counters.json"},
             "note": "achieved = warp instructions per launch (ncu, same sources by sha256) / CUDA-event launch time measured in this run",

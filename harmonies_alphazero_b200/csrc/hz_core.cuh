@@ -798,13 +798,13 @@ __device__ __forceinline__ float global_feature(const uint32_t* w, int g) {
 
 
 // ---- new game (harmonies_engine.py:66-79) ---------------------------------------------------------
-__device__ __forceinline__ void init_state(State& s, uint64_t key) {
+__device__ __forceinline__ void init_state(State& s, uint64_t key, RandTab rtab = nullptr) {
 #pragma unroll
     for (int i = 0; i < SW; i++) s.w[i] = 0;
     uint64_t bag = 23ull | (19ull << 8) | (21ull << 16) | (23ull << 24) | (15ull << 32) | (19ull << 40);
     Piles P;
 #pragma unroll
-    for (int k = 0; k < 5; k++) P.p[k] = draw_pile(bag, rand64(key, (uint64_t)k));   // event 0
+    for (int k = 0; k < 5; k++) P.p[k] = draw_pile(bag, rand64_t(rtab, key, (uint64_t)k));   // event 0
     s.w[HZ_W_KEYLO] = (uint32_t)key; s.w[HZ_W_KEYHI] = (uint32_t)(key >> 32);
     s.w[HZ_W_EVENT] = 1;
     set_bag(s, bag);

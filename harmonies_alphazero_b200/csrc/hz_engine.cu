@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(PTPB) k_playout(void* states, int64_t n, int m
     bool fin = false;
     int s0 = 0, s1 = 0;
     if (g < n) {
-        if (FROM_KEYS) init_state(s, keys ? keys[g] : rand64(seed, first_id + (uint64_t)g));
+        if (FROM_KEYS) init_state(s, keys ? keys[g] : rand64(seed, first_id + (uint64_t)g), rtab);
         else load_state(s, states, g);
 #ifdef HZ_PLAYOUT_CHECKED   // A/B: the three general calls on a mover-relative state (validation + board copy in apply_move)
         if (player_of(s)) swap_boards(s);
