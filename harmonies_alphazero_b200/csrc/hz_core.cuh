@@ -234,15 +234,28 @@ __device__ __forceinline__ void legal_words(const Legal& L, uint32_t out[5]) {
     out[2] = (uint32_t)mid; out[3] = (uint32_t)(mid >> 32);
     out[4] = hi;
 }
+__host__ __device__ constexpr uint32_t nib_sel(int k) {
+    uint32_t t = 0;
+    for (uint32_t y = 0; y < 16; y++) {
+        int c = 0;
+        for (uint32_t b = 0; b < 4; b++)
+            if ((y >> b) & 1u) { if (c == k) t |= b << (2 * y); c++; }
+    }
+    return t;
+}
 // position of the k-th (0-based) set bit of m; k < popc(m)
 __device__ __forceinline__ int nth_set_bit(uint32_t m, int k) {
     int pos = 0, c;
     c = __popc(m & 0xFFFFu); if (k >= c) { k -= c; pos += 16; m >>= 16; }
     c = __popc(m & 0xFFu);   if (k >= c) { k -= c; pos += 8;  m >>= 8; }
     c = __popc(m & 0xFu);    if (k >= c) { k -= c; pos += 4;  m >>= 4; }
-    c = __popc(m & 0x3u);    if (k >= c) { k -= c; pos += 2;  m >>= 2; }
-    c = m & 1u;              if (k >= c) { pos += 1; }
-    return pos;
+    // the last nibble by table: NIB_SEL(k) holds, 2 bits per nibble value, the position of its k-th set bit
+    constexpr uint32_t S0 = nib_sel(0), S1 = nib_sel(1), S2 = nib_sel(2), S3 = nib_sel(3);
+    uint32_t tab;   // S[k] by three selects (written as selp: the compiler turns the ternary chain into a jump table)
+    asm("{\n\t.reg .pred p1, p2, p3;\n\tsetp.eq.s32 p1, %1, 1;\n\tsetp.eq.s32 p2, %1, 2;\n\tsetp.eq.s32 p3, %1, 3;\n\t"
+        "selp.u32 %0, %3, %2, p1;\n\tselp.u32 %0, %4, %0, p2;\n\tselp.u32 %0, %5, %0, p3;\n\t}"
+        : "=&r"(tab) : "r"(k), "n"(S0), "n"(S1), "n"(S2), "n"(S3));
+    return pos + (int)((tab >> (2u * (m & 0xFu))) & 3u);
 }
 // k-th legal action in ascending action-index order; k < legal_count(L)
 __device__ __forceinline__ int kth_action(const Legal& L, int k) {
@@ -664,13 +677,15 @@ __device__ __forceinline__ bool playout_step(State& s, const NbrLut* lut, RandTa
     }
     if (ph > HZ_PHASE_PLACE3) return false;
     uint32_t hand = hand_of(s);
-    Board b;
-#pragma unroll
-    for (int k = 0; k < 9; k++) b.p[k] = s.w[9 * P + k];
-    const Tops t = tops_of(b);
+    const uint32_t* b = &s.w[9 * P];
+    struct { uint32_t occ0, occ1, occ2; } t = {b[0] | b[1] | b[2], b[3] | b[4] | b[5], b[6] | b[7] | b[8]};
     const uint32_t empty = ~t.occ0 & VALID;                            // :173
-    const uint32_t x1 = top_wood(t) & ~t.occ2, x3 = top_stone(t) & ~t.occ2;                     // :183, :186
-    const uint32_t x4 = (top_wood(t) | top_stone(t) | top_building(t)) & ~t.occ1;               // :190-192
+    // Stacking only ever looks at tops below level 3: where occ2 is clear the top tile is the level-1 tile if there is one,
+    // else the level-0 tile, so the code bits of the top need two levels (tops_of() merges all three), and a height-1 top
+    // is the level-0 code itself.
+    const uint32_t T0 = b[3] | (b[0] & ~t.occ1), T1 = b[4] | (b[1] & ~t.occ1), T2 = b[5] | (b[2] & ~t.occ1);
+    const uint32_t x1 = T0 & T1 & ~T2 & ~t.occ2, x3 = ~T0 & ~T1 & T2 & ~t.occ2;                 // wood / stone top, h <= 2: :183, :186
+    const uint32_t x4 = ((b[0] & b[1] & ~b[2]) | (~b[1] & b[2])) & ~t.occ1;                     // wood, stone or building at h == 1: :190-192
     const uint32_t m0 = (hand & 0x003) ? empty : 0, m1 = (hand & 0x00C) ? (empty | x1) : 0, m2 = (hand & 0x030) ? empty : 0;
     const uint32_t m3 = (hand & 0x0C0) ? (empty | x3) : 0, m4 = (hand & 0x300) ? (empty | x4) : 0, m5 = (hand & 0xC00) ? empty : 0;
     const int c0 = __popc(m0), c1 = c0 + __popc(m1), c2 = c1 + __popc(m2), c3 = c2 + __popc(m3), c4 = c3 + __popc(m4);
