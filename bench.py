@@ -198,7 +198,10 @@ def headline_roofline(n_games, steps_per_launch, launch_s, clocks, pk, pk_src, a
                             "at constant latency.  The round-1 kernel executed 338 thread instructions per engine step at frac 0.46 "
                             "(95 us per wave); thread_inst_per_engine_step and the launch time say what this build does (DESIGN.md §8)",
             "ncu": {"duration_us": m.get("gpu__time_duration.sum", 0) / 1e3, "issue_active_pct": m.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                    "warps_active_pct": m.get("sm__warps_active.avg.pct_of_peak_sustained_active"), "source": "profiles/r02_playout_counters.json"},
+                    "warps_active_pct": m.get("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                    "alu_pipe_pct": m.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                    "fma_pipe_pct": m.get("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                    "source": "profiles/r02_playout_counters.json"},
             "note": "achieved = warp instructions per launch (ncu, same sources by sha256) / CUDA-event launch time measured in this run",
             "hbm_algorithmic": hbm}
 

@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 CS=harmonies_alphazero_b200/csrc
-M=smsp__inst_executed.sum,smsp__thread_inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__cycles_elapsed.max,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__cycles_active.avg
+M=sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,smsp__thread_inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__cycles_elapsed.max,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__cycles_active.avg
 python profiles/playout_case.py > gpurun_out/playout_plain.log 2>&1 &&
 ncu --metrics $M --clock-control none -k regex:k_playout -s 2 -c 2 --csv --log-file gpurun_out/r02_playout_counters.csv python profiles/playout_case.py > gpurun_out/playout_ncu.log 2>&1
 python profiles/counters_to_json.py gpurun_out/r02_playout_counters.csv gpurun_out/r02_playout_counters.json k_playout $CS/hz_engine.cu $CS/hz_core.cuh $CS/hz_tables.inc > gpurun_out/playout_counters.log 2>&1

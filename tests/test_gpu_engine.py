@@ -233,6 +233,27 @@ def test_fused_playout_equals_unfused_and_oracle(hb, oracle):
     assert torch.equal(st2, st3)
 
 
+def test_fused_playout_from_mixed_mid_game_states(hb, oracle):
+    """neighbouring lanes at different depths: every warp holds both players and all four phases, so the fused
+    kernel's per-step branch on the player (playout_step<P>) runs diverged; results must still equal the oracle's"""
+    n, groups = 6144, 48
+    st = hb.init_states(n, seed=4711)
+    per = n // groups
+    for d in range(groups):
+        if d:
+            hb.playout(st[d * per:(d + 1) * per], max_steps=d)          # group d is d actions into its game
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(5)).to(st.device)
+    mixed = st[perm].contiguous()
+    meta = host(mixed)[:, 22] >> 24
+    assert len(set((meta[:32] & 1).tolist())) == 2 and len(set(((meta[:32] >> 1) & 7).tolist())) >= 3
+    init = host(mixed).copy()
+    steps, total = hb.playout(mixed)
+    ref, rsteps, rtotal = oracle.playout(init, n_threads=8)
+    assert np.array_equal(host(mixed), ref)
+    assert np.array_equal(steps.cpu().numpy().astype(np.uint32), rsteps)
+    assert int(total.item()) == rtotal
+
+
 def test_host_buffer_api_equals_device_path(hb):
     """HostPlayout.run (pinned host in/out, chunked over streams) == hz_playout on device"""
     n = 10000
