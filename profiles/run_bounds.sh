@@ -8,7 +8,7 @@ HZ_NVCC_EXTRA="-DHZ_DEBUG_BOUNDS" python - <<'PY'
 import os
 from harmonies_alphazero_b200 import build
 build.LIB = os.path.join(build.HERE, "libharmonies_b200_dbg.so")
-print(build.build(force=True))
+print(build.build())   # stale or missing only: build it in the container first, the .so travels
 PY
 {
   echo "== GPU suite on the bounds-checked build (nvcc -DHZ_DEBUG_BOUNDS, $(date -u +%Y-%m-%dT%H:%MZ), $(nvidia-smi --query-gpu=name --format=csv,noheader | head -1))"
