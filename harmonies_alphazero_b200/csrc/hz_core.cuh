@@ -114,6 +114,30 @@ __device__ __forceinline__ void load_state(State& s, const void* base, int64_t i
         s.w[4 * k] = v.x; s.w[4 * k + 1] = v.y; s.w[4 * k + 2] = v.z; s.w[4 * k + 3] = v.w;
     }
 }
+// Warp-cooperative record load for the streaming kernels (k_legal, k_hash): the warp's 32 records (4 KB) arrive as 8 fully
+// coalesced LDG.128 — 512 contiguous bytes = 4 lines per instruction, where the thread-per-record load above touches 32 lines
+// per instruction and is bound by L1 tag lookups, not by HBM — and reach their threads through a swizzled shared-memory
+// tile: chunk c of record r sits at [r][c ^ (r & 7)], which makes both the row-major store and the per-record read
+// conflict-free.  All 32 lanes must call it (lanes past n get zeros); `tile` = 256 uint4 per warp.
+__device__ __forceinline__ void load_state_warp(State& s, const void* base, int64_t g_warp0, int64_t n, uint4* tile) {
+    const int lane = threadIdx.x & 31;
+    const uint4* p = reinterpret_cast<const uint4*>(base) + g_warp0 * 8;
+    const int64_t lim = (n - g_warp0) * 8;                             // 16-byte chunks that exist
+    uint4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = (k * 32 + lane) < lim ? __ldg(p + k * 32 + lane) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int rec = 4 * k + (lane >> 3), c = lane & 7;
+        tile[rec * 8 + (c ^ (rec & 7))] = v[k];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 7; c++) {
+        const uint4 x = tile[lane * 8 + (c ^ (lane & 7))];
+        s.w[4 * c] = x.x; s.w[4 * c + 1] = x.y; s.w[4 * c + 2] = x.z; s.w[4 * c + 3] = x.w;
+    }
+}
 __device__ __forceinline__ void store_state(const State& s, void* base, int64_t idx) {
     uint4* p = reinterpret_cast<uint4*>(base) + idx * 8;
 #pragma unroll

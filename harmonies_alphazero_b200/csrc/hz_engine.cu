@@ -24,14 +24,23 @@ __global__ void __launch_bounds__(TPB) k_init(void* states, int64_t n, const uin
 }
 
 __global__ void __launch_bounds__(TPB) k_legal(const void* states, int64_t n, uint32_t* mask) {
+    __shared__ __align__(16) uint4 tile[TPB / 32][256];
     int64_t g = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    if (g >= n) return;
     State s;
-    load_state(s, states, g);
+    load_state_warp(s, states, g - (threadIdx.x & 31), n, tile[threadIdx.x >> 5]);
     uint32_t out[5];
     legal_words(legal_of(s), out);
+    // the warp's 32 x 5 mask words leave as five coalesced 128-byte stores, through the same tile (stride 5: conflict-free)
+    uint32_t* tw = reinterpret_cast<uint32_t*>(tile[threadIdx.x >> 5]);
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 5; k++) mask[g * 5 + k] = out[k];
+    for (int k = 0; k < 5; k++) tw[lane * 5 + k] = out[k];
+    __syncwarp();
+    const int64_t g0 = g - lane, lim = (n - g0) * 5;
+#pragma unroll
+    for (int k = 0; k < 5; k++)
+        if (k * 32 + lane < lim) mask[g0 * 5 + k * 32 + lane] = tw[k * 32 + lane];
 }
 
 __global__ void __launch_bounds__(TPB) k_apply(void* states, int64_t n, const int16_t* actions,
@@ -159,6 +168,8 @@ __global__ void __launch_bounds__(TPB) k_score(const void* states, int64_t n, in
     }
 }
 
+// (the warp-staged load of k_legal was measured here too: 32.8 us against 29.7 us per 1 M records — the hash has enough
+// arithmetic per record to hide the direct loads, and the staging adds a barrier in front of it)
 __global__ void __launch_bounds__(TPB) k_hash(const void* states, int64_t n, int mode, uint64_t* out) {
     int64_t g = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (g >= n) return;
