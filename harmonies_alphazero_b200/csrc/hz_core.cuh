@@ -207,7 +207,7 @@ struct Legal {
     uint32_t m[6];
     int n_piles;  // choose phase: number of selectable piles (else 0)
 };
-// REL ("mover-relative", fused playout only): words 0..8 always hold the board of the player to
+// REL ("mover-relative", only the fused playout's -DHZ_PLAYOUT_CHECKED comparison path; the default is playout_step<P> below): words 0..8 always hold the board of the player to
 // move and 9..17 the other one; the halves are swapped whenever the player changes, so board
 // access needs no per-word select on the player bit.  swap_boards() converts both ways.
 __device__ __forceinline__ void swap_boards(State& s) {
@@ -687,14 +687,14 @@ __device__ __forceinline__ bool playout_step(State& s, const NbrLut* lut, RandTa
         const int np = n_piles_of(s);
         if (np == 0) return false;
         const int a = (int)__umulhi(rh, (uint32_t)np);
-        Piles P = piles_of(s);
-        uint32_t hand = P.p[0];
+        Piles pl = piles_of(s);
+        uint32_t hand = pl.p[0];
 #pragma unroll
-        for (int j = 1; j < 5; j++) hand = (a == j) ? P.p[j] : hand;
+        for (int j = 1; j < 5; j++) hand = (a == j) ? pl.p[j] : hand;
 #pragma unroll
-        for (int j = 0; j < 4; j++) P.p[j] = (j >= a) ? P.p[j + 1] : P.p[j];
-        P.p[4] = 0;
-        set_piles(s, P, hand, np - 1);
+        for (int j = 0; j < 4; j++) pl.p[j] = (j >= a) ? pl.p[j + 1] : pl.p[j];
+        pl.p[4] = 0;
+        set_piles(s, pl, hand, np - 1);
         set_meta(s, (meta(s) & ~0xEu) | (HZ_PHASE_PLACE1 << 1));
         s.w[HZ_W_MOVES]++;
         return true;
