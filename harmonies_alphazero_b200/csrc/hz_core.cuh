@@ -118,23 +118,26 @@ __device__ __forceinline__ void load_state(State& s, const void* base, int64_t i
 // coalesced LDG.128 — 512 contiguous bytes = 4 lines per instruction, where the thread-per-record load above touches 32 lines
 // per instruction and is bound by L1 tag lookups, not by HBM — and reach their threads through a swizzled shared-memory
 // tile: chunk c of record r sits at [r][c ^ (r & 7)], which makes both the row-major store and the per-record read
-// conflict-free.  All 32 lanes must call it (lanes past n get zeros); `tile` = 256 uint4 per warp.
+// conflict-free.  All 32 lanes must call it (lanes past n get zeros); `tile` = 256 uint4 per warp.  NCH < 8: only the first
+// NCH 16-byte chunks of every record are fetched (the rest of s.w is zero) — a kernel that never looks at words >= 24
+// leaves the record's fourth 32-byte sector in DRAM.
+template <int NCH = 8>
 __device__ __forceinline__ void load_state_warp(State& s, const void* base, int64_t g_warp0, int64_t n, uint4* tile) {
     const int lane = threadIdx.x & 31;
     const uint4* p = reinterpret_cast<const uint4*>(base) + g_warp0 * 8;
     const int64_t lim = (n - g_warp0) * 8;                             // 16-byte chunks that exist
     uint4 v[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = (k * 32 + lane) < lim ? __ldg(p + k * 32 + lane) : make_uint4(0, 0, 0, 0);
+    for (int k = 0; k < 8; k++) v[k] = ((k * 32 + lane) < lim && (lane & 7) < NCH) ? __ldg(p + k * 32 + lane) : make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const int rec = 4 * k + (lane >> 3), c = lane & 7;
-        tile[rec * 8 + (c ^ (rec & 7))] = v[k];
+        if (c < NCH) tile[rec * 8 + (c ^ (rec & 7))] = v[k];
     }
     __syncwarp();
 #pragma unroll
     for (int c = 0; c < 7; c++) {
-        const uint4 x = tile[lane * 8 + (c ^ (lane & 7))];
+        const uint4 x = c < NCH ? tile[lane * 8 + (c ^ (lane & 7))] : make_uint4(0, 0, 0, 0);
         s.w[4 * c] = x.x; s.w[4 * c + 1] = x.y; s.w[4 * c + 2] = x.z; s.w[4 * c + 3] = x.w;
     }
 }

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(TPB) k_legal(const void* states, int64_t n, ui
     __shared__ __align__(16) uint4 tile[TPB / 32][256];
     int64_t g = (int64_t)blockIdx.x * TPB + threadIdx.x;
     State s;
-    load_state_warp(s, states, g - (threadIdx.x & 31), n, tile[threadIdx.x >> 5]);
+    load_state_warp<6>(s, states, g - (threadIdx.x & 31), n, tile[threadIdx.x >> 5]);   // legal moves read words 0..22 only
     uint32_t out[5];
     legal_words(legal_of(s), out);
     // the warp's 32 x 5 mask words leave as five coalesced 128-byte stores, through the same tile (stride 5: conflict-free)
